@@ -1,0 +1,791 @@
+// hgpu_api.cu -- C ABI of libhercules_gpu.so (include/hercules_gpu.h): solver handle, device
+// data layout, the per-step call sequence of solver_run (psolve.c:4265-4319) and the halo
+// exchange that replaces schedule_senddata (psolve.c:4945-5079).
+//
+// There is no CPU fallback anywhere in this file: every entry point either runs CUDA kernels
+// or fails with a negative HGPU_E* code.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "hgpu_internal.h"
+#include "hgpu_kernels.cuh"
+
+using namespace hgpu;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(HGPU_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+// ---- minimal NCCL binding, resolved at run time so single-GPU use needs no libnccl ----------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl()
+{
+    if (g_nccl.h) return HGPU_OK;
+    const char *names[] = {getenv("HGPU_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    void *h = nullptr;
+    for (const char *n : names) {
+        if (n && *n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    }
+    if (!h) return fail(HGPU_ECOMM, "cannot dlopen libnccl (set HGPU_NCCL_LIB): %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(ncclUniqueId *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(ncclComm_t *, int, ncclUniqueId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(ncclComm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.Send = (int (*)(const void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclSend");
+    g_nccl.Recv = (int (*)(void *, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(h, "ncclRecv");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.Send || !g_nccl.Recv ||
+        !g_nccl.GroupStart || !g_nccl.GroupEnd)
+        return fail(HGPU_ECOMM, "libnccl lacks a required symbol");
+    g_nccl.h = h;
+    return HGPU_OK;
+}
+
+#define NK(call)                                                                       \
+    do {                                                                               \
+        int r_ = (call);                                                               \
+        if (r_ != ncclSuccess)                                                         \
+            return fail(HGPU_ECOMM, "%s failed: %s", #call,                            \
+                        g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?");      \
+    } while (0)
+
+// One side of a schedule (c-list or s-list) on the device.
+struct MsgList {
+    std::vector<int32_t> peer, nodes, off;   // off = prefix sum of nodes
+    int32_t total = 0;
+    int32_t *d_map = nullptr;                // concatenated mapping[]
+    double *d_send = nullptr, *d_recv = nullptr;   // [total][3] staging
+};
+
+enum ForceState { F_CLEAN = 0, F_PENDING = 1, F_MATERIALIZED = 2, F_FUSED_DONE = 3 };
+
+struct hgpu_solver {
+    hgpu_params_t P{};
+    int32_t E = 0, N = 0, D = 0;
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    // node arrays
+    double *u[3] = {nullptr, nullptr, nullptr};
+    int i1 = 0, i2 = 1, i3 = 2;          // which buffer plays tm1 / tm2 / tm3
+    double *force = nullptr;
+    double *mass = nullptr, *m2 = nullptr, *m1 = nullptr;
+    uint8_t *ncls = nullptr;
+    // element arrays
+    double *etab = nullptr;
+    double *Kd = nullptr;
+    // tiles
+    TilePlan plan;
+    int32_t *t_elem_off = nullptr, *t_elem_id = nullptr, *t_halo_off = nullptr, *t_halo_id = nullptr;
+    uint4 *t_elem_slot = nullptr;
+    int smem_u2 = 0, smem_nou2 = 0, block = 256;
+    // special-node path
+    int32_t nS = 0; int32_t *d_slist = nullptr;
+    int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
+    double *d_Fall = nullptr; size_t Fall_steps = 0;
+    int32_t *d_dnode = nullptr;
+    int32_t nA = 0; int32_t *d_anchor_id = nullptr, *d_anchor_off = nullptr, *d_anchor_dn = nullptr,
+            *d_anchor_deps = nullptr;
+    // halo
+    MsgList dn_c, dn_s, an_c, an_s;
+    ncclComm_t comm = nullptr;
+    // step state
+    bool want_stiff = false, want_damp = false;
+    ForceState fstate = F_CLEAN;
+    int64_t n_regular = 0, n_special = 0, device_bytes = 0;
+    hgpu_timers_t tm{};
+    // scratch for fetch
+    int32_t *d_fetch_ids = nullptr; double *d_fetch_out = nullptr; int32_t fetch_cap = 0;
+};
+
+template <typename T>
+static int dalloc(hgpu_solver *s, T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess)
+        return fail(HGPU_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    s->device_bytes += (int64_t)(n * sizeof(T));
+    return HGPU_OK;
+}
+
+template <typename T>
+static int upload(hgpu_solver *s, T **p, const T *src, size_t n)
+{
+    int rc = dalloc(s, p, n);
+    if (rc) return rc;
+    if (n) CK(cudaMemcpy(*p, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return HGPU_OK;
+}
+
+static int upload_msglist(hgpu_solver *s, const hgpu_msglist_t &in, MsgList &out, const char *what)
+{
+    out.off.assign(1, 0);
+    for (int32_t i = 0; i < in.count; i++) {
+        if (in.peer[i] < 0 || in.peer[i] >= s->P.nranks || in.peer[i] == s->P.rank)
+            return fail(HGPU_EINVAL, "%s: bad peer rank %d", what, in.peer[i]);
+        out.peer.push_back(in.peer[i]);
+        out.nodes.push_back(in.nodes[i]);
+        out.off.push_back(out.off.back() + in.nodes[i]);
+    }
+    out.total = out.off.back();
+    for (int32_t i = 0; i < out.total; i++)
+        if (in.mapping[i] < 0 || in.mapping[i] >= s->N)
+            return fail(HGPU_EINVAL, "%s: mapping entry out of range", what);
+    int rc;
+    if ((rc = upload(s, &out.d_map, in.mapping, (size_t)out.total))) return rc;
+    if ((rc = dalloc(s, &out.d_send, 3 * (size_t)out.total))) return rc;
+    if ((rc = dalloc(s, &out.d_recv, 3 * (size_t)out.total))) return rc;
+    return HGPU_OK;
+}
+
+extern "C" const char *hgpu_last_error(void) { return g_err.c_str(); }
+extern "C" int hgpu_abi_version(void) { return HGPU_ABI_VERSION; }
+
+extern "C" int hgpu_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(HGPU_ENODEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgpu_params_t *params)
+{
+    if (!out || !mesh || !params) return fail(HGPU_EINVAL, "hgpu_init: null argument");
+    *out = nullptr;
+    if (mesh->lenum < 0 || mesh->nharbored <= 0 || mesh->ldnnum < 0)
+        return fail(HGPU_EINVAL, "hgpu_init: bad mesh counts");
+    if (!mesh->elem_lnid || !mesh->eTable || !mesh->nTable)
+        return fail(HGPU_EINVAL, "hgpu_init: elem_lnid, eTable and nTable are required");
+    if (params->damping < 0 || params->damping > 3 || params->stiffness < 0 || params->stiffness > 1)
+        return fail(HGPU_EINVAL, "hgpu_init: bad damping/stiffness type");
+    if (params->damping == HGPU_DAMPING_BKT)
+        return fail(HGPU_EINVAL, "hgpu_init: BKT damping is not available in this build");
+    if (params->stiffness == HGPU_STIFFNESS_CONVENTIONAL && (!mesh->K1 || !mesh->K2))
+        return fail(HGPU_EINVAL, "hgpu_init: conventional stiffness needs K1 and K2");
+    if (params->nranks < 1 || params->rank < 0 || params->rank >= params->nranks)
+        return fail(HGPU_EINVAL, "hgpu_init: bad rank/nranks");
+    if (params->nloaded < 0 || (params->nloaded > 0 && !params->loaded_lnid))
+        return fail(HGPU_EINVAL, "hgpu_init: bad loaded-node list");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev <= 0)
+        return fail(HGPU_ENODEVICE, "no CUDA device: %s (this library has no CPU path)",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count is 0");
+
+    hgpu_solver *s = new hgpu_solver();
+    s->P = *params;
+    s->P.loaded_lnid = nullptr;
+    s->E = mesh->lenum; s->N = mesh->nharbored; s->D = mesh->ldnnum;
+    s->dev = params->device >= 0 ? params->device : params->rank % ndev;
+    if (s->dev >= ndev) { delete s; return fail(HGPU_ENODEVICE, "device %d not present", params->device); }
+    int rc = HGPU_OK;
+#define TRY(x) do { rc = (x); if (rc) { hgpu_finalize(s); return rc; } } while (0)
+#define TRYCU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { hgpu_finalize(s); \
+        return fail(HGPU_ECUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); } } while (0)
+    TRYCU(cudaSetDevice(s->dev));
+    cudaDeviceProp prop;
+    TRYCU(cudaGetDeviceProperties(&prop, s->dev));
+    if (prop.major < 10) {
+        hgpu_finalize(s);
+        return fail(HGPU_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only",
+                    s->dev, prop.major, prop.minor);
+    }
+    TRYCU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+
+    const int32_t E = s->E, N = s->N, D = s->D;
+    const size_t n3 = 3 * (size_t)N;
+
+    // ---- node arrays: three rotating displacement buffers, force, split n_t -----------------
+    for (int b = 0; b < 3; b++) {
+        TRY(dalloc(s, &s->u[b], n3));
+        TRYCU(cudaMemset(s->u[b], 0, n3 * sizeof(double)));
+    }
+    TRY(dalloc(s, &s->force, n3));
+    TRYCU(cudaMemset(s->force, 0, n3 * sizeof(double)));
+    {
+        std::vector<double> mass((size_t)N), m2(n3), m1(n3);
+        for (int32_t n = 0; n < N; n++) {
+            const double *np = mesh->nTable + 7 * (size_t)n;
+            mass[n] = np[0];
+            for (int c = 0; c < 3; c++) { m2[3 * (size_t)n + c] = np[1 + c]; m1[3 * (size_t)n + c] = np[4 + c]; }
+        }
+        TRY(upload(s, &s->mass, mass.data(), (size_t)N));
+        TRY(upload(s, &s->m2, m2.data(), n3));
+        TRY(upload(s, &s->m1, m1.data(), n3));
+    }
+    TRY(upload(s, &s->etab, mesh->eTable, 4 * (size_t)E));
+    if (params->stiffness == HGPU_STIFFNESS_CONVENTIONAL) {
+        // [8][8][3][3] block form -> two dense 24x24 row-major matrices
+        std::vector<double> kd(2 * 576);
+        for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) for (int k = 0; k < 3; k++) for (int l = 0; l < 3; l++) {
+            kd[(size_t)24 * (3 * i + k) + 3 * j + l] = mesh->K1[9 * (8 * i + j) + 3 * k + l];
+            kd[576 + (size_t)24 * (3 * i + k) + 3 * j + l] = mesh->K2[9 * (8 * i + j) + 3 * k + l];
+        }
+        TRY(upload(s, &s->Kd, kd.data(), kd.size()));
+    }
+
+    // ---- hanging nodes ------------------------------------------------------------------------
+    DanglingPlan dp;
+    std::string err;
+    if (D > 0 && !mesh->dnode) { hgpu_finalize(s); return fail(HGPU_EINVAL, "ldnnum > 0 but dnode is null"); }
+    if (!build_dangling_plan(N, D, mesh->dnode, dp, err)) { hgpu_finalize(s); return fail(HGPU_EINVAL, "%s", err.c_str()); }
+    TRY(upload(s, &s->d_dnode, mesh->dnode, 6 * (size_t)D));
+    s->nA = (int32_t)dp.anchor_id.size();
+    TRY(upload(s, &s->d_anchor_id, dp.anchor_id.data(), dp.anchor_id.size()));
+    TRY(upload(s, &s->d_anchor_off, dp.anchor_off.data(), dp.anchor_off.size()));
+    TRY(upload(s, &s->d_anchor_dn, dp.anchor_dn.data(), dp.anchor_dn.size()));
+    TRY(upload(s, &s->d_anchor_deps, dp.anchor_deps.data(), dp.anchor_deps.size()));
+
+    // ---- halo schedules ------------------------------------------------------------------------
+    TRY(upload_msglist(s, mesh->dn_c, s->dn_c, "dn_sched c-list"));
+    TRY(upload_msglist(s, mesh->dn_s, s->dn_s, "dn_sched s-list"));
+    TRY(upload_msglist(s, mesh->an_c, s->an_c, "an_sched c-list"));
+    TRY(upload_msglist(s, mesh->an_s, s->an_s, "an_sched s-list"));
+
+    // ---- source ----------------------------------------------------------------------------------
+    for (int32_t i = 0; i < params->nloaded; i++)
+        if (params->loaded_lnid[i] < 0 || params->loaded_lnid[i] >= N) {
+            hgpu_finalize(s); return fail(HGPU_EINVAL, "loaded node id out of range");
+        }
+    TRY(upload(s, &s->d_loaded, params->loaded_lnid, (size_t)params->nloaded));
+    TRY(dalloc(s, &s->d_F, 3 * (size_t)params->nloaded));
+    TRYCU(cudaMallocHost((void **)&s->h_F, std::max<size_t>(1, 3 * (size_t)params->nloaded) * sizeof(double)));
+
+    // ---- node classes -----------------------------------------------------------------------------
+    {
+        std::vector<uint8_t> cls((size_t)N, NODE_REGULAR);
+        if (params->flags & HGPU_FLAG_NO_FUSE) std::fill(cls.begin(), cls.end(), (uint8_t)NODE_SPECIAL);
+        for (int32_t i = 0; i < params->nloaded; i++) cls[params->loaded_lnid[i]] = NODE_SPECIAL;
+        for (int32_t d = 0; d < D; d++) {
+            const int32_t *dn = mesh->dnode + 6 * (size_t)d;
+            cls[dn[0]] = NODE_SPECIAL;
+            for (int a = 0; a < 4 && dn[2 + a] >= 0; a++) cls[dn[2 + a]] = NODE_SPECIAL;
+        }
+        const hgpu_msglist_t *lists[4] = {&mesh->dn_c, &mesh->dn_s, &mesh->an_c, &mesh->an_s};
+        for (const hgpu_msglist_t *l : lists) {
+            int32_t tot = 0;
+            for (int32_t i = 0; i < l->count; i++) tot += l->nodes[i];
+            for (int32_t i = 0; i < tot; i++) cls[l->mapping[i]] = NODE_SPECIAL;
+        }
+        std::vector<int32_t> slist;
+        for (int32_t n = 0; n < N; n++) if (cls[n] == NODE_SPECIAL) slist.push_back(n);
+        s->nS = (int32_t)slist.size();
+        s->n_special = s->nS; s->n_regular = (int64_t)N - s->nS;
+        TRY(upload(s, &s->ncls, cls.data(), (size_t)N));
+        if (!(params->flags & HGPU_FLAG_NO_FUSE)) TRY(upload(s, &s->d_slist, slist.data(), slist.size()));
+    }
+
+    // ---- tiles ------------------------------------------------------------------------------------
+    {
+        int max_smem = 0;
+        TRYCU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev));
+        int32_t tn = params->tile_nodes > 0 ? params->tile_nodes : 512;
+        const char *env = getenv("HGPU_TILE_NODES");
+        if (params->tile_nodes <= 0 && env && atoi(env) > 0) tn = atoi(env);
+        tn &= ~1;
+        bool ok = false;
+        for (; tn >= 32; tn /= 2) {
+            // worst case: both displacement buffers staged; two CTAs per SM wanted
+            int32_t max_slots = (int32_t)std::min<long long>(65535, ((long long)max_smem / 8 - 3LL * tn) / 6);
+            if (max_slots <= tn) continue;
+            if (build_tile_plan(E, N, mesh->elem_lnid, tn, max_slots, s->plan, err)) { ok = true; break; }
+            if (params->tile_nodes > 0) break;
+        }
+        if (!ok) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str()); }
+        const TilePlan &pl = s->plan;
+        TRY(upload(s, &s->t_elem_off, pl.elem_off.data(), pl.elem_off.size()));
+        TRY(upload(s, &s->t_elem_id, pl.elem_id.data(), pl.elem_id.size()));
+        TRY(upload(s, (uint16_t **)&s->t_elem_slot, pl.elem_slot.data(), pl.elem_slot.size()));
+        TRY(upload(s, &s->t_halo_off, pl.halo_off.data(), pl.halo_off.size()));
+        TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
+        s->smem_u2 = (6 * pl.max_tile_nodes + 3 * pl.tile_nodes) * (int)sizeof(double);
+        s->smem_nou2 = (3 * pl.max_tile_nodes + 3 * pl.tile_nodes) * (int)sizeof(double);
+        const char *benv = getenv("HGPU_BLOCK");
+        if (benv && atoi(benv) >= 64 && atoi(benv) <= 256) s->block = atoi(benv) & ~31;
+        TRYCU(cudaFuncSetAttribute(tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        TRYCU(cudaFuncSetAttribute(tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
+        TRYCU(cudaFuncSetAttribute(tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        TRYCU(cudaFuncSetAttribute(tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
+    }
+    TRYCU(cudaStreamSynchronize(s->stream));
+    TRYCU(cudaDeviceSynchronize());
+#undef TRY
+#undef TRYCU
+    *out = s;
+    return HGPU_OK;
+}
+
+template <typename T>
+static void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
+
+static void free_msglist(MsgList &m) { dfree(m.d_map); dfree(m.d_send); dfree(m.d_recv); }
+
+extern "C" int hgpu_finalize(hgpu_solver_t *s)
+{
+    if (!s) return HGPU_OK;
+    cudaSetDevice(s->dev);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (int b = 0; b < 3; b++) dfree(s->u[b]);
+    dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->ncls); dfree(s->etab); dfree(s->Kd);
+    dfree(s->t_elem_off); dfree(s->t_elem_id); dfree(s->t_elem_slot); dfree(s->t_halo_off); dfree(s->t_halo_id);
+    dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
+    dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
+    dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
+    free_msglist(s->dn_c); free_msglist(s->dn_s); free_msglist(s->an_c); free_msglist(s->an_s);
+    if (s->h_F) cudaFreeHost(s->h_F);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+    return HGPU_OK;
+}
+
+// ---- force evaluation ---------------------------------------------------------------------------
+
+// Launch the tile kernel for whatever force terms were requested since the last update.
+// fuse = advance REGULAR nodes in the same launch (their force never reaches HBM).
+static int launch_tiles(hgpu_solver *s, bool fuse)
+{
+    const bool stiff = s->want_stiff, damp = s->want_damp;
+    const bool rayleigh = s->P.damping == HGPU_DAMPING_RAYLEIGH;
+    // MASS damping has b = 0, hence c3 = c4 = 0 (psolve.c:5866-5867): damping_addforce adds nothing
+    const bool need_u2 = damp && rayleigh;
+    const bool any = stiff || need_u2;
+    if (!any && !fuse) return HGPU_OK;
+    TileArgs A{};
+    A.u1 = s->u[s->i1]; A.u2 = s->u[s->i2]; A.unext = s->u[s->i3]; A.force = s->force;
+    A.mass = s->mass; A.m2 = s->m2; A.m1 = s->m1; A.ncls = s->ncls; A.etab = s->etab; A.Kd = s->Kd;
+    A.elem_off = s->t_elem_off; A.elem_id = s->t_elem_id; A.elem_slot = s->t_elem_slot;
+    A.halo_off = s->t_halo_off; A.halo_id = s->t_halo_id;
+    A.N = s->N; A.tile_nodes = s->plan.tile_nodes; A.ntiles = s->plan.ntiles; A.tile_begin = 0;
+    A.stage_nodes = s->plan.max_tile_nodes;
+    A.s_u1 = stiff ? 1.0 : 0.0;
+    A.s_du = need_u2 ? 1.0 : 0.0;
+    A.fuse_update = fuse ? 1 : 0;
+    const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
+    const int T = s->plan.ntiles;
+    if (T > 0) {
+        // a damping-only launch runs the u2 variant with s_u1 = 0; a launch with no term at all
+        // (MASS damping alone) is a fused update whose element force is identically zero
+        if (need_u2) {
+            if (dense) tile_kernel<true, true><<<T, s->block, s->smem_u2, s->stream>>>(A);
+            else       tile_kernel<true, false><<<T, s->block, s->smem_u2, s->stream>>>(A);
+        } else {
+            if (dense) tile_kernel<false, true><<<T, s->block, s->smem_nou2, s->stream>>>(A);
+            else       tile_kernel<false, false><<<T, s->block, s->smem_nou2, s->stream>>>(A);
+        }
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    s->want_stiff = s->want_damp = false;
+    return HGPU_OK;
+}
+
+// Make force[] hold the sum of every requested term for EVERY node (unfused semantics).
+static int materialize_forces(hgpu_solver *s)
+{
+    if (s->fstate == F_PENDING) {
+        // temporarily treat all nodes as SPECIAL: run without the fused update
+        int rc = launch_tiles(s, false);
+        if (rc) return rc;
+        s->fstate = F_MATERIALIZED;
+    }
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_step_begin(hgpu_solver_t *s, int32_t step)
+{
+    (void)step;
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (s->fstate == F_PENDING || s->fstate == F_FUSED_DONE)
+        return fail(HGPU_ESTATE, "hgpu_step_begin: previous step's forces were never consumed by hgpu_update");
+    std::swap(s->i1, s->i2);   // psolve.c:4271-4273
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_force_source(hgpu_solver_t *s, const double *F)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    const int n = s->P.nloaded;
+    if (n == 0) return HGPU_OK;
+    if (!F) return fail(HGPU_EINVAL, "hgpu_force_source: F is null but nloaded > 0");
+    if (s->fstate != F_CLEAN)
+        return fail(HGPU_ESTATE, "hgpu_force_source must precede the element forces (assignment, psolve.c:5921)");
+    CK(cudaSetDevice(s->dev));
+    // the pinned staging buffer may still be in flight from the previous step
+    CK(cudaStreamSynchronize(s->stream));
+    memcpy(s->h_F, F, 3 * (size_t)n * sizeof(double));
+    CK(cudaMemcpyAsync(s->d_F, s->h_F, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(n, s->d_loaded, s->d_F, s->P.dt2, s->force);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_force_stiffness(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (s->P.damping == HGPU_DAMPING_BKT) return HGPU_OK;   // psolve.c:3969
+    if (s->fstate == F_FUSED_DONE) return fail(HGPU_ESTATE, "forces already consumed for this step");
+    CK(cudaSetDevice(s->dev));
+    if (s->fstate == F_MATERIALIZED) {
+        s->want_stiff = true;
+        return launch_tiles(s, false);
+    }
+    s->want_stiff = true;
+    s->fstate = F_PENDING;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_force_damping(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (s->P.damping == HGPU_DAMPING_NONE) return HGPU_OK;   // psolve.c:3999-4000
+    if (s->fstate == F_FUSED_DONE) return fail(HGPU_ESTATE, "forces already consumed for this step");
+    CK(cudaSetDevice(s->dev));
+    if (s->fstate == F_MATERIALIZED) {
+        s->want_damp = true;
+        return launch_tiles(s, false);
+    }
+    s->want_damp = true;
+    s->fstate = F_PENDING;
+    return HGPU_OK;
+}
+
+// schedule_senddata (psolve.c:4945-5079) for one schedule and one direction.
+//   contribution: c-list packs v -> owner; owner's s-list unpacks with += (one messenger after another)
+//   sharing     : s-list packs v -> sharers; c-list unpacks with =
+static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool contribution)
+{
+    if (s->P.nranks == 1 || (c.total == 0 && sl.total == 0)) return HGPU_OK;
+    if (!s->comm) return fail(HGPU_ECOMM, "halo exchange needs hgpu_comm_init first");
+    MsgList &snd = contribution ? c : sl;
+    MsgList &rcv = contribution ? sl : c;
+    if (snd.total) {
+        pack_kernel<<<grid_for(3LL * snd.total, 256), 256, 0, s->stream>>>(snd.total, snd.d_map, v, snd.d_send);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    NK(g_nccl.GroupStart());
+    for (size_t i = 0; i < rcv.peer.size(); i++)
+        NK(g_nccl.Recv(rcv.d_recv + 3 * (size_t)rcv.off[i], 3 * (size_t)rcv.nodes[i], ncclFloat64, rcv.peer[i], s->comm, s->stream));
+    for (size_t i = 0; i < snd.peer.size(); i++)
+        NK(g_nccl.Send(snd.d_send + 3 * (size_t)snd.off[i], 3 * (size_t)snd.nodes[i], ncclFloat64, snd.peer[i], s->comm, s->stream));
+    NK(g_nccl.GroupEnd());
+    if (contribution) {
+        // messengers applied one after another, as the reference's unpack loop does
+        for (size_t i = 0; i < rcv.peer.size(); i++) {
+            if (!rcv.nodes[i]) continue;
+            unpack_kernel<<<grid_for(3LL * rcv.nodes[i], 256), 256, 0, s->stream>>>(
+                rcv.nodes[i], rcv.d_map + rcv.off[i], rcv.d_recv + 3 * (size_t)rcv.off[i], v, 1);
+            CK(cudaGetLastError());
+            s->tm.launches++;
+        }
+    } else if (rcv.total) {
+        // a harbored node has exactly one owner, so the overwrite lists are disjoint
+        unpack_kernel<<<grid_for(3LL * rcv.total, 256), 256, 0, s->stream>>>(rcv.total, rcv.d_map, rcv.d_recv, v, 0);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    int rc;
+    if (s->fstate == F_PENDING) {
+        const bool fuse = !(s->P.flags & HGPU_FLAG_NO_FUSE);
+        if ((rc = launch_tiles(s, fuse))) return rc;
+        s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
+    }
+    // phase 8: dangling-node forces to their owners
+    if ((rc = exchange(s, s->dn_c, s->dn_s, s->force, true))) return rc;
+    // phase 9: owned dangling nodes hand force/deps to their anchors
+    if (s->nA > 0) {
+        adjust_dist_kernel<<<grid_for(3LL * s->nA, 128), 128, 0, s->stream>>>(
+            s->nA, s->d_anchor_id, s->d_anchor_off, s->d_anchor_dn, s->d_anchor_deps, s->force);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    // phase 10: anchored-node forces to their owners
+    if ((rc = exchange(s, s->an_c, s->an_s, s->force, true))) return rc;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_update(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    int rc;
+    if (s->fstate == F_PENDING) {
+        // hgpu_force_exchange was skipped (legal on a conforming single-rank mesh)
+        const bool fuse = !(s->P.flags & HGPU_FLAG_NO_FUSE);
+        if ((rc = launch_tiles(s, fuse))) return rc;
+        s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
+    }
+    double *u1 = s->u[s->i1], *u2 = s->u[s->i2], *un = s->u[s->i3];
+    if (s->fstate == F_FUSED_DONE) {
+        if (s->nS > 0) {
+            update_list_kernel<<<grid_for(3LL * s->nS, 256), 256, 0, s->stream>>>(
+                s->nS, s->d_slist, u1, u2, un, s->force, s->mass, s->m2, s->m1);
+            CK(cudaGetLastError());
+            s->tm.launches++;
+        }
+    } else {
+        // F_MATERIALIZED, or F_CLEAN (a step with no element force at all): every node from force[]
+        const long long n3 = 3LL * s->N;
+        int grid = (int)std::min<long long>((n3 + 255) / 256, 148LL * 16);
+        update_all_kernel<<<grid, 256, 0, s->stream>>>(n3, u1, u2, un, s->force, s->mass, s->m2, s->m1);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    // roles after the update: tm1 unchanged, tm2 = new displacement, tm3 = old tm2 (psolve.c:4094-4106)
+    const int old2 = s->i2;
+    s->i2 = s->i3;
+    s->i3 = old2;
+    s->fstate = F_CLEAN;
+    s->tm.steps++;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_disp_exchange(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    int rc;
+    double *tm2 = s->u[s->i2];
+    // phase 13: owners publish anchored-node displacements
+    if ((rc = exchange(s, s->an_c, s->an_s, tm2, false))) return rc;
+    // phase 14: dangling nodes interpolate from their anchors
+    if (s->D > 0) {
+        adjust_asgn_kernel<<<grid_for(3LL * s->D, 128), 128, 0, s->stream>>>(s->D, s->d_dnode, tm2);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    // phase 15: owners publish dangling-node displacements
+    if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false))) return rc;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_step(hgpu_solver_t *s, int32_t step, const double *F)
+{
+    int rc;
+    if ((rc = hgpu_step_begin(s, step))) return rc;
+    if ((rc = hgpu_force_source(s, F))) return rc;
+    if ((rc = hgpu_force_stiffness(s))) return rc;
+    if ((rc = hgpu_force_damping(s))) return rc;
+    if ((rc = hgpu_force_exchange(s))) return rc;
+    if ((rc = hgpu_update(s))) return rc;
+    return hgpu_disp_exchange(s);
+}
+
+extern "C" int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (nsteps < 0) return fail(HGPU_EINVAL, "hgpu_run: negative step count");
+    const int n = s->P.nloaded;
+    if (n > 0 && !F_all) return fail(HGPU_EINVAL, "hgpu_run: F_all is null but nloaded > 0");
+    CK(cudaSetDevice(s->dev));
+    if (n > 0) {
+        // whole source history resident in HBM: no per-step host traffic
+        if (s->Fall_steps < (size_t)nsteps) {
+            dfree(s->d_Fall);
+            int rc = dalloc(s, &s->d_Fall, 3 * (size_t)n * (size_t)nsteps);
+            if (rc) return rc;
+            s->Fall_steps = (size_t)nsteps;
+        }
+        CK(cudaMemcpyAsync(s->d_Fall, F_all, 3 * (size_t)n * (size_t)nsteps * sizeof(double),
+                           cudaMemcpyHostToDevice, s->stream));
+    }
+    for (int32_t k = 0; k < nsteps; k++) {
+        int rc;
+        if ((rc = hgpu_step_begin(s, step0 + k))) return rc;
+        if (n > 0) {
+            source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(
+                n, s->d_loaded, s->d_Fall + 3 * (size_t)n * (size_t)k, s->P.dt2, s->force);
+            CK(cudaGetLastError());
+            s->tm.launches++;
+        }
+        if ((rc = hgpu_force_stiffness(s))) return rc;
+        if ((rc = hgpu_force_damping(s))) return rc;
+        if ((rc = hgpu_force_exchange(s))) return rc;
+        if ((rc = hgpu_update(s))) return rc;
+        if ((rc = hgpu_disp_exchange(s))) return rc;
+    }
+    return HGPU_OK;
+}
+
+// ---- taps ---------------------------------------------------------------------------------------
+
+static int resolve(hgpu_solver *s, int32_t which, double **p, size_t *count)
+{
+    *count = 3 * (size_t)s->N;
+    switch (which) {
+    case HGPU_TM1: *p = s->u[s->i1]; return HGPU_OK;
+    case HGPU_TM2: *p = s->u[s->i2]; return HGPU_OK;
+    case HGPU_TM3: *p = s->u[s->i3]; return HGPU_OK;
+    case HGPU_FORCE: {
+        int rc = materialize_forces(s);
+        if (rc) return rc;
+        if (s->fstate == F_FUSED_DONE)
+            return fail(HGPU_ESTATE, "force of REGULAR nodes is not kept by the fused step; "
+                                     "read it before hgpu_force_exchange or use HGPU_FLAG_NO_FUSE");
+        *p = s->force; return HGPU_OK;
+    }
+    default: return fail(HGPU_EINVAL, "unknown array selector %d", which);
+    }
+}
+
+extern "C" int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out)
+{
+    if (!s || !out) return fail(HGPU_EINVAL, "null argument");
+    CK(cudaSetDevice(s->dev));
+    double *p; size_t cnt;
+    int rc = resolve(s, which, &p, &cnt);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(out, p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in)
+{
+    if (!s || !in) return fail(HGPU_EINVAL, "null argument");
+    CK(cudaSetDevice(s->dev));
+    double *p; size_t cnt;
+    int rc = resolve(s, which, &p, &cnt);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(p, in, cnt * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *lnid, int32_t n, double *out)
+{
+    if (!s || (n > 0 && (!lnid || !out)) || n < 0) return fail(HGPU_EINVAL, "bad argument");
+    if (n == 0) return HGPU_OK;
+    CK(cudaSetDevice(s->dev));
+    double *p; size_t cnt;
+    int rc = resolve(s, which, &p, &cnt);
+    if (rc) return rc;
+    for (int32_t i = 0; i < n; i++)
+        if (lnid[i] < 0 || lnid[i] >= s->N) return fail(HGPU_EINVAL, "node id out of range");
+    if (n > s->fetch_cap) {
+        dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
+        if ((rc = dalloc(s, &s->d_fetch_ids, (size_t)n))) return rc;
+        if ((rc = dalloc(s, &s->d_fetch_out, 3 * (size_t)n))) return rc;
+        s->fetch_cap = n;
+    }
+    CK(cudaMemcpyAsync(s->d_fetch_ids, lnid, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    gather_nodes_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(n, s->d_fetch_ids, p, s->d_fetch_out);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    CK(cudaMemcpyAsync(out, s->d_fetch_out, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_sync(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    CK(cudaSetDevice(s->dev));
+    CK(cudaStreamSynchronize(s->stream));
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_get_timers(hgpu_solver_t *s, hgpu_timers_t *out)
+{
+    if (!s || !out) return fail(HGPU_EINVAL, "null argument");
+    *out = s->tm;
+    return HGPU_OK;
+}
+
+extern "C" void *hgpu_stream(hgpu_solver_t *s) { return s ? (void *)s->stream : nullptr; }
+
+extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
+{
+    if (!s || !out) return fail(HGPU_EINVAL, "null argument");
+    const TilePlan &pl = s->plan;
+    out->tile_nodes = pl.tile_nodes; out->ntiles = pl.ntiles;
+    out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
+    out->tile_elems_total = (int64_t)pl.elem_id.size();
+    out->tile_halo_total = (int64_t)pl.halo_id.size();
+    out->n_regular = s->n_regular; out->n_special = s->n_special;
+    out->device_bytes = s->device_bytes;
+    out->smem_bytes = s->smem_u2; out->block_threads = s->block;
+    return HGPU_OK;
+}
+
+// ---- multi-GPU ------------------------------------------------------------------------------------
+
+extern "C" int hgpu_comm_unique_id(void *unique_id_128)
+{
+    if (!unique_id_128) return fail(HGPU_EINVAL, "null argument");
+    int rc = load_nccl();
+    if (rc) return rc;
+    ncclUniqueId id;
+    NK(g_nccl.GetUniqueId(&id));
+    memcpy(unique_id_128, &id, sizeof id);
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_comm_init(hgpu_solver_t *s, const void *unique_id_128)
+{
+    if (!s || !unique_id_128) return fail(HGPU_EINVAL, "null argument");
+    if (s->P.nranks == 1) return HGPU_OK;
+    int rc = load_nccl();
+    if (rc) return rc;
+    CK(cudaSetDevice(s->dev));
+    ncclUniqueId id;
+    memcpy(&id, unique_id_128, sizeof id);
+    NK(g_nccl.CommInitRank(&s->comm, s->P.nranks, id, s->P.rank));
+    return HGPU_OK;
+}
