@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- element-updates/s of the explicit time-stepping hot path on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (BASELINE.json configs[1]): layered half-space (LOH.1 values: 1000 m of rho 2600 /
+Vp 4000 / Vs 2000 over rho 2700 / Vp 6000 / Vs 3464), uniform octree mesh of 256^3 = 16 777 216
+hexahedra per GPU (h = 25 m), Rayleigh damping, effective stiffness, FP64, point source on the 8
+nodes of one element, 5 stations.  The mesh tables are produced on the host in the reference's
+own layout (hercules_b200/meshgen.py, bit-exact with octor + solver_init on a reference-made
+mesh, tests/test_meshgen.py).  N > 1 is weak scaling: the domain grows to N Morton-contiguous
+256^3 blocks, one per GPU, as octor_partitiontree would cut it; shared nodes are exchanged
+through the halo schedules.
+
+A step = one time step over the whole mesh = E element-updates.
+
+  value  device-resident: source history preloaded in HBM, K steps through hgpu_run, timed with
+         CUDA events on the solver's stream, max over ranks.
+  e2e    the per-step C-ABI sequence with HOST buffers: every step copies that step's source
+         forces host->device (hgpu_step) and reads the stations' 8 nodes back device->host
+         (hgpu_fetch_nodes), as solver_run does with read_myForces and
+         interpolate_station_displacements; the final displacement field is read back once at
+         the end (inside the timed region).
+  roofline  the fused tile kernel (element force + central-difference update): algorithmic bytes
+         = 64 E + 248 N per launch over its mean CUDA-event duration.
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref/psolve_ref_O3, built from /root/reference
+         with the fork-based mini-MPI of oracle/mpistub) on this box's host cores, on a smaller
+         mesh of the same material/damping/stiffness configuration; the reference's own
+         "TOTAL SOLVER" timer.  Falls back to the oracle's C port on one core if the binary did
+         not travel.
+
+--impl reference prints the same line for the reference arm alone (rank 0; other ranks exit).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "element-updates/sec"
+UNIT = "element-updates/s"
+LAYERS = ((0.0, 4000.0, 2000.0, 2600.0), (1000.0, 6000.0, 3464.0, 2700.0))   # ztop, Vp, Vs, rho
+H_M, DT, FREQ = 25.0, 0.002, 1.0
+BYTES_PER_ELEM = 64      # 32 B ids + 32 B coefficients
+BYTES_PER_NODE = 248     # 72 B (tm1, tm2, force write) + 176 B update
+
+
+def peaks() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake"}
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag = index, threading.Event()
+        self.sm, self.reasons, self.sm_max = [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(0.05)
+        except Exception as e:                      # clocks are evidence, not a reason to fail
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def result(self) -> dict:
+        self.stop_flag.set()
+        self.join(timeout=2)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons), "samples": len(self.sm)}
+
+
+# ---- the reference arm / cpu baseline -----------------------------------------------------------
+
+def reference_sample(steps: int, fill: int = 350, cores: int | None = None) -> dict:
+    """Run the unmodified reference on the host cores on a bounded sample of the workload.
+
+    The reference skips elements whose nodes have not moved yet (vector_is_zero / the 1e-20
+    early-outs, quake_util.c:36-96), so its speed depends on how far the wave has spread.  To
+    time it in the state the GPU arm is timed in (every element active) the case is run twice,
+    `fill` steps and `fill + steps` steps (the wave from the central source crosses the 64^3
+    sample in ~300 steps), and the rate is taken over the difference of the two TOTAL SOLVER
+    timers."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import refcase
+    ncpu = os.cpu_count() or 1
+    if refcase.have_ref("psolve_ref_O3") and refcase.have_ref("mkcvm"):
+        # ranks = power of two <= min(cores, 32); the mini-MPI forks one process per rank
+        want = min(cores or ncpu, 32)
+        np_ = 1
+        while np_ * 2 <= want:
+            np_ *= 2
+        n = 64                                       # elements per edge of the sample mesh
+        size = n * H_M
+        # vs rule (quake_util.c:215-226): split while edge > Vs/(f ppw); f chosen so that both
+        # layers stop at edge = H_M exactly (2000/(8 f) in (H_M, 2 H_M) and 3464/(8 f) < 2 H_M)
+        f = 0.99 * 2000.0 / (8.0 * H_M)
+        res = []
+        wall0 = time.time()
+        for nst in (fill, fill + steps):
+            c = refcase.Case(cvm_level=4, cvm_n=(16, 16, 16), east_m=size, layers=[list(l) for l in LAYERS],
+                             freq_hz=f, ppw=8.0, vs_min=1900.0, dt=DT, end_t=DT * (nst + 0.5),
+                             damping="rayleigh", stiffness="effective", src_risetime=0.1,
+                             src_xyz=(size / 2 + H_M / 3, size / 2 + H_M / 3, size / 2 + H_M / 3),
+                             stations=[(size / 2, size / 2, 0.0)], station_rate=1)
+            with tempfile.TemporaryDirectory() as td:
+                d = refcase.write_case(c, td)
+                out = refcase.run("psolve_ref_O3", d, nranks=np_, timeout=1500)
+            t = refcase.parse_timing(out)
+            if not {"elements", "steps", "solver_s"} <= set(t):
+                raise RuntimeError("could not parse the reference's timing report:\n" + out[-2000:])
+            res.append(t)
+        wall = time.time() - wall0
+        dsteps = res[1]["steps"] - res[0]["steps"]
+        dt_s = res[1]["solver_s"] - res[0]["solver_s"]
+        if dsteps <= 0 or dt_s <= 0:
+            raise RuntimeError(f"reference timing difference is not positive: {res}")
+        E = res[1]["elements"]
+        return {"value": E * dsteps / dt_s, "unit": UNIT, "cores": np_, "kind": "reference",
+                "sample": f"psolve_ref_O3 (unmodified reference, gcc -O3 -march=x86-64-v3, {np_} mini-MPI ranks on "
+                          f"{ncpu} host cpus), uniform {n}^3 = {int(E)} elements, same layers/rayleigh/effective; "
+                          f"{int(dsteps)} steps timed as the difference of its TOTAL SOLVER timer between a "
+                          f"{int(res[0]['steps'])}-step run ({res[0]['solver_s']:.2f} s) and a {int(res[1]['steps'])}-step run "
+                          f"({res[1]['solver_s']:.2f} s), i.e. after the wave has reached every element "
+                          f"(wall incl. meshing {wall:.0f} s)",
+                "ms_per_step": 1e3 * dt_s / dsteps, "elements": int(E), "steps": int(dsteps)}
+    # fallback: the oracle's C restatement, one core
+    import hercules_oracle as ho
+    from hercules_b200 import meshgen
+    n = 48
+    mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=LAYERS)
+    m = ho.Mesh(mesh.elem_lnid, mesh.eTable, mesh.nTable)
+    st = ho.State(m)
+    st.tm1[:] = np.random.default_rng(0).standard_normal(st.tm1.shape)
+    t0 = time.time()
+    for _ in range(steps):
+        ho.step(m, st, ho.RAYLEIGH, ho.EFFECTIVE, FREQ, DT)
+    el = time.time() - t0
+    return {"value": m.E * steps / el, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"oracle C port (gcc -O2), 1 core, uniform {n}^3 elements, {steps} steps",
+            "ms_per_step": 1e3 * el / steps, "elements": m.E, "steps": steps}
+
+
+def run_reference_arm(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = reference_sample(max(args.steps, 100))
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, args.n),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---- the B200 arm -----------------------------------------------------------------------------------
+
+def block_grid(world: int) -> tuple[int, int, int]:
+    """Blocks per axis (x, y, z) of the weak-scaling domain: Morton order fills x, then y, then z."""
+    bx = by = bz = 1
+    k = 0
+    while bx * by * bz < world:
+        if k % 3 == 0:
+            bz *= 2          # the most significant Morton bit is z
+        elif k % 3 == 1:
+            by *= 2
+        else:
+            bx *= 2
+        k += 1
+    return bx, by, bz
+
+
+def workload_config(world: int, n: int) -> dict:
+    bx, by, bz = block_grid(world)
+    return {"workload": f"configs[1]: layered half-space (LOH.1 values), uniform octree mesh {n}^3 elements "
+                        f"per GPU (h={H_M:g} m), rayleigh damping, effective stiffness, point source, 5 stations",
+            "elements_per_gpu": n ** 3, "global_elements": n ** 3 * world,
+            "global_grid": [n * bx, n * by, n * bz], "dt": DT,
+            "partition": f"{world} Morton-contiguous block(s) (octor_partitiontree rule), halo via NCCL send/recv"
+            if world > 1 else "single rank",
+            "l2": "inputs larger than L2 (node arrays >= 400 MB each step); no explicit flush"}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="elements per edge per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--tile-nodes", type=int, default=0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hercules_b200 as hb
+    from hercules_b200 import meshgen
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not hb.SO.exists():
+        hb.build()
+
+    # ---- workload -------------------------------------------------------------------------------
+    n = args.n
+    bx, by, bz = block_grid(world)
+    t0 = time.time()
+    if world == 1:
+        mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=LAYERS)
+    else:
+        mesh, info = meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=H_M, dt=DT, freq=FREQ,
+                                               layers=LAYERS, part=(rank, world))
+    E, N = info["E"], info["N"]
+    # point source: the 8 nodes of the element at the centre of this rank's block, 2000 m deep on
+    # rank 0 (other ranks carry no source, as in a real run where one rank holds the hypocentre)
+    steps_hist = max(args.steps, args.warmup)
+    if rank == 0:
+        ce = meshgen.element_index(info, n // 2, n // 2, min(n - 1, int(2000 / H_M)))
+        loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
+        tt = (np.arange(steps_hist) + 1) * DT
+        ramp = np.minimum(1.0, (tt / 0.1) ** 2)[:, None, None]
+        rng = np.random.default_rng(11)
+        F_all = np.ascontiguousarray(ramp * 1e9 * rng.standard_normal((1, 8, 3)))
+    else:
+        loaded, F_all = np.zeros(0, np.int32), np.zeros((steps_hist, 0, 3))
+    # 5 stations x 8 nodes on this rank's surface
+    st_elems = [meshgen.element_index(info, int(n * fx), int(n * fy), 0)
+                for fx, fy in ((.5, .5), (.6, .6), (.7, .7), (.8, .8), (.9, .9))]
+    st_nodes = np.ascontiguousarray(mesh.elem_lnid[st_elems].reshape(-1), np.int32)
+    t_mesh = time.time() - t0
+
+    t0 = time.time()
+    s = hb.Solver(mesh, dt=DT, damping=hb.RAYLEIGH, stiffness=hb.EFFECTIVE, freq=FREQ,
+                  loaded_lnid=loaded, rank=rank, nranks=world, device=local,
+                  tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS)
+    if world > 1:
+        uid = [hb.Solver.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        s.comm_init(uid[0])
+    t_init = time.time() - t0
+    layout = s.layout()
+    stream = torch.cuda.ExternalStream(s.stream, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s.sync()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident run: `value` ------------------------------------------------------------
+    s.source_preload(0, F_all[:steps_hist])
+    s.run(0, args.warmup)
+    barrier()
+    tm0 = s.timers()
+    clk = ClockSampler(local)
+    clk.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    s.run(0, args.steps)
+    ev1.record(stream)
+    barrier()
+    dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
+    clocks = clk.result()
+    tm1 = s.timers()
+    launches = int(tm1["launches"] - tm0["launches"])
+    fused_s = tm1["fused_step"] - tm0["fused_step"]
+    tile_launches = args.steps
+    probe = s.fetch_nodes(hb.TM2, st_nodes)
+    if not np.isfinite(probe).all():
+        raise SystemExit("non-finite displacements after the timed run")
+
+    # ---- end-to-end run through the per-step ABI with host buffers: `e2e` ------------------------
+    e2e = None
+    if not args.no_e2e:
+        for k in range(args.warmup):
+            s.step(k, F_all[k] if loaded.size else None)
+            s.fetch_nodes(hb.TM1, st_nodes)
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            s.step(k, F_all[k] if loaded.size else None)
+            s.fetch_nodes(hb.TM1, st_nodes)
+        final = s.fetch_all(hb.TM1)
+        barrier()
+        e2e_s = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": E * world * args.steps / e2e_s, "unit": UNIT,
+               "h2d_bytes_per_step": int(24 * loaded.size + 4 * st_nodes.size),
+               "d2h_bytes_per_step": int(24 * st_nodes.size + final.nbytes / args.steps),
+               "ms_per_step": 1e3 * e2e_s / args.steps,
+               "what": "per-step hgpu_step(host F) + hgpu_fetch_nodes(stations) + one final hgpu_fetch_all(tm1)"}
+    s.close()
+
+    # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            r = reference_sample(100)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as e:                                   # reported baseline only
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {e}"[:300]}
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        alg_bytes = BYTES_PER_ELEM * E + BYTES_PER_NODE * N
+        k_s = fused_s / max(tile_launches, 1)
+        achieved = alg_bytes / k_s / 1e9 if k_s > 0 else None
+        line = {
+            "metric": METRIC, "value": E * world * args.steps / dev_s, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world, n),
+            "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "tile_kernel<true,false> (element force + update, fused)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "bytes_per_element_update": alg_bytes / E,
+                         "kernel_ms": 1e3 * k_s, "kernel_share_of_step": fused_s / dev_s if dev_s > 0 else None,
+                         "traffic": None},
+            "cpu_baseline": cpu,
+            "layout": {k: layout[k] for k in ("tile_nodes", "ntiles", "max_tile_nodes", "tile_elems_total",
+                                              "tile_halo_total", "n_regular", "n_special", "device_bytes",
+                                              "smem_bytes", "block_threads")},
+            "setup_s": {"mesh": round(t_mesh, 1), "hgpu_init": round(t_init, 1)},
+        }
+        traffic_file = ROOT / "profiles" / "traffic.json"
+        if traffic_file.exists():
+            try:
+                line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("tile_kernel_bytes_per_launch")
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

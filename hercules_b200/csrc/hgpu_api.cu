@@ -101,6 +101,12 @@ struct MsgList {
 
 enum ForceState { F_CLEAN = 0, F_PENDING = 1, F_MATERIALIZED = 2, F_FUSED_DONE = 3 };
 
+// Device-time phases, in the order of hgpu_timers_t's double fields.
+enum Phase { PH_ADDFORCE_S = 0, PH_ADDFORCE_E, PH_DAMPING, PH_SEND_DN_FORCE, PH_ADJUST_FORCE,
+             PH_SEND_AN_FORCE, PH_NEW_DISP, PH_SEND_AN_DISP, PH_ADJUST_DISP, PH_SEND_DN_DISP,
+             PH_FUSED_STEP, PH_COUNT };
+struct EvPair { cudaEvent_t a = nullptr, b = nullptr; int phase = 0; };
+
 struct hgpu_solver {
     hgpu_params_t P{};
     int32_t E = 0, N = 0, D = 0;
@@ -123,7 +129,11 @@ struct hgpu_solver {
     // special-node path
     int32_t nS = 0; int32_t *d_slist = nullptr;
     int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
-    double *d_Fall = nullptr; size_t Fall_steps = 0;
+    // per-step source staging: SRC_RING pinned + device slots so hgpu_force_source never has to
+    // wait for the previous step (slot k is reusable once its own copy has completed)
+    static constexpr int SRC_RING = 8;
+    cudaEvent_t src_done[SRC_RING] = {nullptr}; int src_slot = 0;
+    double *d_Fall = nullptr; size_t Fall_steps = 0, Fall_loaded = 0; int32_t Fall_step0 = 0;
     int32_t *d_dnode = nullptr;
     int32_t nA = 0; int32_t *d_anchor_id = nullptr, *d_anchor_off = nullptr, *d_anchor_dn = nullptr,
             *d_anchor_deps = nullptr;
@@ -135,6 +145,10 @@ struct hgpu_solver {
     ForceState fstate = F_CLEAN;
     int64_t n_regular = 0, n_special = 0, device_bytes = 0;
     hgpu_timers_t tm{};
+    // CUDA-event phase timing (HGPU_FLAG_TIMERS): a pool of event pairs drained at sync points
+    std::vector<EvPair> evpool;
+    size_t ev_used = 0;
+    double phase_s[PH_COUNT] = {0};
     // scratch for fetch
     int32_t *d_fetch_ids = nullptr; double *d_fetch_out = nullptr; int32_t fetch_cap = 0;
 };
@@ -180,6 +194,40 @@ static int upload_msglist(hgpu_solver *s, const hgpu_msglist_t &in, MsgList &out
     if ((rc = dalloc(s, &out.d_recv, 3 * (size_t)out.total))) return rc;
     return HGPU_OK;
 }
+
+// Sum the elapsed time of every recorded event pair into phase_s (synchronises the stream).
+static void drain_events(hgpu_solver *s)
+{
+    if (!s->ev_used) return;
+    cudaStreamSynchronize(s->stream);
+    for (size_t i = 0; i < s->ev_used; i++) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->evpool[i].a, s->evpool[i].b) == cudaSuccess)
+            s->phase_s[s->evpool[i].phase] += 1e-3 * (double)ms;
+    }
+    s->ev_used = 0;
+}
+
+// Brackets the launches of one phase with a CUDA event pair on the solver's stream.
+struct PhaseTimer {
+    hgpu_solver *s; EvPair *p = nullptr;
+    PhaseTimer(hgpu_solver *s_, int phase) : s(s_)
+    {
+        if (!(s->P.flags & HGPU_FLAG_TIMERS)) return;
+        if (s->ev_used == s->evpool.size()) {
+            if (s->evpool.size() >= 8192) drain_events(s);
+            else {
+                EvPair e;
+                if (cudaEventCreate(&e.a) != cudaSuccess || cudaEventCreate(&e.b) != cudaSuccess) return;
+                s->evpool.push_back(e);
+            }
+        }
+        p = &s->evpool[s->ev_used++];
+        p->phase = phase;
+        cudaEventRecord(p->a, s->stream);
+    }
+    ~PhaseTimer() { if (p) cudaEventRecord(p->b, s->stream); }
+};
 
 extern "C" const char *hgpu_last_error(void) { return g_err.c_str(); }
 extern "C" int hgpu_abi_version(void) { return HGPU_ABI_VERSION; }
@@ -295,8 +343,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             hgpu_finalize(s); return fail(HGPU_EINVAL, "loaded node id out of range");
         }
     TRY(upload(s, &s->d_loaded, params->loaded_lnid, (size_t)params->nloaded));
-    TRY(dalloc(s, &s->d_F, 3 * (size_t)params->nloaded));
-    TRYCU(cudaMallocHost((void **)&s->h_F, std::max<size_t>(1, 3 * (size_t)params->nloaded) * sizeof(double)));
+    TRY(dalloc(s, &s->d_F, hgpu_solver::SRC_RING * 3 * (size_t)params->nloaded));
+    TRYCU(cudaMallocHost((void **)&s->h_F, std::max<size_t>(1, hgpu_solver::SRC_RING * 3 * (size_t)params->nloaded) * sizeof(double)));
+    for (int i = 0; i < hgpu_solver::SRC_RING; i++)
+        TRYCU(cudaEventCreateWithFlags(&s->src_done[i], cudaEventDisableTiming));
 
     // ---- node classes -----------------------------------------------------------------------------
     {
@@ -380,6 +430,8 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
     dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
     free_msglist(s->dn_c); free_msglist(s->dn_s); free_msglist(s->an_c); free_msglist(s->an_s);
+    for (int i = 0; i < hgpu_solver::SRC_RING; i++) if (s->src_done[i]) cudaEventDestroy(s->src_done[i]);
+    for (EvPair &e : s->evpool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
     if (s->h_F) cudaFreeHost(s->h_F);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -410,6 +462,9 @@ static int launch_tiles(hgpu_solver *s, bool fuse)
     A.fuse_update = fuse ? 1 : 0;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
     const int T = s->plan.ntiles;
+    // fused launches have no counterpart among the reference's timers; an unfused launch is
+    // booked under "Compute addforces e" when it carries the stiffness term, else under damping
+    PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (stiff ? PH_ADDFORCE_E : PH_DAMPING));
     if (T > 0) {
         // a damping-only launch runs the u2 variant with s_u1 = 0; a launch with no term at all
         // (MASS damping alone) is a fused update whose element force is identically zero
@@ -458,12 +513,17 @@ extern "C" int hgpu_force_source(hgpu_solver_t *s, const double *F)
     if (s->fstate != F_CLEAN)
         return fail(HGPU_ESTATE, "hgpu_force_source must precede the element forces (assignment, psolve.c:5921)");
     CK(cudaSetDevice(s->dev));
-    // the pinned staging buffer may still be in flight from the previous step
-    CK(cudaStreamSynchronize(s->stream));
-    memcpy(s->h_F, F, 3 * (size_t)n * sizeof(double));
-    CK(cudaMemcpyAsync(s->d_F, s->h_F, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(n, s->d_loaded, s->d_F, s->P.dt2, s->force);
+    // ring slot: wait only for the copy issued SRC_RING steps ago (never recorded = ready)
+    const int slot = s->src_slot;
+    s->src_slot = (slot + 1) % hgpu_solver::SRC_RING;
+    CK(cudaEventSynchronize(s->src_done[slot]));
+    double *hF = s->h_F + (size_t)slot * 3 * (size_t)n, *dF = s->d_F + (size_t)slot * 3 * (size_t)n;
+    memcpy(hF, F, 3 * (size_t)n * sizeof(double));
+    PhaseTimer pt(s, PH_ADDFORCE_S);
+    CK(cudaMemcpyAsync(dF, hF, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(n, s->d_loaded, dF, s->P.dt2, s->force);
     CK(cudaGetLastError());
+    CK(cudaEventRecord(s->src_done[slot], s->stream));
     s->tm.launches++;
     return HGPU_OK;
 }
@@ -547,15 +607,20 @@ extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
         s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
     }
     // phase 8: dangling-node forces to their owners
-    if ((rc = exchange(s, s->dn_c, s->dn_s, s->force, true))) return rc;
+    {
+        PhaseTimer pt(s, PH_SEND_DN_FORCE);
+        if ((rc = exchange(s, s->dn_c, s->dn_s, s->force, true))) return rc;
+    }
     // phase 9: owned dangling nodes hand force/deps to their anchors
     if (s->nA > 0) {
+        PhaseTimer pt(s, PH_ADJUST_FORCE);
         adjust_dist_kernel<<<grid_for(3LL * s->nA, 128), 128, 0, s->stream>>>(
             s->nA, s->d_anchor_id, s->d_anchor_off, s->d_anchor_dn, s->d_anchor_deps, s->force);
         CK(cudaGetLastError());
         s->tm.launches++;
     }
     // phase 10: anchored-node forces to their owners
+    PhaseTimer pt(s, PH_SEND_AN_FORCE);
     if ((rc = exchange(s, s->an_c, s->an_s, s->force, true))) return rc;
     return HGPU_OK;
 }
@@ -572,6 +637,7 @@ extern "C" int hgpu_update(hgpu_solver_t *s)
         s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
     }
     double *u1 = s->u[s->i1], *u2 = s->u[s->i2], *un = s->u[s->i3];
+    PhaseTimer pt(s, PH_NEW_DISP);
     if (s->fstate == F_FUSED_DONE) {
         if (s->nS > 0) {
             update_list_kernel<<<grid_for(3LL * s->nS, 256), 256, 0, s->stream>>>(
@@ -603,14 +669,19 @@ extern "C" int hgpu_disp_exchange(hgpu_solver_t *s)
     int rc;
     double *tm2 = s->u[s->i2];
     // phase 13: owners publish anchored-node displacements
-    if ((rc = exchange(s, s->an_c, s->an_s, tm2, false))) return rc;
+    {
+        PhaseTimer pt(s, PH_SEND_AN_DISP);
+        if ((rc = exchange(s, s->an_c, s->an_s, tm2, false))) return rc;
+    }
     // phase 14: dangling nodes interpolate from their anchors
     if (s->D > 0) {
+        PhaseTimer pt(s, PH_ADJUST_DISP);
         adjust_asgn_kernel<<<grid_for(3LL * s->D, 128), 128, 0, s->stream>>>(s->D, s->d_dnode, tm2);
         CK(cudaGetLastError());
         s->tm.launches++;
     }
     // phase 15: owners publish dangling-node displacements
+    PhaseTimer pt(s, PH_SEND_DN_DISP);
     if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false))) return rc;
     return HGPU_OK;
 }
@@ -627,30 +698,51 @@ extern "C" int hgpu_step(hgpu_solver_t *s, int32_t step, const double *F)
     return hgpu_disp_exchange(s);
 }
 
+extern "C" int hgpu_source_preload(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (nsteps < 0) return fail(HGPU_EINVAL, "hgpu_source_preload: negative step count");
+    const int n = s->P.nloaded;
+    if (n == 0 || nsteps == 0) return HGPU_OK;
+    if (!F_all) return fail(HGPU_EINVAL, "hgpu_source_preload: F_all is null but nloaded > 0");
+    CK(cudaSetDevice(s->dev));
+    // whole source history resident in HBM: no per-step host traffic
+    if (s->Fall_steps < (size_t)nsteps) {
+        CK(cudaStreamSynchronize(s->stream));
+        dfree(s->d_Fall);
+        int rc = dalloc(s, &s->d_Fall, 3 * (size_t)n * (size_t)nsteps);
+        if (rc) return rc;
+        s->Fall_steps = (size_t)nsteps;
+    }
+    CK(cudaMemcpyAsync(s->d_Fall, F_all, 3 * (size_t)n * (size_t)nsteps * sizeof(double),
+                       cudaMemcpyHostToDevice, s->stream));
+    CK(cudaStreamSynchronize(s->stream));     // F_all is the caller's pageable memory
+    s->Fall_loaded = (size_t)nsteps;
+    s->Fall_step0 = step0;
+    return HGPU_OK;
+}
+
 extern "C" int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all)
 {
     if (!s) return fail(HGPU_EINVAL, "null solver");
     if (nsteps < 0) return fail(HGPU_EINVAL, "hgpu_run: negative step count");
     const int n = s->P.nloaded;
-    if (n > 0 && !F_all) return fail(HGPU_EINVAL, "hgpu_run: F_all is null but nloaded > 0");
     CK(cudaSetDevice(s->dev));
-    if (n > 0) {
-        // whole source history resident in HBM: no per-step host traffic
-        if (s->Fall_steps < (size_t)nsteps) {
-            dfree(s->d_Fall);
-            int rc = dalloc(s, &s->d_Fall, 3 * (size_t)n * (size_t)nsteps);
-            if (rc) return rc;
-            s->Fall_steps = (size_t)nsteps;
-        }
-        CK(cudaMemcpyAsync(s->d_Fall, F_all, 3 * (size_t)n * (size_t)nsteps * sizeof(double),
-                           cudaMemcpyHostToDevice, s->stream));
-    }
+    if (n > 0 && F_all) {
+        int rc = hgpu_source_preload(s, step0, nsteps, F_all);
+        if (rc) return rc;
+    } else if (n > 0 && (step0 < s->Fall_step0 ||
+                         (size_t)(step0 - s->Fall_step0) + (size_t)nsteps > s->Fall_loaded))
+        return fail(HGPU_EINVAL, "hgpu_run: steps [%d, %d) are not covered by the preloaded source history",
+                    step0, step0 + nsteps);
+    const size_t row0 = n > 0 ? (size_t)(step0 - s->Fall_step0) : 0;
     for (int32_t k = 0; k < nsteps; k++) {
         int rc;
         if ((rc = hgpu_step_begin(s, step0 + k))) return rc;
         if (n > 0) {
+            PhaseTimer pt(s, PH_ADDFORCE_S);
             source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(
-                n, s->d_loaded, s->d_Fall + 3 * (size_t)n * (size_t)k, s->P.dt2, s->force);
+                n, s->d_loaded, s->d_Fall + 3 * (size_t)n * (row0 + (size_t)k), s->P.dt2, s->force);
             CK(cudaGetLastError());
             s->tm.launches++;
         }
@@ -744,6 +836,10 @@ extern "C" int hgpu_sync(hgpu_solver_t *s)
 extern "C" int hgpu_get_timers(hgpu_solver_t *s, hgpu_timers_t *out)
 {
     if (!s || !out) return fail(HGPU_EINVAL, "null argument");
+    CK(cudaSetDevice(s->dev));
+    drain_events(s);
+    double *dst = &s->tm.addforce_s;   // the eleven double fields are contiguous, in Phase order
+    for (int i = 0; i < PH_COUNT; i++) dst[i] = s->phase_s[i];
     *out = s->tm;
     return HGPU_OK;
 }

@@ -207,3 +207,12 @@ def node_index(info: dict, ix: int, iy: int, iz: int) -> int:
     nx, ny, nz = info["dims"]
     lin = (ix * (ny + 1) + iy) * (nz + 1) + iz
     return int(np.nonzero(info["node_order"] == lin)[0][0])
+
+
+def element_index(info: dict, ex: int, ey: int, ez: int) -> int:
+    """Local element id of the element whose lowest corner is grid point (ex, ey, ez) (local grid)."""
+    X, Y, Z = info["elem_xyz"]
+    hit = np.nonzero((X == ex) & (Y == ey) & (Z == ez))[0]
+    if hit.size != 1:
+        raise ValueError(f"element ({ex},{ey},{ez}) is not on this rank")
+    return int(hit[0])

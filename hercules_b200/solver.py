@@ -28,6 +28,7 @@ RAYLEIGH, MASS, NONE, BKT = 0, 1, 2, 3      # damping_type_t, damping.h:28
 CONVENTIONAL, EFFECTIVE = 0, 1              # stiffness_type_t, stiffness.h:24
 TM1, TM2, TM3, FORCE = 1, 2, 3, 4
 FLAG_NO_FUSE = 1
+FLAG_TIMERS = 2
 
 
 class HerculesGpuError(RuntimeError):
@@ -192,8 +193,15 @@ class Solver:
         else:
             _chk(self._L.hgpu_step(self._h, step, None))
 
-    def run(self, step0: int, nsteps: int, F_all=None) -> None:
+    def source_preload(self, step0: int, F_all) -> int:
+        """Make source rows for steps step0.. ([nsteps][nloaded][3]) resident in HBM; returns nsteps."""
+        F_all = np.ascontiguousarray(F_all, np.float64).reshape(-1, max(self.nloaded, 1), 3)
         if self.nloaded:
+            _chk(self._L.hgpu_source_preload(self._h, step0, F_all.shape[0], F_all.ctypes.data))
+        return F_all.shape[0]
+
+    def run(self, step0: int, nsteps: int, F_all=None) -> None:
+        if self.nloaded and F_all is not None:
             F_all = np.ascontiguousarray(F_all, np.float64)
             if F_all.size < 3 * self.nloaded * nsteps:
                 raise ValueError("F_all must be [nsteps][nloaded][3]")

@@ -101,6 +101,7 @@ typedef struct hgpu_params {
 } hgpu_params_t;
 
 #define HGPU_FLAG_NO_FUSE 1     /* keep force evaluation and update as separate kernels */
+#define HGPU_FLAG_TIMERS  2     /* bracket every phase with CUDA events (hgpu_get_timers)   */
 
 typedef struct hgpu_solver hgpu_solver_t;
 
@@ -164,8 +165,12 @@ int hgpu_disp_exchange(hgpu_solver_t *s);
 
 /* The seven calls above in sequence; F may be NULL when nloaded == 0. */
 int hgpu_step(hgpu_solver_t *s, int32_t step, const double *F);
-/* nsteps steps starting at step0 with the whole source history resident:
- * F_all = [nsteps][nloaded][3] host doubles (the body of force_process.<rank>). */
+/* Source streaming (read_myForces does fseeko+fread per step, psolve.c:3651-3667):
+ * copy F_all = [nsteps][nloaded][3] host doubles (rows step0.. of force_process.<rank>) to HBM once. */
+int hgpu_source_preload(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all);
+/* nsteps steps starting at step0 with the source history resident in HBM.  F_all non-NULL =
+ * preload rows for [step0, step0+nsteps) first; NULL = use what hgpu_source_preload left
+ * resident (it must cover those steps). */
 int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all);
 
 /* ---- output taps and restart (host <-> device only when the host asks) ------------------- */
