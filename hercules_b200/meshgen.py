@@ -23,7 +23,7 @@ import math
 
 import numpy as np
 
-from .solver import HostMesh, RAYLEIGH, MASS
+from .solver import HostMesh, MsgList, RAYLEIGH, MASS
 
 _XI = np.array([[-1, 1, -1, 1, -1, 1, -1, 1],
                 [-1, -1, 1, 1, -1, -1, 1, 1],
@@ -93,42 +93,73 @@ def compute_setab(damping: int, freq: float):
     return 0.0, 0.0
 
 
-def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: float = 1.0,
-                      damping: int = RAYLEIGH, layers=((0.0, 6000.0, 3464.0, 2700.0),),
-                      thr_damping: float = 0.05, thr_vpvs: float = 3.0, exact: bool = False):
-    """nx x ny x nz elements of edge h (x = north, y = east, z = depth).  layers = (ztop, Vp, Vs,
-    rho) by depth of the element centre.  exact=True accumulates nTable in the reference's exact
-    operation order (slow, for the bit-for-bit test); otherwise sums are grouped per element.
-    Returns (HostMesh, info)."""
+def _compact1by2(v: np.ndarray) -> np.ndarray:
+    v = v.astype(np.uint64) & np.uint64(0x1249249249249249)
+    v = (v | (v >> np.uint64(2))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v >> np.uint64(4))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v >> np.uint64(8))) & np.uint64(0x1F0000FF0000FF)
+    v = (v | (v >> np.uint64(16))) & np.uint64(0x1F00000000FFFF)
+    v = (v | (v >> np.uint64(32))) & np.uint64(0x1FFFFF)
+    return v.astype(np.int64)
+
+
+def block_low(task: int, group: int, n: int) -> int:
+    """octor.c:685-690."""
+    return task * n // group
+
+
+def block_owner(idx, group: int, n: int):
+    """octor.c:738-742."""
+    return ((np.asarray(idx, np.int64) + 1) * group - 1) // n
+
+
+class _MortonIndex:
+    """Global preorder (Morton) rank of the leaves of a uniform nx x ny x nz grid, i.e. octor's
+    geid (octor.c:5362-5374, 5505), without sorting the whole grid: the grid is cut into cubes of
+    n^3 elements, n the largest power of two dividing all three dimensions; cubes are ordered by
+    the Morton code of their coordinates and elements inside a cube by theirs."""
+
+    def __init__(self, nx: int, ny: int, nz: int):
+        g = math.gcd(math.gcd(nx, ny), nz)
+        n = g & -g
+        self.n, self.n3 = n, n ** 3
+        self.dims = (nx, ny, nz)
+        B = (nx // n, ny // n, nz // n)
+        bx, by, bz = np.meshgrid(np.arange(B[0]), np.arange(B[1]), np.arange(B[2]), indexing="ij")
+        bx, by, bz = bx.ravel(), by.ravel(), bz.ravel()
+        o = np.argsort(morton3(bx, by, bz), kind="stable")
+        self.bx, self.by, self.bz = bx[o].astype(np.int64), by[o].astype(np.int64), bz[o].astype(np.int64)
+        self.brank = np.empty(B, np.int64)
+        self.brank[self.bx, self.by, self.bz] = np.arange(o.size)
+        self.total = nx * ny * nz
+
+    def index(self, ex, ey, ez) -> np.ndarray:
+        n = self.n
+        ex, ey, ez = np.asarray(ex, np.int64), np.asarray(ey, np.int64), np.asarray(ez, np.int64)
+        return self.brank[ex // n, ey // n, ez // n] * self.n3 + \
+            morton3(ex % n, ey % n, ez % n).astype(np.int64)
+
+    def coords(self, idx):
+        idx = np.asarray(idx, np.int64)
+        b, w = idx // self.n3, (idx % self.n3).astype(np.uint64)
+        n = self.n
+        return (self.bx[b] * n + _compact1by2(w), self.by[b] * n + _compact1by2(w >> np.uint64(1)),
+                self.bz[b] * n + _compact1by2(w >> np.uint64(2)))
+
+
+def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs):
+    """Per-element quantities of solver_init (psolve.c:3360-3473) for uniform elements of edge h at
+    global grid coordinates (ex, ey, ez): eTable rows, lumped mass, a, dashpot terms."""
     f32 = np.float32
-    # ---- elements in Morton order ------------------------------------------------------------
-    ex, ey, ez = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
-    ex, ey, ez = ex.ravel(), ey.ravel(), ez.ravel()
-    order = np.argsort(morton3(ex, ey, ez), kind="stable")
-    ex, ey, ez = ex[order], ey[order], ez[order]
+    nx, ny, nz = dims
     E = ex.size
-    # ---- nodes in Morton order -------------------------------------------------------------------
-    ix, iy, iz = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
-    def key(i, n):
-        i = i.ravel()
-        return np.where(i == n, 2 * n - 1, 2 * i)
-    norder = np.argsort(morton3(key(ix, nx), key(iy, ny), key(iz, nz)), kind="stable")
-    N = norder.size
-    rank = np.empty(N, np.int32)
-    rank[norder] = np.arange(N, dtype=np.int32)
-    rank = rank.reshape(nx + 1, ny + 1, nz + 1)
-    lnid = np.empty((E, 8), np.int32)
-    for j in range(8):
-        lnid[:, j] = rank[ex + (j & 1), ey + ((j >> 1) & 1), ez + ((j >> 2) & 1)]
-    del rank
-    # ---- edata_t (floats) --------------------------------------------------------------------------
     zc = (ez + 0.5) * h
     Vp, Vs, rho = np.empty(E, f32), np.empty(E, f32), np.empty(E, f32)
     for (zt, vp, vs, r) in layers:
         sel = zc >= zt
         Vp[sel], Vs[sel], rho[sel] = vp, vs, r
     edge = np.full(E, h, f32)
-    # ---- mu_and_lambda (psolve.c:3236-3272): float products, then double ------------------------
+    # mu_and_lambda (psolve.c:3236-3272): float products, then double
     mu = (rho * Vs * Vs).astype(np.float64)
     big = Vp > (Vs.astype(np.float64) * thr_vpvs)
     lam = np.where(big, (rho * Vs * Vs).astype(np.float64) * thr_vpvs * thr_vpvs - 2 * mu,
@@ -140,7 +171,6 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
         Vp[neg] = (f[neg] * Vs[neg].astype(np.float64)).astype(f32)
         lam[neg] = (rho[neg] * Vp[neg] * Vp[neg]).astype(np.float64)
     dt2 = dt * dt
-    abase, bbase = compute_setab(damping, freq)
     eT = np.empty((E, 4))
     eT[:, 0] = dt2 * edge * mu / 9
     eT[:, 1] = dt2 * edge * lam / 9
@@ -149,57 +179,226 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
     a, b = zeta * abase, zeta * bbase
     eT[:, 2] = b * dt * edge * mu / 9
     eT[:, 3] = b * dt * edge * lam / 9
-    # ---- lumped mass and dashpots (psolve.c:3411-3473, 5752-5804) -------------------------------
+    # lumped mass and dashpots (psolve.c:3411-3473, 5752-5804)
     M = (rho * edge * edge * edge).astype(np.float64) / 8
     scale = (rho * (edge / f32(2)) * (edge / f32(2))).astype(np.float64)
     # absorbing faces: x near/far, y near/far, z far; the top (z near) is free under HALFSPACE
-    touch = np.stack([np.stack([ex == 0, ex == nx - 1]), np.stack([ey == 0, ey == ny - 1]),
-                      np.stack([np.zeros(E, bool), ez == nz - 1])])          # [axis][near/far][E]
-    dash = np.zeros((E, 8, 3))
-    bits = np.zeros((E, 8), np.int64)
-    for j in range(8):
-        for ax in range(3):
-            far = (j >> ax) & 1
-            bits[:, j] |= (touch[ax, far].astype(np.int64) << ax)
-    nb = (bits & 1) + ((bits >> 1) & 1) + ((bits >> 2) & 1)
-    vp_plus_2vs = (Vp + f32(2) * Vs).astype(np.float64)
-    for c in range(3):
-        on = ((bits >> c) & 1).astype(bool)
-        vsel = np.where(on, Vp[:, None], Vs[:, None])                     # float
-        two = (Vs[:, None] + vsel).astype(np.float64) * scale[:, None]    # (Vs + Vp|Vs) float, * double
-        one = vsel.astype(np.float64) * scale[:, None]
-        three = np.broadcast_to((vp_plus_2vs * scale)[:, None], (E, 8))
-        dash[:, :, c] = np.where(nb == 3, three, np.where(nb == 2, two, np.where(nb == 1, one, 0.0)))
-    boundary = nb.max(axis=1) > 0                                           # flag != 13
-    nT = np.zeros((N, 7))
-    flat = lnid.reshape(-1)
+    touch = ((ex == 0, ex == nx - 1), (ey == 0, ey == ny - 1), (np.zeros(E, bool), ez == nz - 1))
+    boundary = touch[0][0] | touch[0][1] | touch[1][0] | touch[1][1] | touch[2][1]   # flag != 13
+    # dashpots only on boundary elements: keep them sparse
+    bi = np.nonzero(boundary)[0]
+    nb_ = bi.size
+    dash = np.zeros((nb_, 8, 3))
+    if nb_:
+        bits = np.zeros((nb_, 8), np.int64)
+        for j in range(8):
+            for ax in range(3):
+                far = (j >> ax) & 1
+                bits[:, j] |= (touch[ax][far][bi].astype(np.int64) << ax)
+        nb = (bits & 1) + ((bits >> 1) & 1) + ((bits >> 2) & 1)
+        Vpb, Vsb, sc = Vp[bi], Vs[bi], scale[bi]
+        vp_plus_2vs = (Vpb + f32(2) * Vsb).astype(np.float64)
+        for c in range(3):
+            on = ((bits >> c) & 1).astype(bool)
+            vsel = np.where(on, Vpb[:, None], Vsb[:, None])                   # float
+            two = (Vsb[:, None] + vsel).astype(np.float64) * sc[:, None]      # (Vs + Vp|Vs) float, * double
+            one = vsel.astype(np.float64) * sc[:, None]
+            three = np.broadcast_to((vp_plus_2vs * sc)[:, None], (nb_, 8))
+            dash[:, :, c] = np.where(nb == 3, three, np.where(nb == 2, two, np.where(nb == 1, one, 0.0)))
+    return dict(Vp=Vp, Vs=Vs, rho=rho, edge=edge, eT=eT, M=M, a=a, bidx=bi, dash=dash)
+
+
+def _accumulate(nT, nodes8, pr, dt, exact, keep=None):
+    """Add the elements' lumped-mass / damping / dashpot terms into nT (psolve.c:3445-3473).
+    nodes8 = [E][8] node rows; keep = optional [E][8] mask of corners to include."""
+    E = nodes8.shape[0]
+    N = nT.shape[0]
+    M, a = pr["M"], pr["a"]
+    bi, dash = pr["bidx"], pr["dash"]
+    flat = nodes8.reshape(-1)
+    kf = None if keep is None else keep.reshape(-1)
     if exact:
         # the reference's exact sequence per (element, corner, axis): -= dt a M; -= dt dashpot
         # (boundary elements only); += M  |  mass2: -= dt a M; -= dt dashpot; += 2 M
-        np.add.at(nT[:, 0], flat, np.repeat(M, 8))
+        dd = np.zeros((E, 8, 3)); dd[bi] = dt * dash
+        dd = dd.reshape(-1, 3)
+        bnd = np.zeros(E, bool); bnd[bi] = True
+        bnd = np.repeat(bnd, 8)
+        ones = np.ones_like(bnd) if kf is None else kf
+        np.add.at(nT[:, 0], flat[ones], np.repeat(M, 8)[ones])
         daM = np.repeat(dt * a * M, 8)
-        dd = dt * dash.reshape(-1, 3)
-        bnd = np.repeat(boundary, 8)
         for ax in range(3):
             for col, mult in ((4 + ax, 1.0), (1 + ax, 2.0)):
                 idx = np.stack([flat, flat, flat], 1)
                 val = np.stack([-daM, np.where(bnd, -dd[:, ax], 0.0), np.repeat(M * mult, 8)], 1)
-                keep = np.stack([np.ones_like(bnd), bnd, np.ones_like(bnd)], 1)
-                np.add.at(nT[:, col], idx[keep], val[keep])
+                k3 = np.stack([ones, bnd & ones, ones], 1)
+                np.add.at(nT[:, col], idx[k3], val[k3])
+        return
+    w8 = None if kf is None else kf.astype(np.float64)
+    def bc(vals):
+        return np.bincount(flat, vals if w8 is None else vals * w8, N)
+    nT[:, 0] += bc(np.repeat(M, 8))
+    base1 = bc(np.repeat(M - dt * a * M, 8))
+    base2 = bc(np.repeat(2 * M - dt * a * M, 8))
+    bflat = nodes8[bi].reshape(-1)
+    bw = None if keep is None else keep[bi].reshape(-1).astype(np.float64)
+    for ax in range(3):
+        d = dt * dash[:, :, ax].reshape(-1)
+        dsum = np.bincount(bflat, d if bw is None else d * bw, N) if bflat.size else 0.0
+        nT[:, 4 + ax] += base1 - dsum
+        nT[:, 1 + ax] += base2 - dsum
+
+
+def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: float = 1.0,
+                      damping: int = RAYLEIGH, layers=((0.0, 6000.0, 3464.0, 2700.0),),
+                      thr_damping: float = 0.05, thr_vpvs: float = 3.0, exact: bool = False,
+                      part: tuple | None = None):
+    """nx x ny x nz elements of edge h (x = north, y = east, z = depth).  layers = (ztop, Vp, Vs,
+    rho) by depth of the element centre.  exact=True accumulates nTable in the reference's exact
+    operation order (slow, for the bit-for-bit test); otherwise sums are grouped per element.
+
+    part = (rank, nranks) returns that rank's share under octor's partition rule: the Morton
+    ordered leaf list is cut into contiguous blocks (octor.c:685-746, 4940-4941); a rank harbors
+    the corner nodes of its elements; a node belongs to the rank that owns the element whose
+    lowest corner it is (far-boundary nodes pulled in by one tick, octor.c:5466-5475); the halo
+    schedules follow schedule_build (psolve.c:4705-4863) and the owners' nTable rows include the
+    sharers' partial sums in messenger order (mass exchange, psolve.c:3498-3507).
+    Returns (HostMesh, info)."""
+    rank, world = part if part is not None else (0, 1)
+    mi = _MortonIndex(nx, ny, nz)
+    Etot = mi.total
+    lo, hi = block_low(rank, world, Etot), block_low(rank + 1, world, Etot)
+    ex, ey, ez = mi.coords(np.arange(lo, hi, dtype=np.int64))
+    E = ex.size
+    # ---- harbored nodes in Morton order ----------------------------------------------------------
+    x0, y0, z0 = int(ex.min()), int(ey.min()), int(ez.min())
+    X, Y, Z = int(ex.max()) - x0 + 2, int(ey.max()) - y0 + 2, int(ez.max()) - z0 + 2
+    lx, ly, lz = ex - x0, ey - y0, ez - z0
+    full = E == (X - 1) * (Y - 1) * (Z - 1)
+    if full:
+        hf = np.ones((X, Y, Z), bool)
     else:
-        nT[:, 0] = np.bincount(flat, np.repeat(M, 8), N)
-        for ax in range(3):
-            d = dt * dash[:, :, ax].reshape(-1)
-            base = np.repeat(M - dt * a * M, 8)
-            nT[:, 4 + ax] = np.bincount(flat, base - d, N)
-            nT[:, 1 + ax] = np.bincount(flat, np.repeat(2 * M - dt * a * M, 8) - d, N)
-    edata = np.zeros((E, 14), f32)
-    edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = edge, Vp, Vs, rho
+        hf = np.zeros((X, Y, Z), bool)
+        for j in range(8):
+            hf[lx + (j & 1), ly + ((j >> 1) & 1), lz + ((j >> 2) & 1)] = True
+    ix, iy, iz = np.nonzero(hf)
+    gx, gy, gz = ix + x0, iy + y0, iz + z0
+
+    def key(g, n):
+        return np.where(g == n, 2 * n - 1, 2 * g)
+    norder = np.argsort(morton3(key(gx, nx), key(gy, ny), key(gz, nz)), kind="stable")
+    ix, iy, iz, gx, gy, gz = ix[norder], iy[norder], iz[norder], gx[norder], gy[norder], gz[norder]
+    N = norder.size
+    del norder
+    nrank = np.full((X, Y, Z), -1, np.int32)
+    nrank[ix, iy, iz] = np.arange(N, dtype=np.int32)
+    lnid = np.empty((E, 8), np.int32)
+    for j in range(8):
+        lnid[:, j] = nrank[lx + (j & 1), ly + ((j >> 1) & 1), lz + ((j >> 2) & 1)]
+    # ---- solver tables from my own elements ------------------------------------------------------
+    abase, bbase = compute_setab(damping, freq)
+    args = ((nx, ny, nz), h, dt, layers, abase, bbase, thr_damping, thr_vpvs)
+    pr = _elem_props(ex, ey, ez, *args)
+    nT = np.zeros((N, 7))
+    _accumulate(nT, lnid, pr, dt, exact)
+    # ---- ownership, sharers, schedules -----------------------------------------------------------
+    owner = np.full(N, rank, np.int32)
+    msg = {k: MsgList() for k in ("dn_c", "dn_s", "an_c", "an_s")}
+    share = np.zeros((0, 2), np.int32)
+    if world > 1:
+        # nodes all of whose in-domain adjacent elements are mine need no look-up
+        mine = np.zeros((X + 1, Y + 1, Z + 1), bool)          # element grid x0-1 .. x0+X-1
+        mine[lx + 1, ly + 1, lz + 1] = True
+        gxs, gys, gzs = np.arange(x0 - 1, x0 + X), np.arange(y0 - 1, y0 + Y), np.arange(z0 - 1, z0 + Z)
+        outside = ((gxs < 0) | (gxs >= nx))[:, None, None] | ((gys < 0) | (gys >= ny))[None, :, None] | \
+                  ((gzs < 0) | (gzs >= nz))[None, None, :]
+        ok = mine | outside
+        all8 = np.ones((X, Y, Z), bool)
+        for j in range(8):
+            dx, dy, dz = j & 1, (j >> 1) & 1, (j >> 2) & 1
+            all8 &= ok[1 - dx:1 - dx + X, 1 - dy:1 - dy + Y, 1 - dz:1 - dz + Z]
+        cand = np.nonzero(~all8[ix, iy, iz])[0]               # ascending lnid
+        del mine, outside, ok, all8
+        cx, cy, cz = gx[cand], gy[cand], gz[cand]
+        owner[cand] = block_owner(mi.index(np.minimum(cx, nx - 1), np.minimum(cy, ny - 1),
+                                           np.minimum(cz, nz - 1)), world, Etot)
+        # adjacent elements of the candidate nodes and their ranks
+        adj_rank = np.full((cand.size, 8), -1, np.int64)
+        adj_gidx = np.full((cand.size, 8), -1, np.int64)
+        for j in range(8):
+            ax_, ay_, az_ = cx - (j & 1), cy - ((j >> 1) & 1), cz - ((j >> 2) & 1)
+            inb = (ax_ >= 0) & (ax_ < nx) & (ay_ >= 0) & (ay_ < ny) & (az_ >= 0) & (az_ < nz)
+            g = mi.index(ax_[inb], ay_[inb], az_[inb])
+            adj_gidx[inb, j] = g
+            adj_rank[inb, j] = block_owner(g, world, Etot)
+        mine_c = owner[cand] == rank
+        # c-lists: nodes I harbor but do not own, per owner, ascending lnid; messengers are pushed
+        # to the front of the list as they first appear (psolve.c:4733-4746)
+        def make_list(nodes, peers):
+            if nodes.size == 0:
+                return MsgList()
+            firsts = {}
+            for nd, p in zip(nodes.tolist(), peers.tolist()):
+                firsts.setdefault(p, None)
+            order = list(firsts.keys())[::-1]
+            maps = [nodes[peers == p] for p in order]
+            return MsgList(np.array(order, np.int32), np.array([m.size for m in maps], np.int32),
+                           np.concatenate(maps).astype(np.int32))
+        notmine = cand[~mine_c]
+        msg["an_c"] = make_list(notmine, owner[notmine].astype(np.int64))
+        # s-lists: (node, sharer) for nodes I own; a node's sharers in ascending rank order
+        sh_nodes, sh_peers = [], []
+        ar = adj_rank[mine_c]
+        own_nodes = cand[mine_c]
+        ar_sorted = np.sort(ar, axis=1)
+        for col in range(8):
+            r = ar_sorted[:, col]
+            new = (r >= 0) & (r != rank)
+            if col:
+                new &= r != ar_sorted[:, col - 1]
+            sh_nodes.append(own_nodes[new]); sh_peers.append(r[new])
+        sh_nodes, sh_peers = np.concatenate(sh_nodes), np.concatenate(sh_peers)
+        o = np.lexsort((sh_peers, sh_nodes))                  # by node, then by sharer rank
+        sh_nodes, sh_peers = sh_nodes[o], sh_peers[o]
+        share = np.stack([sh_nodes, sh_peers], 1).astype(np.int32)
+        msg["an_s"] = make_list(sh_nodes, sh_peers)
+        # mass exchange (psolve.c:3505-3507): owners add each sharer's partial sums, messenger
+        # after messenger; a sharer's partial is its own element loop over the elements that
+        # touch the node, in its local (Morton) element order
+        for p in msg["an_s"].peer.tolist():
+            sel = (adj_rank == p) & mine_c[:, None]           # [cand][8]: ghost element of rank p
+            ci, cj = np.nonzero(sel)
+            gid = adj_gidx[ci, cj]
+            ug, inv = np.unique(gid, return_inverse=True)     # ghost elements in p's element order
+            gex, gey, gez = mi.coords(ug)
+            gpr = _elem_props(gex, gey, gez, *args)
+            # corner c of ghost element g is node (g + corner offset); corner index = the j whose
+            # offset leads from the element to the node: node = elem + (j&1, ...)  =>  j = cj
+            nodes8 = np.zeros((ug.size, 8), np.int64)
+            keep = np.zeros((ug.size, 8), bool)
+            nodes8[inv, cj] = cand[ci]
+            keep[inv, cj] = True
+            partial = np.zeros((N, 7))
+            _accumulate(partial, nodes8, gpr, dt, exact, keep)
+            rows = msg["an_s"].mapping[_slice_of(msg["an_s"], p)]
+            nT[rows] += partial[rows]
+    edata = np.zeros((E, 14), np.float32)
+    edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
     K1, K2 = compute_K()
-    mesh = HostMesh(lnid, eT, nT, np.zeros((0, 6), np.int32), edata, K1, K2)
-    info = dict(E=E, N=N, abase=abase, bbase=bbase, node_order=norder, elem_xyz=(ex, ey, ez),
-                dims=(nx, ny, nz), h=h)
+    mesh = HostMesh(lnid, pr["eT"], nT, np.zeros((0, 6), np.int32), edata, K1, K2,
+                    msg["dn_c"], msg["dn_s"], msg["an_c"], msg["an_s"])
+    node_lin = (gx * (ny + 1) + gy) * (nz + 1) + gz
+    info = dict(E=E, N=N, abase=abase, bbase=bbase, node_order=node_lin, node_xyz=(gx, gy, gz),
+                elem_xyz=(ex, ey, ez), elem_geid=np.arange(lo, hi, dtype=np.int64), origin=(x0, y0, z0),
+                dims=(nx, ny, nz), h=h, owner=owner, share=share, rank=rank, nranks=world,
+                etotal=Etot)
     return mesh, info
+
+
+def _slice_of(ml: MsgList, peer: int) -> slice:
+    i = int(np.nonzero(ml.peer == peer)[0][0])
+    off = int(ml.nodes[:i].sum())
+    return slice(off, off + int(ml.nodes[i]))
 
 
 def node_index(info: dict, ix: int, iy: int, iz: int) -> int:
@@ -210,9 +409,11 @@ def node_index(info: dict, ix: int, iy: int, iz: int) -> int:
 
 
 def element_index(info: dict, ex: int, ey: int, ez: int) -> int:
-    """Local element id of the element whose lowest corner is grid point (ex, ey, ez) (local grid)."""
+    """Local element id of the element whose lowest corner is grid point (ex, ey, ez), counted
+    from the lowest corner of this rank's bounding box."""
     X, Y, Z = info["elem_xyz"]
-    hit = np.nonzero((X == ex) & (Y == ey) & (Z == ez))[0]
+    x0, y0, z0 = info["origin"]
+    hit = np.nonzero((X == ex + x0) & (Y == ey + y0) & (Z == ez + z0))[0]
     if hit.size != 1:
         raise ValueError(f"element ({ex},{ey},{ez}) is not on this rank")
     return int(hit[0])

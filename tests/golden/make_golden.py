@@ -55,6 +55,8 @@ CASES = {
     "graded3_rayleigh_eff_np2": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 2, 25),
     "graded3_rayleigh_eff_np4": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 4, 25),
     "uniform_rayleigh_eff": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 1, 25),
+    "uniform_rayleigh_eff_np3": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 3, 25),
+    "uniform_rayleigh_eff_np4": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 4, 25),
 }
 
 KEEP = ["params", "counts", "domain_ticks", "elem_lnid", "elem_geid", "elem_level", "elem_edata",
