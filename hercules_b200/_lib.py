@@ -46,7 +46,7 @@ class Layout(C.Structure):
     _fields_ = [("tile_nodes", i32), ("ntiles", i32), ("max_tile_nodes", i32),
                 ("max_tile_elems", i32), ("tile_elems_total", i64), ("tile_halo_total", i64),
                 ("n_regular", i64), ("n_special", i64), ("device_bytes", i64),
-                ("smem_bytes", i32), ("block_threads", i32)]
+                ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32)]
 
 
 # every symbol include/hercules_gpu.h declares: name -> (restype, argtypes)
@@ -76,6 +76,7 @@ SYMBOLS = {
     "hgpu_get_timers": (C.c_int, [_H, C.POINTER(Timers)]),
     "hgpu_stream": (C.c_void_p, [_H]),
     "hgpu_get_layout": (C.c_int, [_H, C.POINTER(Layout)]),
+    "hgpu_plan_build": (C.c_int, [C.POINTER(Mesh), i32, C.POINTER(Layout)]),
 }
 
 

@@ -117,15 +117,16 @@ struct hgpu_solver {
     int i1 = 0, i2 = 1, i3 = 2;          // which buffer plays tm1 / tm2 / tm3
     double *force = nullptr;
     double *mass = nullptr, *m2 = nullptr, *m1 = nullptr;
-    uint8_t *ncls = nullptr;
     // element arrays
     double *etab = nullptr;
     double *Kd = nullptr;
     // tiles
     TilePlan plan;
-    int32_t *t_elem_off = nullptr, *t_elem_id = nullptr, *t_halo_off = nullptr, *t_halo_id = nullptr;
-    uint4 *t_elem_slot = nullptr;
-    int smem_u2 = 0, smem_nou2 = 0, block = 256;
+    int32_t *t_node_off = nullptr, *t_elem_off = nullptr, *t_halo_off = nullptr, *t_halo_id = nullptr;
+    uint4 *t_ent_slot = nullptr;         // per entry 8 x uint16 = 3 * slot
+    double *t_ent_coef = nullptr;        // per entry c1, c2, beta
+    double *nt3 = nullptr;               // [N][3] {+-1/mass, m2, m1} for the fused update
+    int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, cap_slots = 0, cap_owned = 0, ctas_per_sm = 0;
     // special-node path
     int32_t nS = 0; int32_t *d_slist = nullptr;
     int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
@@ -240,6 +241,29 @@ extern "C" int hgpu_device_count(void)
     return n;
 }
 
+// Tile capacities for a device with max_smem bytes of opt-in shared memory per CTA.
+// Two CTAs per SM: each may use half of the SM's shared memory minus the 1 KB the system reserves
+// per CTA.  Per CTA: 2 stages x (u1 + u2) x cap_slots nodes + cap_owned accumulator nodes.
+static void tile_caps(int max_smem, int32_t tile_nodes, int32_t *cap_owned_o, int32_t *cap_slots_o,
+                      int32_t *elem_block_o)
+{
+    const int per_cta = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
+    int32_t cap_owned = tile_nodes > 0 ? tile_nodes : 730;
+    const char *env = getenv("HGPU_TILE_NODES");
+    if (tile_nodes <= 0 && env && atoi(env) > 0) cap_owned = atoi(env);
+    cap_owned = std::max(2, cap_owned & ~1);
+    int32_t elem_block = 512;
+    const char *eenv = getenv("HGPU_ELEM_BLOCK");
+    if (eenv && atoi(eenv) > 0) elem_block = atoi(eenv);
+    int32_t cap_slots = (per_cta / 8 - 3 * cap_owned) / 12;
+    if (cap_slots <= cap_owned) {
+        cap_owned = (per_cta / 8 / 18) & ~1;       // owned : staged about 1 : 1.25
+        cap_slots = (per_cta / 8 - 3 * cap_owned) / 12;
+    }
+    cap_slots = std::min(cap_slots, 65535 / 3);
+    *cap_owned_o = cap_owned; *cap_slots_o = cap_slots; *elem_block_o = elem_block;
+}
+
 static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
 extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgpu_params_t *params)
@@ -349,6 +373,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRYCU(cudaEventCreateWithFlags(&s->src_done[i], cudaEventDisableTiming));
 
     // ---- node classes -----------------------------------------------------------------------------
+    // A node is advanced inside the fused step kernel unless something else must see or change its
+    // force first (source assignment, hanging-node transfer, halo exchange), or unless its
+    // mass2_minusaM / mass_minusaM differ between components (absorbing-boundary dashpots,
+    // psolve.c:3445-3473): the fused path keeps one scalar of each per node.
     {
         std::vector<uint8_t> cls((size_t)N, NODE_REGULAR);
         if (params->flags & HGPU_FLAG_NO_FUSE) std::fill(cls.begin(), cls.end(), (uint8_t)NODE_SPECIAL);
@@ -364,45 +392,70 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             for (int32_t i = 0; i < l->count; i++) tot += l->nodes[i];
             for (int32_t i = 0; i < tot; i++) cls[l->mapping[i]] = NODE_SPECIAL;
         }
+        std::vector<double> nt3(n3);
+        for (int32_t n = 0; n < N; n++) {
+            const double *np = mesh->nTable + 7 * (size_t)n;
+            const bool iso = np[1] == np[2] && np[1] == np[3] && np[4] == np[5] && np[4] == np[6];
+            if (!iso || !(np[0] > 0.0)) cls[n] = NODE_SPECIAL;
+            const double rm = np[0] > 0.0 ? 1.0 / np[0] : 1.0;
+            nt3[3 * (size_t)n] = cls[n] == NODE_SPECIAL ? -rm : rm;
+            nt3[3 * (size_t)n + 1] = np[1];
+            nt3[3 * (size_t)n + 2] = np[4];
+        }
         std::vector<int32_t> slist;
         for (int32_t n = 0; n < N; n++) if (cls[n] == NODE_SPECIAL) slist.push_back(n);
         s->nS = (int32_t)slist.size();
         s->n_special = s->nS; s->n_regular = (int64_t)N - s->nS;
-        TRY(upload(s, &s->ncls, cls.data(), (size_t)N));
+        TRY(upload(s, &s->nt3, nt3.data(), n3));
         if (!(params->flags & HGPU_FLAG_NO_FUSE)) TRY(upload(s, &s->d_slist, slist.data(), slist.size()));
     }
 
     // ---- tiles ------------------------------------------------------------------------------------
     {
-        int max_smem = 0;
+        int max_smem = 0, nsm = 0;
         TRYCU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev));
-        int32_t tn = params->tile_nodes > 0 ? params->tile_nodes : 512;
-        const char *env = getenv("HGPU_TILE_NODES");
-        if (params->tile_nodes <= 0 && env && atoi(env) > 0) tn = atoi(env);
-        tn &= ~1;
-        bool ok = false;
-        for (; tn >= 32; tn /= 2) {
-            // worst case: both displacement buffers staged; two CTAs per SM wanted
-            int32_t max_slots = (int32_t)std::min<long long>(65535, ((long long)max_smem / 8 - 3LL * tn) / 6);
-            if (max_slots <= tn) continue;
-            if (build_tile_plan(E, N, mesh->elem_lnid, tn, max_slots, s->plan, err)) { ok = true; break; }
-            if (params->tile_nodes > 0) break;
+        TRYCU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->dev));
+        int32_t cap_owned, cap_slots, elem_block;
+        tile_caps(max_smem, params->tile_nodes, &cap_owned, &cap_slots, &elem_block);
+        if (!build_tile_plan(E, N, mesh->elem_lnid, elem_block, cap_owned, cap_slots, s->plan, err)) {
+            hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
         }
-        if (!ok) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str()); }
-        const TilePlan &pl = s->plan;
+        TilePlan &pl = s->plan;
+        const size_t entries = pl.elem_id.size();
+        // entry records: slot offsets premultiplied by 3; c1, c2 and beta = c3/c1 (= c4/c2 = b/dt,
+        // psolve.c:3387-3409) copied per entry so a tile streams them without indirection
+        for (uint16_t &v : pl.elem_slot) v = (uint16_t)(3 * v);
+        std::vector<double> coef(3 * entries);
+        for (size_t k = 0; k < entries; k++) {
+            const double *et = mesh->eTable + 4 * (size_t)pl.elem_id[k];
+            coef[3 * k] = et[0]; coef[3 * k + 1] = et[1];
+            coef[3 * k + 2] = et[0] != 0.0 ? et[2] / et[0] : 0.0;
+        }
+        TRY(upload(s, &s->t_node_off, pl.node_off.data(), pl.node_off.size()));
         TRY(upload(s, &s->t_elem_off, pl.elem_off.data(), pl.elem_off.size()));
-        TRY(upload(s, &s->t_elem_id, pl.elem_id.data(), pl.elem_id.size()));
-        TRY(upload(s, (uint16_t **)&s->t_elem_slot, pl.elem_slot.data(), pl.elem_slot.size()));
+        TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
+        TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
         TRY(upload(s, &s->t_halo_off, pl.halo_off.data(), pl.halo_off.size()));
         TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
-        s->smem_u2 = (6 * pl.max_tile_nodes + 3 * pl.tile_nodes) * (int)sizeof(double);
-        s->smem_nou2 = (3 * pl.max_tile_nodes + 3 * pl.tile_nodes) * (int)sizeof(double);
+        // shared memory actually needed by this plan
+        s->cap_slots = pl.max_tile_nodes; s->cap_owned = (pl.max_tile_owned + 1) & ~1;
+        s->smem_u2 = (12 * s->cap_slots + 3 * s->cap_owned) * (int)sizeof(double);
+        s->smem_nou2 = (6 * s->cap_slots + 9 * s->cap_owned) * (int)sizeof(double);
         const char *benv = getenv("HGPU_BLOCK");
         if (benv && atoi(benv) >= 64 && atoi(benv) <= 256) s->block = atoi(benv) & ~31;
-        TRYCU(cudaFuncSetAttribute(tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
-        TRYCU(cudaFuncSetAttribute(tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
-        TRYCU(cudaFuncSetAttribute(tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
-        TRYCU(cudaFuncSetAttribute(tile_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        TRYCU(cudaFuncSetAttribute(step_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        int occ = 0;
+        TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false>, s->block, s->smem_u2));
+        if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
+        s->ctas_per_sm = occ;
+        s->grid = std::max(1, std::min(pl.ntiles, nsm * occ));
+        const char *genv = getenv("HGPU_GRID");
+        if (genv && atoi(genv) > 0) s->grid = std::min(pl.ntiles, atoi(genv));
     }
     TRYCU(cudaStreamSynchronize(s->stream));
     TRYCU(cudaDeviceSynchronize());
@@ -424,8 +477,9 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
-    dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->ncls); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_elem_off); dfree(s->t_elem_id); dfree(s->t_elem_slot); dfree(s->t_halo_off); dfree(s->t_halo_id);
+    dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
+    dfree(s->t_node_off); dfree(s->t_elem_off); dfree(s->t_ent_slot); dfree(s->t_ent_coef);
+    dfree(s->t_halo_off); dfree(s->t_halo_id);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
     dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
@@ -440,45 +494,45 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
 
 // ---- force evaluation ---------------------------------------------------------------------------
 
-// Launch the tile kernel for whatever force terms were requested since the last update.
+// Launch the step kernel for whatever force terms were requested since the last update.
 // fuse = advance REGULAR nodes in the same launch (their force never reaches HBM).
-static int launch_tiles(hgpu_solver *s, bool fuse)
+// Returns through *launched whether a kernel ran (no term requested = nothing to add).
+static int launch_tiles(hgpu_solver *s, bool fuse, bool *launched)
 {
     const bool stiff = s->want_stiff, damp = s->want_damp;
     const bool rayleigh = s->P.damping == HGPU_DAMPING_RAYLEIGH;
     // MASS damping has b = 0, hence c3 = c4 = 0 (psolve.c:5866-5867): damping_addforce adds nothing
     const bool need_u2 = damp && rayleigh;
-    const bool any = stiff || need_u2;
-    if (!any && !fuse) return HGPU_OK;
-    TileArgs A{};
+    s->want_stiff = s->want_damp = false;
+    *launched = false;
+    if (!stiff && !need_u2) return HGPU_OK;
+    StepArgs A{};
     A.u1 = s->u[s->i1]; A.u2 = s->u[s->i2]; A.unext = s->u[s->i3]; A.force = s->force;
-    A.mass = s->mass; A.m2 = s->m2; A.m1 = s->m1; A.ncls = s->ncls; A.etab = s->etab; A.Kd = s->Kd;
-    A.elem_off = s->t_elem_off; A.elem_id = s->t_elem_id; A.elem_slot = s->t_elem_slot;
-    A.halo_off = s->t_halo_off; A.halo_id = s->t_halo_id;
-    A.N = s->N; A.tile_nodes = s->plan.tile_nodes; A.ntiles = s->plan.ntiles; A.tile_begin = 0;
-    A.stage_nodes = s->plan.max_tile_nodes;
-    A.s_u1 = stiff ? 1.0 : 0.0;
-    A.s_du = need_u2 ? 1.0 : 0.0;
+    A.nt3 = s->nt3; A.Kd = s->Kd;
+    A.node_off = s->t_node_off; A.elem_off = s->t_elem_off; A.halo_off = s->t_halo_off; A.halo_id = s->t_halo_id;
+    A.ent_slot = s->t_ent_slot; A.ent_coef = s->t_ent_coef;
+    A.ntiles = s->plan.ntiles; A.cap_slots = s->cap_slots; A.cap_owned = s->cap_owned;
     A.fuse_update = fuse ? 1 : 0;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
-    const int T = s->plan.ntiles;
+    const int mode = stiff ? (need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (stiff ? PH_ADDFORCE_E : PH_DAMPING));
-    if (T > 0) {
-        // a damping-only launch runs the u2 variant with s_u1 = 0; a launch with no term at all
-        // (MASS damping alone) is a fused update whose element force is identically zero
-        if (need_u2) {
-            if (dense) tile_kernel<true, true><<<T, s->block, s->smem_u2, s->stream>>>(A);
-            else       tile_kernel<true, false><<<T, s->block, s->smem_u2, s->stream>>>(A);
+    if (s->plan.ntiles > 0) {
+        const int G = s->grid, B = s->block;
+        if (dense) {
+            if (mode == 0)      step_kernel<0, true><<<G, B, s->smem_nou2, s->stream>>>(A);
+            else if (mode == 1) step_kernel<1, true><<<G, B, s->smem_u2, s->stream>>>(A);
+            else                step_kernel<2, true><<<G, B, s->smem_u2, s->stream>>>(A);
         } else {
-            if (dense) tile_kernel<false, true><<<T, s->block, s->smem_nou2, s->stream>>>(A);
-            else       tile_kernel<false, false><<<T, s->block, s->smem_nou2, s->stream>>>(A);
+            if (mode == 0)      step_kernel<0, false><<<G, B, s->smem_nou2, s->stream>>>(A);
+            else if (mode == 1) step_kernel<1, false><<<G, B, s->smem_u2, s->stream>>>(A);
+            else                step_kernel<2, false><<<G, B, s->smem_u2, s->stream>>>(A);
         }
         CK(cudaGetLastError());
         s->tm.launches++;
+        *launched = true;
     }
-    s->want_stiff = s->want_damp = false;
     return HGPU_OK;
 }
 
@@ -487,7 +541,8 @@ static int materialize_forces(hgpu_solver *s)
 {
     if (s->fstate == F_PENDING) {
         // temporarily treat all nodes as SPECIAL: run without the fused update
-        int rc = launch_tiles(s, false);
+        bool ran;
+        int rc = launch_tiles(s, false, &ran);
         if (rc) return rc;
         s->fstate = F_MATERIALIZED;
     }
@@ -535,8 +590,9 @@ extern "C" int hgpu_force_stiffness(hgpu_solver_t *s)
     if (s->fstate == F_FUSED_DONE) return fail(HGPU_ESTATE, "forces already consumed for this step");
     CK(cudaSetDevice(s->dev));
     if (s->fstate == F_MATERIALIZED) {
+        bool ran;
         s->want_stiff = true;
-        return launch_tiles(s, false);
+        return launch_tiles(s, false, &ran);
     }
     s->want_stiff = true;
     s->fstate = F_PENDING;
@@ -550,8 +606,9 @@ extern "C" int hgpu_force_damping(hgpu_solver_t *s)
     if (s->fstate == F_FUSED_DONE) return fail(HGPU_ESTATE, "forces already consumed for this step");
     CK(cudaSetDevice(s->dev));
     if (s->fstate == F_MATERIALIZED) {
+        bool ran;
         s->want_damp = true;
-        return launch_tiles(s, false);
+        return launch_tiles(s, false, &ran);
     }
     s->want_damp = true;
     s->fstate = F_PENDING;
@@ -603,8 +660,9 @@ extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
     int rc;
     if (s->fstate == F_PENDING) {
         const bool fuse = !(s->P.flags & HGPU_FLAG_NO_FUSE);
-        if ((rc = launch_tiles(s, fuse))) return rc;
-        s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
+        bool ran;
+        if ((rc = launch_tiles(s, fuse, &ran))) return rc;
+        s->fstate = (fuse && ran) ? F_FUSED_DONE : F_MATERIALIZED;
     }
     // phase 8: dangling-node forces to their owners
     {
@@ -633,8 +691,9 @@ extern "C" int hgpu_update(hgpu_solver_t *s)
     if (s->fstate == F_PENDING) {
         // hgpu_force_exchange was skipped (legal on a conforming single-rank mesh)
         const bool fuse = !(s->P.flags & HGPU_FLAG_NO_FUSE);
-        if ((rc = launch_tiles(s, fuse))) return rc;
-        s->fstate = fuse ? F_FUSED_DONE : F_MATERIALIZED;
+        bool ran;
+        if ((rc = launch_tiles(s, fuse, &ran))) return rc;
+        s->fstate = (fuse && ran) ? F_FUSED_DONE : F_MATERIALIZED;
     }
     double *u1 = s->u[s->i1], *u2 = s->u[s->i2], *un = s->u[s->i3];
     PhaseTimer pt(s, PH_NEW_DISP);
@@ -846,17 +905,41 @@ extern "C" int hgpu_get_timers(hgpu_solver_t *s, hgpu_timers_t *out)
 
 extern "C" void *hgpu_stream(hgpu_solver_t *s) { return s ? (void *)s->stream : nullptr; }
 
+// Host-only: build the tile plan for a mesh with the capacities of a B200 SM (227 KB opt-in shared
+// memory, two CTAs per SM), check it against the mesh, and report its sizes.  Needs no device.
+extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu_layout_t *out)
+{
+    if (!mesh || !out || !mesh->elem_lnid) return fail(HGPU_EINVAL, "null argument");
+    TilePlan pl;
+    std::string err;
+    int32_t cap_owned, cap_slots, elem_block;
+    tile_caps(232448, tile_nodes, &cap_owned, &cap_slots, &elem_block);
+    if (!build_tile_plan(mesh->lenum, mesh->nharbored, mesh->elem_lnid, elem_block, cap_owned, cap_slots, pl, err))
+        return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
+    if (!validate_tile_plan(mesh->lenum, mesh->nharbored, mesh->elem_lnid, pl, err))
+        return fail(HGPU_EINVAL, "tile plan check: %s", err.c_str());
+    memset(out, 0, sizeof *out);
+    out->tile_nodes = pl.max_tile_owned; out->ntiles = pl.ntiles;
+    out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
+    out->tile_elems_total = (int64_t)pl.elem_id.size();
+    out->tile_halo_total = (int64_t)pl.halo_id.size();
+    out->smem_bytes = (12 * pl.max_tile_nodes + 3 * ((pl.max_tile_owned + 1) & ~1)) * (int)sizeof(double);
+    out->block_threads = 256;
+    return HGPU_OK;
+}
+
 extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
 {
     if (!s || !out) return fail(HGPU_EINVAL, "null argument");
     const TilePlan &pl = s->plan;
-    out->tile_nodes = pl.tile_nodes; out->ntiles = pl.ntiles;
+    out->tile_nodes = pl.max_tile_owned; out->ntiles = pl.ntiles;
     out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
     out->tile_elems_total = (int64_t)pl.elem_id.size();
     out->tile_halo_total = (int64_t)pl.halo_id.size();
     out->n_regular = s->n_regular; out->n_special = s->n_special;
     out->device_bytes = s->device_bytes;
     out->smem_bytes = s->smem_u2; out->block_threads = s->block;
+    out->grid_ctas = s->grid; out->ctas_per_sm = s->ctas_per_sm;
     return HGPU_OK;
 }
 

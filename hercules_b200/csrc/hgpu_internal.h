@@ -15,13 +15,15 @@ namespace hgpu {
 enum : uint8_t { NODE_REGULAR = 0, NODE_SPECIAL = 1 };
 
 // Owner-computes tiling of the node range.  Tile t owns the contiguous node
-// ids [t*tile_nodes, min(N,(t+1)*tile_nodes)); it evaluates every element incident to an owned
+// ids [node_off[t], node_off[t+1]) (even start); it evaluates every element incident to an owned
 // node, so the force on an owned node is complete inside the tile and no atomics are needed.
 struct TilePlan {
-    int32_t tile_nodes = 0;
+    int32_t tile_nodes = 0;       // cap on owned nodes per tile
     int32_t ntiles = 0;
+    int32_t max_tile_owned = 0;
     int32_t max_tile_nodes = 0;   // owned + gathered
     int32_t max_tile_elems = 0;
+    std::vector<int32_t>  node_off;   // [ntiles+1]
     std::vector<int32_t>  elem_off;   // [ntiles+1] into elem_id / elem_slot
     std::vector<int32_t>  elem_id;    // element evaluated by this tile entry
     std::vector<uint16_t> elem_slot;  // [entries][8] tile-local slot of each corner node
@@ -29,9 +31,11 @@ struct TilePlan {
     std::vector<int32_t>  halo_id;    // gathered (non-owned) node ids; slot = owned_count + index
 };
 
-// Builds the plan; returns false and sets err when a tile would exceed max_slots local nodes.
-bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t tile_nodes,
-                     int32_t max_slots, TilePlan &plan, std::string &err);
+// Builds the plan; returns false and sets err on inconsistent input.
+bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_block,
+                     int32_t max_owned, int32_t max_slots, TilePlan &plan, std::string &err);
+
+bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePlan &plan, std::string &err);
 
 // Hanging-node lists (flattened dnode_t, octor.h:153-158).
 struct DanglingPlan {

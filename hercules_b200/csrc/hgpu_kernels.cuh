@@ -1,9 +1,10 @@
 // hgpu_kernels.cuh -- sm_100a device code of libhercules_gpu.so.
 //
 // Kernels (DESIGN.md sections 3-4):
-//   tile_kernel        per-element internal force (stiffness + Rayleigh damping) gathered per
+//   step_kernel        per-element internal force (stiffness + Rayleigh damping) gathered per
 //                      owned node inside an owner-computes tile, optionally fused with the
-//                      central-difference update of the tile's REGULAR nodes
+//                      central-difference update of the tile's REGULAR nodes; persistent CTAs with
+//                      a two-stage cp.async pipeline
 //   source_kernel      compute_addforce_s            (psolve.c:5912-5928)
 //   adjust_dist_kernel compute_adjust(DISTRIBUTION)  (psolve.c:5943-5987), anchor-centric
 //   update_list_kernel solver_compute_displacement   (psolve.c:4072-4114) on the SPECIAL nodes
@@ -106,164 +107,237 @@ __device__ __forceinline__ void scale_modes(const double (&tx)[8], const double 
     vz[7] = a2b9 * tz[7];
 }
 
-struct TileArgs {
+// ------------------------------------------------------------------------------------------
+// step_kernel: persistent, software-pipelined owner-computes kernel.
+//
+// One CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While tile i is being computed out
+// of shared-memory stage i&1, the displacements of tile i+1 stream into the other stage with
+// cp.async (LDGSTS): 16-byte copies for the owned node range (contiguous, even start), 8-byte
+// copies for the gathered halo nodes.  The per-entry element data (8 slot offsets + c1, c2, beta)
+// is prefetched into registers one round ahead.  Two CTAs per SM hide each other's barriers.
+//
+//   MODE 0: w = u1                     stiffness term only            (damping none / mass)
+//   MODE 1: w = u1 + beta (u1 - u2)    stiffness + Rayleigh damping   beta = c3/c1 = c4/c2 = b/dt
+//   MODE 2: w = beta (u1 - u2)         Rayleigh damping only          (psolve.c:3387-3409)
+// ------------------------------------------------------------------------------------------
+struct StepArgs {
     const double *__restrict__ u1;      // tm1  [N][3]
     const double *__restrict__ u2;      // tm2  [N][3]
     double *__restrict__ unext;         // u(t+dt) target (fused update) [N][3]
     double *__restrict__ force;         // [N][3]
-    const double *__restrict__ mass;    // n_t.mass_simple   [N]
-    const double *__restrict__ m2;      // n_t.mass2_minusaM [N][3]
-    const double *__restrict__ m1;      // n_t.mass_minusaM  [N][3]
-    const uint8_t *__restrict__ ncls;   // node class [N]
-    const double *__restrict__ etab;    // e_t [E][4]
+    const double *__restrict__ nt3;     // [N][3] {1/mass_simple, mass2_minusaM, mass_minusaM} of nodes the
+                                        // fused update may advance; first entry negative = hand the force on
     const double *__restrict__ Kd;      // dense K1|K2 as [2][24][24] (conventional only)
+    const int32_t *__restrict__ node_off;
     const int32_t *__restrict__ elem_off;
-    const int32_t *__restrict__ elem_id;
-    const uint4 *__restrict__ elem_slot;   // 8 x uint16 per entry
     const int32_t *__restrict__ halo_off;
     const int32_t *__restrict__ halo_id;
-    int32_t N, tile_nodes, ntiles, tile_begin;
-    int32_t stage_nodes;                // smem capacity in node slots
-    double s_u1;                        // 1: include -K(c1,c2) u1          (stiffness term)
-    double s_du;                        // 1: include -K(c3,c4) (u1 - u2)   (Rayleigh term)
-    int32_t fuse_update;                // 1: advance REGULAR owned nodes here
+    const uint4 *__restrict__ ent_slot; // per entry 8 x uint16: 3 * tile-local slot of each corner
+    const double *__restrict__ ent_coef;// per entry c1, c2, beta
+    int32_t ntiles;
+    int32_t cap_slots;                  // staged nodes per stage
+    int32_t cap_owned;                  // accumulator nodes
+    int32_t fuse_update;                // 1: advance owned nodes flagged in nt3 here
 };
 
-// One CTA per tile.  Shared memory: su1[3*S] | su2[3*S] (only when NEED_U2) | acc[3*tile_nodes].
-template <bool NEED_U2, bool DENSE>
-__global__ void __launch_bounds__(256, 2) tile_kernel(const TileArgs A)
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
 {
-    extern __shared__ double smem[];
-    const int t = A.tile_begin + blockIdx.x;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    const int n0 = t * A.tile_nodes;
-    const int nown = min(A.tile_nodes, A.N - n0);
-    const int hb = A.halo_off[t], nh = A.halo_off[t + 1] - hb;
-    double *su1 = smem;
-    double *su2 = smem + 3 * A.stage_nodes;
-    double *acc = smem + (NEED_U2 ? 6 : 3) * A.stage_nodes;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-    // ---- phase 0: stage the tile's displacements --------------------------------------------
-    {
-        // owned range: contiguous, 16-byte aligned (tile_nodes is even) -> 128-bit loads
-        const int nd = 3 * nown, nv = nd >> 1;
-        const double2 *g1 = reinterpret_cast<const double2 *>(A.u1 + 3 * (size_t)n0);
-        const double2 *g2 = reinterpret_cast<const double2 *>(A.u2 + 3 * (size_t)n0);
-        for (int i = tid; i < nv; i += nthr) {
-            double2 v = __ldg(g1 + i);
-            su1[2 * i] = v.x; su1[2 * i + 1] = v.y;
-            if (NEED_U2) { double2 w = __ldg(g2 + i); su2[2 * i] = w.x; su2[2 * i + 1] = w.y; }
-            acc[2 * i] = 0.0; acc[2 * i + 1] = 0.0;
-        }
-        if ((nd & 1) && tid == 0) {
-            su1[nd - 1] = A.u1[3 * (size_t)n0 + nd - 1];
-            if (NEED_U2) su2[nd - 1] = A.u2[3 * (size_t)n0 + nd - 1];
-            acc[nd - 1] = 0.0;
-        }
-        // gathered nodes: 3 consecutive lanes read the 24 contiguous bytes of one node
-        for (int i = tid; i < 3 * nh; i += nthr) {
-            const int h = i / 3, c = i - 3 * h;
-            const size_t g = 3 * (size_t)A.halo_id[hb + h] + c;
-            su1[3 * nown + i] = __ldg(A.u1 + g);
-            if (NEED_U2) su2[3 * nown + i] = __ldg(A.u2 + g);
-        }
+struct TileMeta { int n0, nown, hb, nh, eb, ne; };
+
+__device__ __forceinline__ TileMeta load_meta(const StepArgs &A, int t)
+{
+    TileMeta m;
+    m.n0 = __ldg(A.node_off + t); m.nown = __ldg(A.node_off + t + 1) - m.n0;
+    m.hb = __ldg(A.halo_off + t); m.nh = __ldg(A.halo_off + t + 1) - m.hb;
+    m.eb = __ldg(A.elem_off + t); m.ne = __ldg(A.elem_off + t + 1) - m.eb;
+    return m;
+}
+
+struct Entry { uint4 s; double c1, c2, beta; };
+
+template <bool NEED_BETA>
+__device__ __forceinline__ Entry load_entry(const StepArgs &A, int idx)
+{
+    Entry e;
+    e.s = __ldg(A.ent_slot + idx);
+    const double *c = A.ent_coef + 3 * (size_t)idx;
+    e.c1 = __ldg(c); e.c2 = __ldg(c + 1);
+    e.beta = NEED_BETA ? __ldg(c + 2) : 0.0;
+    return e;
+}
+
+// Stage the displacements of one tile: su1 (and su2) <- owned range + gathered halo nodes.
+// U2_OWNED: copy the owned part of u2; U2_HALO: also its halo part.
+template <bool U2_OWNED, bool U2_HALO>
+__device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m, double *su1, double *su2,
+                                           int tid, int nthr)
+{
+    const int nd = 3 * m.nown, nv = nd >> 1;
+    const double *g1 = A.u1 + 3 * (size_t)m.n0, *g2 = A.u2 + 3 * (size_t)m.n0;
+    for (int i = tid; i < nv; i += nthr) {
+        cp_async16(su1 + 2 * i, g1 + 2 * i);
+        if (U2_OWNED) cp_async16(su2 + 2 * i, g2 + 2 * i);
     }
-    __syncthreads();
+    if ((nd & 1) && tid == 0) {
+        cp_async8(su1 + nd - 1, g1 + nd - 1);
+        if (U2_OWNED) cp_async8(su2 + nd - 1, g2 + nd - 1);
+    }
+    for (int i = tid; i < 3 * m.nh; i += nthr) {
+        const int h = i / 3, c = i - 3 * h;
+        const size_t g = 3 * (size_t)__ldg(A.halo_id + m.hb + h) + c;
+        cp_async8(su1 + nd + i, A.u1 + g);
+        if (U2_HALO) cp_async8(su2 + nd + i, A.u2 + g);
+    }
+}
 
-    // ---- phase 1: element forces, accumulated per owned node ------------------------------
-    const int eb = A.elem_off[t], ne = A.elem_off[t + 1] - eb;
-    for (int base = 0; base < ne; base += nthr) {
-        const int le = base + tid;
-        const bool act = le < ne;
-        double fx[8], fy[8], fz[8];
-        uint32_t sl[8];
-#pragma unroll
-        for (int j = 0; j < 8; j++) { sl[j] = 0xffffu; fx[j] = fy[j] = fz[j] = 0.0; }
-        if (act) {
-            const uint4 s4 = __ldg(A.elem_slot + eb + le);
-            sl[0] = s4.x & 0xffffu; sl[1] = s4.x >> 16; sl[2] = s4.y & 0xffffu; sl[3] = s4.y >> 16;
-            sl[4] = s4.z & 0xffffu; sl[5] = s4.z >> 16; sl[6] = s4.w & 0xffffu; sl[7] = s4.w >> 16;
-            const int e = __ldg(A.elem_id + eb + le);
-            const double2 c12 = __ldg(reinterpret_cast<const double2 *>(A.etab + 4 * (size_t)e));
-            double beta = 0.0;
-            if (NEED_U2) {
-                const double2 c34 = __ldg(reinterpret_cast<const double2 *>(A.etab + 4 * (size_t)e) + 1);
-                // c3/c1 == c4/c2 == b/dt by construction (psolve.c:3387-3409)
-                beta = (c12.x != 0.0) ? A.s_du * (c34.x / c12.x) : 0.0;
+template <int MODE, bool DENSE>
+__global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
+{
+    constexpr bool U2E = MODE != 0;          // elements read u2
+    extern __shared__ double smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int S3 = 3 * A.cap_slots, O3 = 3 * A.cap_owned;
+    const int stage_doubles = S3 + (U2E ? S3 : O3);
+    double *acc = smem + 2 * stage_doubles;
+    const bool fuse = A.fuse_update != 0;
+
+    int t = blockIdx.x;
+    if (t >= A.ntiles) return;
+    for (int k = tid; k < O3; k += nthr) acc[k] = 0.0;
+    TileMeta cur = load_meta(A, t), nxt = cur;
+    if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr);
+    else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr);
+    cp_async_commit();
+    Entry ecur;
+    if (tid < cur.ne) ecur = load_entry<U2E>(A, cur.eb + tid);
+
+    for (int it = 0;; it++) {
+        double *su1 = smem + (it & 1) * stage_doubles;
+        double *su2 = su1 + S3;
+        const int tn = t + gridDim.x;
+        const bool has_next = tn < A.ntiles;
+        cp_async_wait_all();
+        __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1
+        if (has_next) {
+            nxt = load_meta(A, tn);
+            double *n1 = smem + ((it + 1) & 1) * stage_doubles;
+            if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr);
+            else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr);
+            cp_async_commit();
+        }
+        const int nown3 = 3 * cur.nown;
+
+        // ---- element forces, accumulated per owned node ------------------------------------
+        for (int base = 0; base < cur.ne; base += nthr) {
+            const bool act = base + tid < cur.ne;
+            // next round's entry (or the first round of the next tile) rides along with the math
+            Entry enext;
+            bool have_next_entry = false;
+            if (base + nthr < cur.ne) {
+                if (base + nthr + tid < cur.ne) { enext = load_entry<U2E>(A, cur.eb + base + nthr + tid); have_next_entry = true; }
+            } else if (has_next && tid < nxt.ne) {
+                enext = load_entry<U2E>(A, nxt.eb + tid); have_next_entry = true;
             }
-            // w = s_u1 * u1 + beta * (u1 - u2), per corner and component
-            double wx[8], wy[8], wz[8];
+            double fx[8], fy[8], fz[8];
+            uint32_t sl[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { sl[j] = 0xffffffffu; fx[j] = fy[j] = fz[j] = 0.0; }
+            if (act) {
+                sl[0] = ecur.s.x & 0xffffu; sl[1] = ecur.s.x >> 16; sl[2] = ecur.s.y & 0xffffu; sl[3] = ecur.s.y >> 16;
+                sl[4] = ecur.s.z & 0xffffu; sl[5] = ecur.s.z >> 16; sl[6] = ecur.s.w & 0xffffu; sl[7] = ecur.s.w >> 16;
+                double wx[8], wy[8], wz[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int o = sl[j];
+                    const double ax = su1[o], ay = su1[o + 1], az = su1[o + 2];
+                    if (MODE == 0) { wx[j] = ax; wy[j] = ay; wz[j] = az; }
+                    else {
+                        const double dx = ax - su2[o], dy = ay - su2[o + 1], dz = az - su2[o + 2];
+                        if (MODE == 1) { wx[j] = fma(ecur.beta, dx, ax); wy[j] = fma(ecur.beta, dy, ay); wz[j] = fma(ecur.beta, dz, az); }
+                        else           { wx[j] = ecur.beta * dx; wy[j] = ecur.beta * dy; wz[j] = ecur.beta * dz; }
+                    }
+                }
+                if (!DENSE) {
+                    double tx[8], ty[8], tz[8];
+                    wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+                    const double a = -0.5625 * (ecur.c2 + 2.0 * ecur.c1);
+                    const double c = -0.5625 * ecur.c2;
+                    const double b = -0.5625 * ecur.c1;
+                    scale_modes(tx, ty, tz, a, c, b, wx, wy, wz);   // reuse w* as the scaled modes
+                    wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
+                } else {
+                    // conventional form (stiffness.c:143-162): f_i = -c1 K1[i][j] w_j - c2 K2[i][j] w_j,
+                    // K1|K2 stored as two 24x24 row-major matrices (row = 3 i + k, col = 3 j + l)
+                    const double *K1 = A.Kd, *K2 = A.Kd + 576;
+#pragma unroll 1
+                    for (int i = 0; i < 8; i++) {
+                        double r[3];
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const double *r1 = K1 + 24 * (3 * i + k), *r2 = K2 + 24 * (3 * i + k);
+                            double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+                            for (int j = 0; j < 8; j++) {
+                                s1 = fma(__ldg(r1 + 3 * j), wx[j], s1); s1 = fma(__ldg(r1 + 3 * j + 1), wy[j], s1);
+                                s1 = fma(__ldg(r1 + 3 * j + 2), wz[j], s1);
+                                s2 = fma(__ldg(r2 + 3 * j), wx[j], s2); s2 = fma(__ldg(r2 + 3 * j + 1), wy[j], s2);
+                                s2 = fma(__ldg(r2 + 3 * j + 2), wz[j], s2);
+                            }
+                            r[k] = -ecur.c1 * s1 - ecur.c2 * s2;
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; jj++)
+                            if (jj == i) { fx[jj] = r[0]; fy[jj] = r[1]; fz[jj] = r[2]; }
+                    }
+                }
+            }
+            // A node is corner j of at most one element (leaf octants do not overlap), so within
+            // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                const int o = 3 * sl[j];
-                const double ax = su1[o], ay = su1[o + 1], az = su1[o + 2];
-                if (NEED_U2) {
-                    wx[j] = fma(beta, ax - su2[o], A.s_u1 * ax);
-                    wy[j] = fma(beta, ay - su2[o + 1], A.s_u1 * ay);
-                    wz[j] = fma(beta, az - su2[o + 2], A.s_u1 * az);
-                } else {
-                    wx[j] = A.s_u1 * ax; wy[j] = A.s_u1 * ay; wz[j] = A.s_u1 * az;
+                if (sl[j] < (uint32_t)nown3) {
+                    const int o = sl[j];
+                    acc[o] += fx[j]; acc[o + 1] += fy[j]; acc[o + 2] += fz[j];
                 }
+                __syncthreads();
             }
-            if (!DENSE) {
-                double tx[8], ty[8], tz[8];
-                wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
-                const double a = -0.5625 * (c12.y + 2.0 * c12.x);
-                const double c = -0.5625 * c12.y;
-                const double b = -0.5625 * c12.x;
-                scale_modes(tx, ty, tz, a, c, b, wx, wy, wz);   // reuse w* as the scaled modes
-                wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
-            } else {
-                // conventional form (stiffness.c:143-162): f_i = -c1 K1[i][j] w_j - c2 K2[i][j] w_j,
-                // K1|K2 stored as two 24x24 row-major matrices (row = 3 i + k, col = 3 j + l)
-                const double *K1 = A.Kd, *K2 = A.Kd + 576;
-#pragma unroll 1
-                for (int i = 0; i < 8; i++) {
-                    double r[3];
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        const double *r1 = K1 + 24 * (3 * i + k), *r2 = K2 + 24 * (3 * i + k);
-                        double s1 = 0.0, s2 = 0.0;
-#pragma unroll
-                        for (int j = 0; j < 8; j++) {
-                            s1 = fma(__ldg(r1 + 3 * j), wx[j], s1); s1 = fma(__ldg(r1 + 3 * j + 1), wy[j], s1);
-                            s1 = fma(__ldg(r1 + 3 * j + 2), wz[j], s1);
-                            s2 = fma(__ldg(r2 + 3 * j), wx[j], s2); s2 = fma(__ldg(r2 + 3 * j + 1), wy[j], s2);
-                            s2 = fma(__ldg(r2 + 3 * j + 2), wz[j], s2);
-                        }
-                        r[k] = -c12.x * s1 - c12.y * s2;
-                    }
-                    // i is a runtime index here; write through a switch-free select
-#pragma unroll
-                    for (int jj = 0; jj < 8; jj++)
-                        if (jj == i) { fx[jj] = r[0]; fy[jj] = r[1]; fz[jj] = r[2]; }
-                }
-            }
+            if (have_next_entry) ecur = enext;
         }
-        // A node is corner j of at most one element (leaf octants do not overlap), so within
-        // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            if (sl[j] < (uint32_t)nown) {
-                const int o = 3 * sl[j];
-                acc[o] += fx[j]; acc[o + 1] += fy[j]; acc[o + 2] += fz[j];
-            }
-            __syncthreads();
-        }
-    }
 
-    // ---- phase 2: per owned node component: fused update, or hand the force on --------------
-    for (int k = tid; k < 3 * nown; k += nthr) {
-        const int i = k / 3;
-        const size_t g = 3 * (size_t)n0 + k;
-        const double F = acc[k];
-        if (A.fuse_update && A.ncls[n0 + i] == NODE_REGULAR) {
-            const double p = NEED_U2 ? su2[k] : __ldg(A.u2 + g);
-            const double nf = F + (__ldg(A.m2 + g) * su1[k] - __ldg(A.m1 + g) * p);
-            A.unext[g] = nf / __ldg(A.mass + n0 + i);
-        } else {
-            A.force[g] += F;
+        // ---- per owned node component: fused update, or hand the force on ---------------------
+        {
+            const size_t g0 = 3 * (size_t)cur.n0;
+            for (int k = tid; k < nown3; k += nthr) {
+                const double F = acc[k];
+                acc[k] = 0.0;
+                const size_t g = g0 + k;
+                bool done = false;
+                if (fuse) {
+                    const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + k / 3);
+                    const double rm = __ldg(nt);
+                    if (rm > 0.0) {
+                        const double nf = F + (__ldg(nt + 1) * su1[k] - __ldg(nt + 2) * su2[k]);
+                        A.unext[g] = nf * rm;
+                        done = true;
+                    }
+                }
+                if (!done) A.force[g] += F;
+            }
         }
+        if (!has_next) break;
+        t = tn;
+        cur = nxt;
     }
 }
 

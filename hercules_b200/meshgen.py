@@ -346,7 +346,12 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
                            np.concatenate(maps).astype(np.int32))
         notmine = cand[~mine_c]
         msg["an_c"] = make_list(notmine, owner[notmine].astype(np.int64))
-        # s-lists: (node, sharer) for nodes I own; a node's sharers in ascending rank order
+        # s-lists: (node, sharer) for nodes I own.  A node's share list holds its sharers in the
+        # order this rank discovered its neighbour ranks (octor.c:5701-5785 pushes onto the list
+        # while walking the pctl list, itself pushed in discovery order by com_allocpctl,
+        # octor.c:2639-2742: leaves in Morton order, 4x4x4 probe points per leaf, z outermost).
+        disc = _discovery_order(mi, ex, ey, ez, (x0, y0, z0), (X, Y, Z), rank, world)
+        pos = {p: i for i, p in enumerate(disc)}
         sh_nodes, sh_peers = [], []
         ar = adj_rank[mine_c]
         own_nodes = cand[mine_c]
@@ -358,7 +363,9 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
                 new &= r != ar_sorted[:, col - 1]
             sh_nodes.append(own_nodes[new]); sh_peers.append(r[new])
         sh_nodes, sh_peers = np.concatenate(sh_nodes), np.concatenate(sh_peers)
-        o = np.lexsort((sh_peers, sh_nodes))                  # by node, then by sharer rank
+        sh_pos = np.array([pos[int(p)] for p in np.unique(sh_peers)], np.int64)
+        lut = np.zeros(world, np.int64); lut[np.unique(sh_peers)] = sh_pos
+        o = np.lexsort((lut[sh_peers], sh_nodes))             # by node, then by discovery order
         sh_nodes, sh_peers = sh_nodes[o], sh_peers[o]
         share = np.stack([sh_nodes, sh_peers], 1).astype(np.int32)
         msg["an_s"] = make_list(sh_nodes, sh_peers)
@@ -393,6 +400,45 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
                 dims=(nx, ny, nz), h=h, owner=owner, share=share, rank=rank, nranks=world,
                 etotal=Etot)
     return mesh, info
+
+
+def _discovery_order(mi, ex, ey, ez, origin, shape, rank, world):
+    """Neighbour ranks in the order com_allocpctl (octor.c:2639-2742) first meets them."""
+    nx, ny, nz = mi.dims
+    x0, y0, z0 = origin
+    X, Y, Z = shape
+    mine = np.zeros((X + 1, Y + 1, Z + 1), bool)
+    mine[ex - x0 + 1, ey - y0 + 1, ez - z0 + 1] = True
+    gxs, gys, gzs = np.arange(x0 - 1, x0 + X), np.arange(y0 - 1, y0 + Y), np.arange(z0 - 1, z0 + Z)
+    ok = mine | ((gxs < 0) | (gxs >= nx))[:, None, None] | ((gys < 0) | (gys >= ny))[None, :, None] | \
+        ((gzs < 0) | (gzs >= nz))[None, None, :]
+    # elements with a foreign in-domain neighbour among the 26 around them
+    pad = np.pad(ok, 1, constant_values=True)
+    inner = np.ones_like(ok)
+    for dz in (0, 1, 2):
+        for dy in (0, 1, 2):
+            for dx in (0, 1, 2):
+                inner &= pad[dx:dx + X + 1, dy:dy + Y + 1, dz:dz + Z + 1]
+    bsel = np.nonzero(~inner[ex - x0 + 1, ey - y0 + 1, ez - z0 + 1])[0]     # local element order
+    bx, by, bz = ex[bsel], ey[bsel], ez[bsel]
+    first = {}
+    d = (-1, 0, 0, 1)
+    for k in range(4):
+        for j in range(4):
+            for i in range(4):
+                px, py, pz = bx + d[i], by + d[j], bz + d[k]
+                inb = (px >= 0) & (px < nx) & (py >= 0) & (py < ny) & (pz >= 0) & (pz < nz)
+                if not inb.any():
+                    continue
+                r = block_owner(mi.index(px[inb], py[inb], pz[inb]), world, mi.total)
+                keyv = bsel[inb].astype(np.int64) * 64 + (k * 16 + j * 4 + i)
+                for p in np.unique(r):
+                    if p == rank:
+                        continue
+                    m = int(keyv[r == p].min())
+                    if p not in first or m < first[p]:
+                        first[int(p)] = m
+    return [p for p, _ in sorted(first.items(), key=lambda kv: kv[1])]
 
 
 def _slice_of(ml: MsgList, peer: int) -> slice:

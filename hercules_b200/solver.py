@@ -243,3 +243,15 @@ class Solver:
         t = _lib.Layout()
         _chk(self._L.hgpu_get_layout(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in t._fields_}
+
+
+def plan_build(elem_lnid, nharbored: int, tile_nodes: int = 0) -> dict:
+    """Host-only: build and self-check the tile plan for a mesh (no GPU needed); returns its sizes."""
+    L = _lib.lib()
+    lnid = np.ascontiguousarray(elem_lnid, np.int32).reshape(-1, 8)
+    m = _lib.Mesh()
+    m.lenum, m.nharbored, m.ldnnum = lnid.shape[0], int(nharbored), 0
+    m.elem_lnid = _p(lnid, C.c_int32)
+    out = _lib.Layout()
+    _chk(L.hgpu_plan_build(C.byref(m), tile_nodes, C.byref(out)))
+    return {n: getattr(out, n) for n, _ in out._fields_}

@@ -96,7 +96,7 @@ typedef struct hgpu_params {
     int32_t nloaded;            /* Global.theNodesLoaded   */
     const int32_t *loaded_lnid; /* Global.theNodesLoadedList [nloaded] */
     int32_t device;             /* CUDA device ordinal, -1 = rank % device count */
-    int32_t tile_nodes;         /* nodes per tile, 0 = default   */
+    int32_t tile_nodes;         /* cap on owned nodes per tile, 0 = default */
     int32_t flags;              /* HGPU_FLAG_* */
 } hgpu_params_t;
 
@@ -196,8 +196,12 @@ typedef struct hgpu_layout {
     int64_t n_regular, n_special;
     int64_t device_bytes;
     int32_t smem_bytes, block_threads;
+    int32_t grid_ctas, ctas_per_sm;   /* persistent step kernel: CTAs launched, resident per SM */
 } hgpu_layout_t;
 int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out);
+/* Host-only (no device needed): build and self-check the tile plan hgpu_init would use for this
+ * mesh on a B200 and report its sizes.  Only lenum, nharbored and elem_lnid are read. */
+int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu_layout_t *out);
 
 #ifdef __cplusplus
 }

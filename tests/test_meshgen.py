@@ -26,3 +26,35 @@ def test_uniform_mesh_matches_octor_and_solver_init():
     # the fast (grouped) accumulation differs only by rounding
     fast, _ = meshgen.uniform_halfspace(16, 16, 8, h=62.5, dt=P["dt"], freq=P["freq"], damping=P["damping"])
     assert np.allclose(fast.nTable, g["nTable"], rtol=1e-13, atol=0)
+
+
+import pytest
+
+
+@pytest.mark.parametrize("name,world", [("uniform_rayleigh_eff_np3", 3), ("uniform_rayleigh_eff_np4", 4)])
+def test_partition_matches_octor(name, world):
+    """Mesh and partition indexing bit-exact with octor_partitiontree / octor_extractmesh and
+    schedule_build on a multi-rank run of the unmodified reference: element blocks (geid), local
+    node numbering, ownership, sharer lists, halo schedules; and the exchanged nTable."""
+    from conftest import rank_view
+    from hercules_b200 import meshgen
+    g = load_golden(name)
+    for r in range(world):
+        v = rank_view(g, r); P = params_of(v)
+        mesh, info = meshgen.uniform_halfspace(16, 16, 8, h=62.5, dt=P["dt"], freq=P["freq"],
+                                               damping=P["damping"], exact=True, part=(r, world))
+        assert np.array_equal(info["elem_geid"], v["elem_geid"])
+        assert np.array_equal(mesh.elem_lnid, v["elem_lnid"])
+        h = int(v["node_ticks"][v["node_ticks"] > 0].min())
+        assert np.array_equal(np.stack(info["node_xyz"], 1) * h, v["node_ticks"])
+        ismine = v["node_flags"][:, 0].astype(bool)
+        assert np.array_equal(info["owner"] == r, ismine)
+        assert np.array_equal(info["owner"][~ismine], v["node_owner"][~ismine])
+        assert np.array_equal(info["share"], v["node_share"])
+        for side in ("dn_c", "dn_s", "an_c", "an_s"):
+            ml = getattr(mesh, side)
+            hdr = np.stack([ml.peer, ml.nodes], 1).reshape(-1, 2)
+            assert np.array_equal(hdr, v[side + "_hdr"].reshape(-1, 2)), (r, side)
+            assert np.array_equal(ml.mapping, v[side + "_map"]), (r, side)
+        assert np.array_equal(mesh.eTable, v["eTable"])
+        assert np.array_equal(mesh.nTable, v["nTable"]), r
