@@ -46,7 +46,8 @@ class Layout(C.Structure):
     _fields_ = [("tile_nodes", i32), ("ntiles", i32), ("max_tile_nodes", i32),
                 ("max_tile_elems", i32), ("tile_elems_total", i64), ("tile_halo_total", i64),
                 ("n_regular", i64), ("n_special", i64), ("device_bytes", i64),
-                ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32)]
+                ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32),
+                ("est_gather_wavefronts", f64), ("est_scatter_wavefronts", f64)]
 
 
 # every symbol include/hercules_gpu.h declares: name -> (restype, argtypes)

@@ -260,7 +260,7 @@ static void tile_caps(int max_smem, int32_t tile_nodes, int32_t *cap_owned_o, in
         cap_owned = (per_cta / 8 / 18) & ~1;       // owned : staged about 1 : 1.25
         cap_slots = (per_cta / 8 - 3 * cap_owned) / 12;
     }
-    cap_slots = std::min(cap_slots, 65535 / 3);
+    cap_slots = std::min(cap_slots, 65535 / 3) & ~15;  // 3*cap_slots doubles = whole 128-byte rows per array
     *cap_owned_o = cap_owned; *cap_slots_o = cap_slots; *elem_block_o = elem_block;
 }
 
@@ -438,7 +438,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRY(upload(s, &s->t_halo_off, pl.halo_off.data(), pl.halo_off.size()));
         TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
         // shared memory actually needed by this plan
-        s->cap_slots = pl.max_tile_nodes; s->cap_owned = (pl.max_tile_owned + 1) & ~1;
+        s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_owned = (pl.max_tile_owned + 15) & ~15;
         s->smem_u2 = (12 * s->cap_slots + 3 * s->cap_owned) * (int)sizeof(double);
         s->smem_nou2 = (6 * s->cap_slots + 9 * s->cap_owned) * (int)sizeof(double);
         const char *benv = getenv("HGPU_BLOCK");
@@ -922,8 +922,9 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     out->tile_nodes = pl.max_tile_owned; out->ntiles = pl.ntiles;
     out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
     out->tile_elems_total = (int64_t)pl.elem_id.size();
-    out->tile_halo_total = (int64_t)pl.halo_id.size();
-    out->smem_bytes = (12 * pl.max_tile_nodes + 3 * ((pl.max_tile_owned + 1) & ~1)) * (int)sizeof(double);
+    out->tile_halo_total = pl.halo_nodes_total;
+    estimate_wavefronts(pl, &out->est_gather_wavefronts, &out->est_scatter_wavefronts);
+    out->smem_bytes = (12 * ((pl.max_tile_nodes + 15) & ~15) + 3 * ((pl.max_tile_owned + 15) & ~15)) * (int)sizeof(double);
     out->block_threads = 256;
     return HGPU_OK;
 }
@@ -935,7 +936,8 @@ extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
     out->tile_nodes = pl.max_tile_owned; out->ntiles = pl.ntiles;
     out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
     out->tile_elems_total = (int64_t)pl.elem_id.size();
-    out->tile_halo_total = (int64_t)pl.halo_id.size();
+    out->tile_halo_total = pl.halo_nodes_total;
+    estimate_wavefronts(pl, &out->est_gather_wavefronts, &out->est_scatter_wavefronts);
     out->n_regular = s->n_regular; out->n_special = s->n_special;
     out->device_bytes = s->device_bytes;
     out->smem_bytes = s->smem_u2; out->block_threads = s->block;

@@ -28,7 +28,8 @@ struct TilePlan {
     std::vector<int32_t>  elem_id;    // element evaluated by this tile entry
     std::vector<uint16_t> elem_slot;  // [entries][8] tile-local slot of each corner node
     std::vector<int32_t>  halo_off;   // [ntiles+1] into halo_id
-    std::vector<int32_t>  halo_id;    // gathered (non-owned) node ids; slot = owned_count + index
+    std::vector<int32_t>  halo_id;    // gathered (non-owned) node ids; slot = owned_count + index; -1 = unused slot
+    int64_t halo_nodes_total = 0;     // gathered nodes over all tiles (unused slots not counted)
 };
 
 // Builds the plan; returns false and sets err on inconsistent input.
@@ -36,6 +37,8 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
                      int32_t max_owned, int32_t max_slots, TilePlan &plan, std::string &err);
 
 bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePlan &plan, std::string &err);
+
+void estimate_wavefronts(const TilePlan &plan, double *gather, double *scatter);
 
 // Hanging-node lists (flattened dnode_t, octor.h:153-158).
 struct DanglingPlan {

@@ -153,35 +153,69 @@ __device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+struct Entry { uint4 s; double c1, c2, beta; };
+
+// Loads that must be ISSUED where they are written (register prefetch one round / one phase ahead
+// of their use): volatile asm keeps the compiler from sinking them next to the consumer.
+__device__ __forceinline__ double ldg_f64_pinned(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_u4_pinned(const uint4 *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ldg_i32_pinned(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+
 struct TileMeta { int n0, nown, hb, nh, eb, ne; };
 
 __device__ __forceinline__ TileMeta load_meta(const StepArgs &A, int t)
 {
     TileMeta m;
-    m.n0 = __ldg(A.node_off + t); m.nown = __ldg(A.node_off + t + 1) - m.n0;
-    m.hb = __ldg(A.halo_off + t); m.nh = __ldg(A.halo_off + t + 1) - m.hb;
-    m.eb = __ldg(A.elem_off + t); m.ne = __ldg(A.elem_off + t + 1) - m.eb;
+    m.n0 = ldg_i32_pinned(A.node_off + t); m.nown = ldg_i32_pinned(A.node_off + t + 1) - m.n0;
+    m.hb = ldg_i32_pinned(A.halo_off + t); m.nh = ldg_i32_pinned(A.halo_off + t + 1) - m.hb;
+    m.eb = ldg_i32_pinned(A.elem_off + t); m.ne = ldg_i32_pinned(A.elem_off + t + 1) - m.eb;
     return m;
 }
-
-struct Entry { uint4 s; double c1, c2, beta; };
 
 template <bool NEED_BETA>
 __device__ __forceinline__ Entry load_entry(const StepArgs &A, int idx)
 {
     Entry e;
-    e.s = __ldg(A.ent_slot + idx);
+    e.s = ldg_u4_pinned(A.ent_slot + idx);
     const double *c = A.ent_coef + 3 * (size_t)idx;
-    e.c1 = __ldg(c); e.c2 = __ldg(c + 1);
-    e.beta = NEED_BETA ? __ldg(c + 2) : 0.0;
+    e.c1 = ldg_f64_pinned(c); e.c2 = ldg_f64_pinned(c + 1);
+    e.beta = NEED_BETA ? ldg_f64_pinned(c + 2) : 0.0;
     return e;
 }
 
 // Stage the displacements of one tile: su1 (and su2) <- owned range + gathered halo nodes.
-// U2_OWNED: copy the owned part of u2; U2_HALO: also its halo part.
+// U2_OWNED: copy the owned part of u2; U2_HALO: also its halo part.  The ids of the first
+// HALO_PRE * blockDim.x halo nodes are loaded by the caller ahead of time (hid[]).
+constexpr int HALO_PRE = 2;
+
+__device__ __forceinline__ void load_halo_ids(const StepArgs &A, const TileMeta &m, int tid, int nthr,
+                                              int (&hid)[HALO_PRE])
+{
+#pragma unroll
+    for (int q = 0; q < HALO_PRE; q++) {
+        const int h = tid + q * nthr;
+        hid[q] = h < m.nh ? ldg_i32_pinned(A.halo_id + m.hb + h) : -1;
+    }
+}
+
 template <bool U2_OWNED, bool U2_HALO>
 __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m, double *su1, double *su2,
-                                           int tid, int nthr)
+                                           int tid, int nthr, const int (&hid)[HALO_PRE])
 {
     const int nd = 3 * m.nown, nv = nd >> 1;
     const double *g1 = A.u1 + 3 * (size_t)m.n0, *g2 = A.u2 + 3 * (size_t)m.n0;
@@ -193,11 +227,58 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m,
         cp_async8(su1 + nd - 1, g1 + nd - 1);
         if (U2_OWNED) cp_async8(su2 + nd - 1, g2 + nd - 1);
     }
-    for (int i = tid; i < 3 * m.nh; i += nthr) {
-        const int h = i / 3, c = i - 3 * h;
-        const size_t g = 3 * (size_t)__ldg(A.halo_id + m.hb + h) + c;
-        cp_async8(su1 + nd + i, A.u1 + g);
-        if (U2_HALO) cp_async8(su2 + nd + i, A.u2 + g);
+    // gathered nodes: one thread per node, three 8-byte copies per array
+#pragma unroll
+    for (int q = 0; q < HALO_PRE; q++) {
+        const int h = tid + q * nthr;
+        if (h < m.nh && hid[q] >= 0) {        // -1 = slot left unused by the plan
+            const size_t g = 3 * (size_t)hid[q];
+            double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
+            cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
+            if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
+        }
+    }
+    for (int h = tid + HALO_PRE * nthr; h < m.nh; h += nthr) {
+        const int id = __ldg(A.halo_id + m.hb + h);
+        if (id < 0) continue;
+        const size_t g = 3 * (size_t)id;
+        double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
+        cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
+        if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
+    }
+}
+
+constexpr int NT_PRE = 3;
+
+__device__ __forceinline__ void load_node_tables(const StepArgs &A, const TileMeta &m, int tid, int nthr,
+                                                 double (&ntv)[NT_PRE][3])
+{
+#pragma unroll
+    for (int q = 0; q < NT_PRE; q++) {
+        const int i = tid + q * nthr;
+        if (i < m.nown) {
+            const double *nt = A.nt3 + 3 * (size_t)(m.n0 + i);
+            ntv[q][0] = ldg_f64_pinned(nt); ntv[q][1] = ldg_f64_pinned(nt + 1); ntv[q][2] = ldg_f64_pinned(nt + 2);
+        } else {
+            ntv[q][0] = ntv[q][1] = ntv[q][2] = 0.0;
+        }
+    }
+}
+
+// solver_compute_displacement (psolve.c:4078-4108) for one owned node whose force is complete in
+// acc: acc <- u(t+dt).  rm <= 0 flags a node that is advanced later from the force array.
+__device__ __forceinline__ void advance_node(const StepArgs &A, double *acc, const double *su1,
+                                             const double *su2, size_t g0, int i, double rm, double m2,
+                                             double m1)
+{
+    const int k = 3 * i;
+    if (rm > 0.0) {
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+            acc[k + c] = (acc[k + c] + (m2 * su1[k + c] - m1 * su2[k + c])) * rm;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 3; c++) A.force[g0 + k + c] += acc[k + c];
     }
 }
 
@@ -212,47 +293,63 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
     double *acc = smem + 2 * stage_doubles;
     const bool fuse = A.fuse_update != 0;
 
+    // Register pipeline.  All global loads of a warp share one hardware scoreboard, so a consumer
+    // waits for EVERY load issued before it, however young.  Each prefetch is therefore consumed
+    // (moved out of its landing registers) right BEFORE the next batch of loads is issued:
+    //   entries   : enext is copied to ecur at the top of a round, then the following round's
+    //               entry is requested
+    //   tile meta : tile t+2G is requested at the top of tile t
+    //   halo ids  : those of tile t+G... are requested before the accumulation passes of the last
+    //               round of tile t-... (one tile ahead of the cp.async that needs them)
+    const int G = gridDim.x;
     int t = blockIdx.x;
     if (t >= A.ntiles) return;
     for (int k = tid; k < O3; k += nthr) acc[k] = 0.0;
-    TileMeta cur = load_meta(A, t), nxt = cur;
-    if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr);
-    else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr);
+    TileMeta cur = load_meta(A, t), nxt = cur, nn = cur;
+    int hid[HALO_PRE];
+    load_halo_ids(A, cur, tid, nthr, hid);
+    if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr, hid);
+    else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr, hid);
     cp_async_commit();
-    Entry ecur;
-    if (tid < cur.ne) ecur = load_entry<U2E>(A, cur.eb + tid);
+    if (t + G < A.ntiles) { nxt = load_meta(A, t + G); load_halo_ids(A, nxt, tid, nthr, hid); }
+    Entry ecur, enext;
+    enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
+    if (tid < cur.ne) enext = load_entry<U2E>(A, cur.eb + tid);
 
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
         double *su2 = su1 + S3;
-        const int tn = t + gridDim.x;
+        const int tn = t + G;
         const bool has_next = tn < A.ntiles;
         cp_async_wait_all();
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1
         if (has_next) {
-            nxt = load_meta(A, tn);
             double *n1 = smem + ((it + 1) & 1) * stage_doubles;
-            if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr);
-            else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr);
+            if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
+            else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             cp_async_commit();
         }
+        const bool has_nn = tn + G < A.ntiles;
         const int nown3 = 3 * cur.nown;
+
+        // node tables of the (up to NT_PRE) owned nodes this thread advances, prefetched into
+        // registers before the last round's accumulation passes
+        double ntv[NT_PRE][3];
+        bool nt_loaded = false;
 
         // ---- element forces, accumulated per owned node ------------------------------------
         for (int base = 0; base < cur.ne; base += nthr) {
             const bool act = base + tid < cur.ne;
+            ecur = enext;
             // next round's entry (or the first round of the next tile) rides along with the math
-            Entry enext;
-            bool have_next_entry = false;
             if (base + nthr < cur.ne) {
-                if (base + nthr + tid < cur.ne) { enext = load_entry<U2E>(A, cur.eb + base + nthr + tid); have_next_entry = true; }
+                if (base + nthr + tid < cur.ne) enext = load_entry<U2E>(A, cur.eb + base + nthr + tid);
             } else if (has_next && tid < nxt.ne) {
-                enext = load_entry<U2E>(A, nxt.eb + tid); have_next_entry = true;
+                enext = load_entry<U2E>(A, nxt.eb + tid);
             }
+            if (base == 0 && has_nn) nn = load_meta(A, tn + G);
             double fx[8], fy[8], fz[8];
             uint32_t sl[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) { sl[j] = 0xffffffffu; fx[j] = fy[j] = fz[j] = 0.0; }
             if (act) {
                 sl[0] = ecur.s.x & 0xffffu; sl[1] = ecur.s.x >> 16; sl[2] = ecur.s.y & 0xffffu; sl[3] = ecur.s.y >> 16;
                 sl[4] = ecur.s.z & 0xffffu; sl[5] = ecur.s.z >> 16; sl[6] = ecur.s.w & 0xffffu; sl[7] = ecur.s.w >> 16;
@@ -302,42 +399,61 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
                     }
                 }
             }
+            if (base + nthr >= cur.ne) {
+                if (fuse) { load_node_tables(A, cur, tid, nthr, ntv); nt_loaded = true; }
+                if (has_nn) load_halo_ids(A, nn, tid, nthr, hid);
+            }
             // A node is corner j of at most one element (leaf octants do not overlap), so within
             // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                if (sl[j] < (uint32_t)nown3) {
+                if (act && sl[j] < (uint32_t)nown3) {
                     const int o = sl[j];
                     acc[o] += fx[j]; acc[o + 1] += fy[j]; acc[o + 2] += fz[j];
                 }
                 __syncthreads();
             }
-            if (have_next_entry) ecur = enext;
+        }
+        if (cur.ne == 0) {                    // a tile of element-less nodes: keep the pipeline fed
+            if (has_next && tid < nxt.ne) enext = load_entry<U2E>(A, nxt.eb + tid);
+            if (has_nn) { nn = load_meta(A, tn + G); load_halo_ids(A, nn, tid, nthr, hid); }
         }
 
-        // ---- per owned node component: fused update, or hand the force on ---------------------
+        // ---- owned nodes: fused update, or hand the force on ------------------------------------
         {
             const size_t g0 = 3 * (size_t)cur.n0;
-            for (int k = tid; k < nown3; k += nthr) {
-                const double F = acc[k];
-                acc[k] = 0.0;
-                const size_t g = g0 + k;
-                bool done = false;
-                if (fuse) {
-                    const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + k / 3);
-                    const double rm = __ldg(nt);
-                    if (rm > 0.0) {
-                        const double nf = F + (__ldg(nt + 1) * su1[k] - __ldg(nt + 2) * su2[k]);
-                        A.unext[g] = nf * rm;
-                        done = true;
-                    }
+            if (fuse) {
+                if (!nt_loaded) load_node_tables(A, cur, tid, nthr, ntv);
+                // node-wise: u(t+dt) replaces the force in acc; nodes flagged in nt3 keep their force
+#pragma unroll
+                for (int q = 0; q < NT_PRE; q++) {
+                    const int i = tid + q * nthr;
+                    if (i < cur.nown) advance_node(A, acc, su1, su2, g0, i, ntv[q][0], ntv[q][1], ntv[q][2]);
                 }
-                if (!done) A.force[g] += F;
+                for (int i = tid + NT_PRE * nthr; i < cur.nown; i += nthr) {
+                    const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + i);
+                    advance_node(A, acc, su1, su2, g0, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
+                }
+                __syncthreads();
+                // coalesced 128-bit copy-out (g0 is even); rows of flagged nodes carry their force,
+                // which the special-node update overwrites afterwards
+                double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);
+                for (int v = tid; v < (nown3 >> 1); v += nthr) {
+                    dst[v] = make_double2(acc[2 * v], acc[2 * v + 1]);
+                    acc[2 * v] = 0.0; acc[2 * v + 1] = 0.0;
+                }
+                if ((nown3 & 1) && tid == 0) { A.unext[g0 + nown3 - 1] = acc[nown3 - 1]; acc[nown3 - 1] = 0.0; }
+            } else {
+                for (int k = tid; k < nown3; k += nthr) {
+                    A.force[g0 + k] += acc[k];
+                    acc[k] = 0.0;
+                }
             }
         }
         if (!has_next) break;
         t = tn;
         cur = nxt;
+        nxt = nn;
     }
 }
 

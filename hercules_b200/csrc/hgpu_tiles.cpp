@@ -7,7 +7,10 @@
 #include "hgpu_internal.h"
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <unordered_map>
 
 namespace hgpu {
 
@@ -64,6 +67,10 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
         cuts.push_back(N);
     }
 
+    const char *e1 = getenv("HGPU_PLAN_SORT"), *e2 = getenv("HGPU_PLAN_GREEDY");
+    const char *e3 = getenv("HGPU_PLAN_PACK");
+    const bool opt_sort = !(e1 && atoi(e1) == 0), opt_greedy = !(e2 && atoi(e2) == 0), opt_pack = !(e3 && atoi(e3) == 0);
+    std::unordered_map<std::string, std::vector<int32_t>> pack_cache;
     std::vector<int32_t> stamp_e((size_t)E, -1), stamp_n((size_t)N, -1), slot_of((size_t)N, 0);
     std::vector<int32_t> elems, halo;
     plan.node_off.push_back(0);
@@ -105,7 +112,131 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
             continue;
         }
         std::sort(halo.begin(), halo.end());
-        for (size_t h = 0; h < halo.size(); h++) slot_of[halo[h]] = nown + (int32_t)h;
+        // Entry order.  Threads take consecutive entries, and a shared-memory access of 16 lanes
+        // (one half-warp of 8-byte words) is conflict-free when the 16 slots differ modulo 16.
+        // "Core" entries -- corner 0 is an owned node -- sorted by that node are, in a uniform
+        // region, the tile's own Morton cell in Morton order: every aligned run of 16 is a 4x2x2
+        // block whose corner-j nodes have 16 different slot residues.  The remaining entries (the
+        // layers shared with lower neighbours) follow, sorted by their lowest owned corner.
+        {
+            auto key = [&](int32_t e) -> int64_t {
+                const int32_t *ln = lnid + 8 * (size_t)e;
+                if (ln[0] >= a && ln[0] < b) return (int64_t)(ln[0] - a);
+                int32_t lo = INT32_MAX;
+                for (int j = 1; j < 8; j++) if (ln[j] >= a && ln[j] < b) lo = std::min(lo, ln[j] - a);
+                return ((int64_t)1 << 32) + lo;
+            };
+            if (opt_sort) std::stable_sort(elems.begin(), elems.end(), [&](int32_t x, int32_t y) { return key(x) < key(y); });
+            // Non-core entries touch owned nodes on one face / edge of the patch only, whose slots
+            // share residues: pack them into half-warp groups of 16 greedily so that, corner by
+            // corner, the owned slots of a group collide as little as possible.  The packing
+            // depends only on the residue pattern, which repeats from tile to tile: memoised.
+            int32_t ncore = 0;
+            for (int32_t e : elems) { const int32_t n0c = lnid[8 * (size_t)e]; if (n0c >= a && n0c < b) ncore++; }
+            const int32_t nrest = (int32_t)elems.size() - ncore;
+            if (opt_sort && opt_pack && nrest > 1) {
+                // signature: residues (or 255) of the 8 corners of every non-core entry + the partial group
+                std::string sig;
+                sig.reserve((size_t)8 * (nrest + 16) + 4);
+                const int32_t g0 = ncore & ~15;                   // first entry of the partially filled group
+                for (int32_t k = g0; k < (int32_t)elems.size(); k++)
+                    for (int j = 0; j < 8; j++) {
+                        const int32_t n = lnid[8 * (size_t)elems[k] + j];
+                        sig.push_back((n >= a && n < b) ? (char)((n - a) & 15) : (char)-1);
+                    }
+                sig.push_back((char)(ncore & 15));
+                auto hit = pack_cache.find(sig);
+                std::vector<int32_t> perm;
+                if (hit != pack_cache.end()) perm = hit->second;
+                else {
+                    perm.reserve(nrest);
+                    std::vector<uint8_t> used((size_t)nrest, 0);
+                    int cnt[8][16];
+                    int32_t filled = ncore;                        // entries placed so far
+                    int32_t first_free = 0;
+                    while ((int32_t)perm.size() < nrest) {
+                        if ((filled & 15) == 0 || perm.empty()) {
+                            memset(cnt, 0, sizeof cnt);
+                            if (perm.empty())                      // core entries already in this group
+                                for (int32_t k = g0; k < ncore; k++)
+                                    for (int j = 0; j < 8; j++) {
+                                        const unsigned char r = (unsigned char)sig[(size_t)8 * (k - g0) + j];
+                                        if (r != 255) cnt[j][r]++;
+                                    }
+                        }
+                        while (first_free < nrest && used[first_free]) first_free++;
+                        int32_t best = -1, best_cost = 0, seen = 0;
+                        for (int32_t c = first_free; c < nrest && seen < 100000; c++) {
+                            if (used[c]) continue;
+                            seen++;
+                            int32_t cost = 0;
+                            const char *sg = sig.data() + (size_t)8 * (ncore - g0 + c);
+                            for (int j = 0; j < 8; j++) { const unsigned char r = (unsigned char)sg[j]; if (r != 255) cost += cnt[j][r]; }
+                            if (best < 0 || cost < best_cost) { best = c; best_cost = cost; if (!cost) break; }
+                        }
+                        used[best] = 1;
+                        perm.push_back(best);
+                        const char *sg = sig.data() + (size_t)8 * (ncore - g0 + best);
+                        for (int j = 0; j < 8; j++) { const unsigned char r = (unsigned char)sg[j]; if (r != 255) cnt[j][r]++; }
+                        filled++;
+                    }
+                    if (pack_cache.size() < 4096) pack_cache.emplace(sig, perm);
+                }
+                std::vector<int32_t> rest(elems.begin() + ncore, elems.end());
+                for (int32_t k = 0; k < nrest; k++) elems[(size_t)ncore + k] = rest[perm[k]];
+            }
+        }
+        // Halo slots: greedy choice of the slot residue (mod 16) that collides least with the other
+        // lanes of every half-warp access the node takes part in; most-referenced nodes first.
+        int32_t nslots = nown + (int32_t)halo.size();
+        {
+            const int32_t ne = (int32_t)elems.size(), ngrp = (ne + 15) / 16;
+            const int32_t limit = std::min(max_slots, (nown + (int32_t)halo.size() + 31) & ~15);
+            std::vector<uint8_t> cnt((size_t)ngrp * 8 * 16, 0);
+            std::vector<std::vector<int32_t>> refs(halo.size());     // (group * 8 + corner) per halo node
+            for (size_t h = 0; h < halo.size(); h++) slot_of[halo[h]] = -1 - (int32_t)h;   // index while unassigned
+            for (int32_t k = 0; k < ne; k++) {
+                const int32_t *ln = lnid + 8 * (size_t)elems[k];
+                for (int j = 0; j < 8; j++) {
+                    const int32_t n = ln[j];
+                    if (n >= a && n < b) cnt[((size_t)(k / 16) * 8 + j) * 16 + ((n - a) & 15)]++;
+                    else refs[(size_t)(-1 - slot_of[n])].push_back((k / 16) * 8 + j);
+                }
+            }
+            std::vector<int32_t> order(halo.size());
+            for (size_t h = 0; h < halo.size(); h++) order[h] = (int32_t)h;
+            std::stable_sort(order.begin(), order.end(),
+                             [&](int32_t x, int32_t y) { return refs[x].size() > refs[y].size(); });
+            std::vector<std::vector<int32_t>> freeslots(16);
+            for (int32_t sl = limit - 1; sl >= nown; sl--) freeslots[sl & 15].push_back(sl);   // pop_back = lowest
+            std::vector<int32_t> hslot(halo.size(), -1);
+            nslots = nown;
+            for (int32_t h : order) {
+                int best = -1; int64_t best_cost = 0; int32_t best_slot = 0;
+                for (int r = 0; r < 16; r++) {
+                    if (freeslots[r].empty()) continue;
+                    int64_t cost = 0;
+                    if (opt_greedy) for (int32_t gj : refs[h]) cost += cnt[(size_t)gj * 16 + r];
+                    const int32_t sl = freeslots[r].back();
+                    // equal cost: keep the staged range compact
+                    if (best < 0 || cost < best_cost || (cost == best_cost && sl < best_slot)) {
+                        best = r; best_cost = cost; best_slot = sl;
+                    }
+                }
+                if (best < 0) { err = "internal: no free halo slot"; return false; }
+                freeslots[best].pop_back();
+                hslot[h] = best_slot;
+                for (int32_t gj : refs[h]) cnt[(size_t)gj * 16 + best]++;
+                nslots = std::max(nslots, best_slot + 1);
+            }
+            // halo list in slot order, -1 marks an unused slot
+            const size_t base = plan.halo_id.size();
+            plan.halo_id.resize(base + (size_t)(nslots - nown), -1);
+            for (size_t h = 0; h < halo.size(); h++) {
+                plan.halo_id[base + (size_t)(hslot[h] - nown)] = halo[h];
+                slot_of[halo[h]] = hslot[h];
+            }
+        }
         for (int32_t e : elems) {
             plan.elem_id.push_back(e);
             for (int j = 0; j < 8; j++) {
@@ -115,12 +246,12 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
             }
         }
         if (plan.elem_id.size() > (size_t)INT32_MAX) { err = "tile plan exceeds 2^31 entries"; return false; }
-        plan.halo_id.insert(plan.halo_id.end(), halo.begin(), halo.end());
         plan.node_off.push_back(b);
         plan.elem_off.push_back((int32_t)plan.elem_id.size());
         plan.halo_off.push_back((int32_t)plan.halo_id.size());
         plan.max_tile_owned = std::max(plan.max_tile_owned, nown);
-        plan.max_tile_nodes = std::max(plan.max_tile_nodes, nown + (int32_t)halo.size());
+        plan.max_tile_nodes = std::max(plan.max_tile_nodes, nslots);
+        plan.halo_nodes_total += (int64_t)halo.size();
         plan.max_tile_elems = std::max(plan.max_tile_elems, (int32_t)elems.size());
         tile++;
     }
@@ -135,7 +266,7 @@ bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePla
 {
     if (pl.ntiles < 0 || (int32_t)pl.node_off.size() != pl.ntiles + 1) { err = "node_off size"; return false; }
     if (pl.node_off.front() != 0 || pl.node_off.back() != N) { err = "tiles do not cover the node range"; return false; }
-    std::vector<int32_t> degree((size_t)N, 0), seen((size_t)N, 0);
+    std::vector<int32_t> degree((size_t)N, 0), seen((size_t)N, 0), stamp((size_t)N, -1), stamp_slot((size_t)N, -1);
     for (int32_t e = 0; e < E; e++) for (int j = 0; j < 8; j++) degree[lnid[8 * (size_t)e + j]]++;
     for (int32_t t = 0; t < pl.ntiles; t++) {
         const int32_t a = pl.node_off[t], b = pl.node_off[(size_t)t + 1];
@@ -144,12 +275,12 @@ bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePla
         if (nown > pl.max_tile_owned || nown + nh > pl.max_tile_nodes) { err = "tile exceeds recorded maxima"; return false; }
         for (int32_t h = 0; h < nh; h++) {
             const int32_t n = pl.halo_id[(size_t)hb + h];
+            if (n < -1 || n >= N) { err = "halo id out of range"; return false; }
             if (n >= a && n < b) { err = "owned node listed as halo"; return false; }
-            if (h && n <= pl.halo_id[(size_t)hb + h - 1]) { err = "halo list not ascending"; return false; }
         }
         for (int32_t k = pl.elem_off[t]; k < pl.elem_off[(size_t)t + 1]; k++) {
             const int32_t e = pl.elem_id[k];
-            if (k > pl.elem_off[t] && e <= pl.elem_id[(size_t)k - 1]) { err = "element list not ascending"; return false; }
+            if (e < 0 || e >= E) { err = "element id out of range"; return false; }
             bool touches = false;
             for (int j = 0; j < 8; j++) {
                 const int32_t sl = pl.elem_slot[8 * (size_t)k + j];
@@ -157,6 +288,8 @@ bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePla
                 const int32_t n = sl < nown ? a + sl : pl.halo_id[(size_t)hb + sl - nown];
                 if (n != lnid[8 * (size_t)e + j]) { err = "slot decodes to the wrong node"; return false; }
                 if (sl < nown) { seen[n]++; touches = true; }
+                else if (stamp[n] == t && stamp_slot[n] != sl) { err = "halo node staged twice"; return false; }
+                else { stamp[n] = t; stamp_slot[n] = sl; }
             }
             if (!touches) { err = "tile evaluates an element that touches none of its nodes"; return false; }
         }
@@ -164,6 +297,57 @@ bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePla
     for (int32_t n = 0; n < N; n++)
         if (seen[n] != degree[n]) { err = "node " + std::to_string(n) + " misses incident elements"; return false; }
     return true;
+}
+
+// Shared-memory wavefronts per 8-byte access instruction of the step kernel under the bank model
+// "16 lanes per wavefront, 16 banks of 8 bytes": gather = the 8 corner reads of every entry,
+// scatter = the accumulator updates of owned corners.  2.0 per 32-lane instruction is ideal.
+void estimate_wavefronts(const TilePlan &pl, double *gather, double *scatter)
+{
+    int64_t gw = 0, gi = 0, sw = 0, si = 0;
+    const char *dbg = getenv("HGPU_PLAN_DEBUG");
+    bool printed = false;
+    for (int32_t t = 0; t < pl.ntiles; t++) {
+        const int32_t nown = pl.node_off[(size_t)t + 1] - pl.node_off[t];
+        const int32_t eb = pl.elem_off[t], ne = pl.elem_off[(size_t)t + 1] - eb;
+        if (dbg && atoi(dbg) > 0 && ne != atoi(dbg)) continue;      // only tiles with that many entries
+        if (t > 0 && gi > 0) printed = true;
+        for (int32_t w0 = 0; w0 < ne; w0 += 32) {
+            for (int j = 0; j < 8; j++) {
+                int any_owned = 0;
+                for (int half = 0; half < 2; half++) {
+                    int c_all[16] = {0}, c_own[16] = {0};
+                    for (int l = 0; l < 16; l++) {
+                        const int32_t k = w0 + 16 * half + l;
+                        if (k >= ne) break;
+                        const int32_t sl = pl.elem_slot[8 * (size_t)(eb + k) + j];
+                        c_all[sl & 15]++;
+                        if (sl < nown) { c_own[sl & 15]++; any_owned = 1; }
+                    }
+                    int ma = 0, mo = 0;
+                    for (int r = 0; r < 16; r++) { ma = std::max(ma, c_all[r]); mo = std::max(mo, c_own[r]); }
+                    gw += ma; sw += mo;
+                }
+                gi++; si += any_owned;
+            }
+            if (dbg && atoi(dbg) > 0 && !printed) {
+                fprintf(stderr, "tile %d warp %d: per corner gather:", t, w0 / 32);
+                for (int j = 0; j < 8; j++) {
+                    int tot = 0;
+                    for (int half = 0; half < 2; half++) {
+                        int c_all[16] = {0};
+                        for (int l = 0; l < 16; l++) { const int32_t k = w0 + 16 * half + l; if (k >= ne) break; c_all[pl.elem_slot[8 * (size_t)(eb + k) + j] & 15]++; }
+                        int ma = 0; for (int r = 0; r < 16; r++) ma = std::max(ma, c_all[r]);
+                        tot += ma;
+                    }
+                    fprintf(stderr, " %d", tot);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
+    }
+    *gather = gi ? (double)gw / (double)gi : 0.0;
+    *scatter = si ? (double)sw / (double)si : 0.0;
 }
 
 bool build_dangling_plan(int32_t N, int32_t D, const int32_t *dnode, DanglingPlan &plan,

@@ -197,6 +197,8 @@ typedef struct hgpu_layout {
     int64_t device_bytes;
     int32_t smem_bytes, block_threads;
     int32_t grid_ctas, ctas_per_sm;   /* persistent step kernel: CTAs launched, resident per SM */
+    /* modelled shared-memory wavefronts per 32-lane 8-byte access (2.0 = conflict-free) */
+    double est_gather_wavefronts, est_scatter_wavefronts;
 } hgpu_layout_t;
 int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out);
 /* Host-only (no device needed): build and self-check the tile plan hgpu_init would use for this

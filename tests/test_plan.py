@@ -27,7 +27,7 @@ def test_tile_plan_uniform_redundancy():
     from hercules_b200 import meshgen, solver
     mesh, info = meshgen.uniform_halfspace(32, 32, 32, h=25.0, dt=0.002)
     r = solver.plan_build(mesh.elem_lnid, info["N"])
-    assert r["max_tile_elems"] <= 729 and r["max_tile_nodes"] <= 1000
+    assert r["max_tile_elems"] <= 729 and r["max_tile_nodes"] <= 1008   # 10^3 staged + conflict-avoiding slack
     assert r["tile_elems_total"] / info["E"] < 1.43
 
 
