@@ -442,15 +442,20 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         s->smem_u2 = (12 * s->cap_slots + 3 * s->cap_owned) * (int)sizeof(double);
         s->smem_nou2 = (6 * s->cap_slots + 9 * s->cap_owned) * (int)sizeof(double);
         const char *benv = getenv("HGPU_BLOCK");
-        if (benv && atoi(benv) >= 64 && atoi(benv) <= 256) s->block = atoi(benv) & ~31;
-        TRYCU(cudaFuncSetAttribute(step_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
-        TRYCU(cudaFuncSetAttribute(step_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
-        TRYCU(cudaFuncSetAttribute(step_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
-        TRYCU(cudaFuncSetAttribute(step_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));
-        TRYCU(cudaFuncSetAttribute(step_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
-        TRYCU(cudaFuncSetAttribute(step_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));
+        if (benv && atoi(benv) == 384) s->block = 384;
         int occ = 0;
-        TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false>, s->block, s->smem_u2));
+#define SETUP(T)                                                                                             \
+        do {                                                                                                 \
+            TRYCU(cudaFuncSetAttribute(step_kernel<0, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2)); \
+            TRYCU(cudaFuncSetAttribute(step_kernel<1, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));   \
+            TRYCU(cudaFuncSetAttribute(step_kernel<2, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));   \
+            TRYCU(cudaFuncSetAttribute(step_kernel<0, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));  \
+            TRYCU(cudaFuncSetAttribute(step_kernel<1, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));    \
+            TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));    \
+            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
+        } while (0)
+        if (s->block == 384) SETUP(384); else SETUP(256);
+#undef SETUP
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
         s->ctas_per_sm = occ;
         s->grid = std::max(1, std::min(pl.ntiles, nsm * occ));
@@ -520,15 +525,20 @@ static int launch_tiles(hgpu_solver *s, bool fuse, bool *launched)
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (stiff ? PH_ADDFORCE_E : PH_DAMPING));
     if (s->plan.ntiles > 0) {
         const int G = s->grid, B = s->block;
-        if (dense) {
-            if (mode == 0)      step_kernel<0, true><<<G, B, s->smem_nou2, s->stream>>>(A);
-            else if (mode == 1) step_kernel<1, true><<<G, B, s->smem_u2, s->stream>>>(A);
-            else                step_kernel<2, true><<<G, B, s->smem_u2, s->stream>>>(A);
-        } else {
-            if (mode == 0)      step_kernel<0, false><<<G, B, s->smem_nou2, s->stream>>>(A);
-            else if (mode == 1) step_kernel<1, false><<<G, B, s->smem_u2, s->stream>>>(A);
-            else                step_kernel<2, false><<<G, B, s->smem_u2, s->stream>>>(A);
-        }
+#define LAUNCH(T)                                                                                    \
+        do {                                                                                         \
+            if (dense) {                                                                             \
+                if (mode == 0)      step_kernel<0, true, T><<<G, B, s->smem_nou2, s->stream>>>(A);   \
+                else if (mode == 1) step_kernel<1, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
+                else                step_kernel<2, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
+            } else {                                                                                 \
+                if (mode == 0)      step_kernel<0, false, T><<<G, B, s->smem_nou2, s->stream>>>(A);  \
+                else if (mode == 1) step_kernel<1, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
+                else                step_kernel<2, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
+            }                                                                                        \
+        } while (0)
+        if (B == 384) LAUNCH(384); else LAUNCH(256);
+#undef LAUNCH
         CK(cudaGetLastError());
         s->tm.launches++;
         *launched = true;

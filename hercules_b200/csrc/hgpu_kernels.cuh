@@ -176,14 +176,34 @@ __device__ __forceinline__ int ldg_i32_pinned(const int32_t *p)
     return v;
 }
 
-struct TileMeta { int n0, nown, hb, nh, eb, ne; };
+// Raw offsets as loaded (differences are taken where they are used, so that nothing consumes a
+// freshly requested value early).
+struct TileMeta {
+    int n0, n1, hb, h1, eb, e1;
+    __device__ __forceinline__ int nown() const { return n1 - n0; }
+    __device__ __forceinline__ int nh() const { return h1 - hb; }
+    __device__ __forceinline__ int ne() const { return e1 - eb; }
+};
 
-__device__ __forceinline__ TileMeta load_meta(const StepArgs &A, int t)
+// Tile offsets travel through a 4-deep shared-memory ring filled by cp.async (no registers, no
+// scoreboard): slot i & 3 holds the offsets of the CTA's i-th tile.
+__device__ __forceinline__ void cp_async4(int *smem_dst, const int32_t *gsrc)
 {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fetch_meta_async(const StepArgs &A, int t, int *slot, int tid)
+{
+    if (tid < 6) {
+        const int32_t *src = (tid < 2 ? A.node_off : tid < 4 ? A.halo_off : A.elem_off) + t + (tid & 1);
+        cp_async4(slot + tid, src);
+    }
+}
+__device__ __forceinline__ TileMeta read_meta(const int *slot)
+{
+    const volatile int *v = slot;
     TileMeta m;
-    m.n0 = ldg_i32_pinned(A.node_off + t); m.nown = ldg_i32_pinned(A.node_off + t + 1) - m.n0;
-    m.hb = ldg_i32_pinned(A.halo_off + t); m.nh = ldg_i32_pinned(A.halo_off + t + 1) - m.hb;
-    m.eb = ldg_i32_pinned(A.elem_off + t); m.ne = ldg_i32_pinned(A.elem_off + t + 1) - m.eb;
+    m.n0 = v[0]; m.n1 = v[1]; m.hb = v[2]; m.h1 = v[3]; m.eb = v[4]; m.e1 = v[5];
     return m;
 }
 
@@ -209,7 +229,7 @@ __device__ __forceinline__ void load_halo_ids(const StepArgs &A, const TileMeta 
 #pragma unroll
     for (int q = 0; q < HALO_PRE; q++) {
         const int h = tid + q * nthr;
-        hid[q] = h < m.nh ? ldg_i32_pinned(A.halo_id + m.hb + h) : -1;
+        hid[q] = h < m.nh() ? ldg_i32_pinned(A.halo_id + m.hb + h) : -1;
     }
 }
 
@@ -217,7 +237,7 @@ template <bool U2_OWNED, bool U2_HALO>
 __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m, double *su1, double *su2,
                                            int tid, int nthr, const int (&hid)[HALO_PRE])
 {
-    const int nd = 3 * m.nown, nv = nd >> 1;
+    const int nd = 3 * m.nown(), nv = nd >> 1;
     const double *g1 = A.u1 + 3 * (size_t)m.n0, *g2 = A.u2 + 3 * (size_t)m.n0;
     for (int i = tid; i < nv; i += nthr) {
         cp_async16(su1 + 2 * i, g1 + 2 * i);
@@ -231,14 +251,14 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m,
 #pragma unroll
     for (int q = 0; q < HALO_PRE; q++) {
         const int h = tid + q * nthr;
-        if (h < m.nh && hid[q] >= 0) {        // -1 = slot left unused by the plan
+        if (h < m.nh() && hid[q] >= 0) {        // -1 = slot left unused by the plan
             const size_t g = 3 * (size_t)hid[q];
             double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
             cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
             if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
         }
     }
-    for (int h = tid + HALO_PRE * nthr; h < m.nh; h += nthr) {
+    for (int h = tid + HALO_PRE * nthr; h < m.nh(); h += nthr) {
         const int id = __ldg(A.halo_id + m.hb + h);
         if (id < 0) continue;
         const size_t g = 3 * (size_t)id;
@@ -256,7 +276,7 @@ __device__ __forceinline__ void load_node_tables(const StepArgs &A, const TileMe
 #pragma unroll
     for (int q = 0; q < NT_PRE; q++) {
         const int i = tid + q * nthr;
-        if (i < m.nown) {
+        if (i < m.nown()) {
             const double *nt = A.nt3 + 3 * (size_t)(m.n0 + i);
             ntv[q][0] = ldg_f64_pinned(nt); ntv[q][1] = ldg_f64_pinned(nt + 1); ntv[q][2] = ldg_f64_pinned(nt + 2);
         } else {
@@ -282,8 +302,8 @@ __device__ __forceinline__ void advance_node(const StepArgs &A, double *acc, con
     }
 }
 
-template <int MODE, bool DENSE>
-__global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
+template <int MODE, bool DENSE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 {
     constexpr bool U2E = MODE != 0;          // elements read u2
     extern __shared__ double smem[];
@@ -293,44 +313,65 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
     double *acc = smem + 2 * stage_doubles;
     const bool fuse = A.fuse_update != 0;
 
-    // Register pipeline.  All global loads of a warp share one hardware scoreboard, so a consumer
-    // waits for EVERY load issued before it, however young.  Each prefetch is therefore consumed
-    // (moved out of its landing registers) right BEFORE the next batch of loads is issued:
-    //   entries   : enext is copied to ecur at the top of a round, then the following round's
-    //               entry is requested
-    //   tile meta : tile t+2G is requested at the top of tile t
-    //   halo ids  : those of tile t+G... are requested before the accumulation passes of the last
-    //               round of tile t-... (one tile ahead of the cp.async that needs them)
+    // Pipeline.  All global loads of a warp share one hardware scoreboard, so a consumer waits
+    // for EVERY load issued before it, however young.  Each register prefetch is therefore
+    // consumed right BEFORE the next batch of loads is issued, and everything that can avoid
+    // registers does:
+    //   displacements : cp.async into the other stage, one tile ahead
+    //   tile offsets  : cp.async into a 4-slot ring, three tiles ahead
+    //   entries       : registers; enext -> ecur at the top of a round, then the following round's
+    //                   entry is requested
+    //   halo ids      : registers; requested before the accumulation passes of a tile's last round
+    //                   for the tile that is staged at the top of the next iteration
+    //   node tables   : registers; requested before the accumulation passes of the last round
+    __shared__ int smeta[4][8];
     const int G = gridDim.x;
     int t = blockIdx.x;
     if (t >= A.ntiles) return;
     for (int k = tid; k < O3; k += nthr) acc[k] = 0.0;
-    TileMeta cur = load_meta(A, t), nxt = cur, nn = cur;
-    int hid[HALO_PRE];
-    load_halo_ids(A, cur, tid, nthr, hid);
-    if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr, hid);
-    else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr, hid);
+    fetch_meta_async(A, t, smeta[0], tid);
+    if (t + G < A.ntiles) fetch_meta_async(A, t + G, smeta[1], tid);
+    if (t + 2 * G < A.ntiles) fetch_meta_async(A, t + 2 * G, smeta[2], tid);
     cp_async_commit();
-    if (t + G < A.ntiles) { nxt = load_meta(A, t + G); load_halo_ids(A, nxt, tid, nthr, hid); }
+    cp_async_wait_all();
+    __syncthreads();
+    int hid[HALO_PRE];
+    {
+        const TileMeta cur = read_meta(smeta[0]);
+        load_halo_ids(A, cur, tid, nthr, hid);
+        if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr, hid);
+        else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr, hid);
+        cp_async_commit();
+        if (t + G < A.ntiles) load_halo_ids(A, read_meta(smeta[1]), tid, nthr, hid);
+    }
     Entry ecur, enext;
     enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
-    if (tid < cur.ne) enext = load_entry<U2E>(A, cur.eb + tid);
+    {
+        const TileMeta cur = read_meta(smeta[0]);
+        if (tid < cur.ne()) enext = load_entry<U2E>(A, cur.eb + tid);
+    }
 
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
         double *su2 = su1 + S3;
         const int tn = t + G;
         const bool has_next = tn < A.ntiles;
+        const bool has_nn = tn + G < A.ntiles;
+        const int *m_cur = smeta[it & 3], *m_nxt = smeta[(it + 1) & 3], *m_nn = smeta[(it + 2) & 3];
         cp_async_wait_all();
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1
         if (has_next) {
             double *n1 = smem + ((it + 1) & 1) * stage_doubles;
+            const TileMeta nxt = read_meta(m_nxt);
             if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
+            if (tn + 2 * G < A.ntiles) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & 3], tid);
             cp_async_commit();
         }
-        const bool has_nn = tn + G < A.ntiles;
-        const int nown3 = 3 * cur.nown;
+        const TileMeta cur = read_meta(m_cur);
+        const int nown3 = 3 * cur.nown();
+        const int nxt_eb = has_next ? ((const volatile int *)m_nxt)[4] : 0;
+        const int nxt_ne = has_next ? ((const volatile int *)m_nxt)[5] - nxt_eb : 0;
 
         // node tables of the (up to NT_PRE) owned nodes this thread advances, prefetched into
         // registers before the last round's accumulation passes
@@ -338,16 +379,15 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
         bool nt_loaded = false;
 
         // ---- element forces, accumulated per owned node ------------------------------------
-        for (int base = 0; base < cur.ne; base += nthr) {
-            const bool act = base + tid < cur.ne;
+        for (int base = 0; base < cur.ne(); base += nthr) {
+            const bool act = base + tid < cur.ne();
             ecur = enext;
             // next round's entry (or the first round of the next tile) rides along with the math
-            if (base + nthr < cur.ne) {
-                if (base + nthr + tid < cur.ne) enext = load_entry<U2E>(A, cur.eb + base + nthr + tid);
-            } else if (has_next && tid < nxt.ne) {
-                enext = load_entry<U2E>(A, nxt.eb + tid);
+            if (base + nthr < cur.ne()) {
+                if (base + nthr + tid < cur.ne()) enext = load_entry<U2E>(A, cur.eb + base + nthr + tid);
+            } else if (tid < nxt_ne) {
+                enext = load_entry<U2E>(A, nxt_eb + tid);
             }
-            if (base == 0 && has_nn) nn = load_meta(A, tn + G);
             double fx[8], fy[8], fz[8];
             uint32_t sl[8];
             if (act) {
@@ -399,9 +439,9 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
                     }
                 }
             }
-            if (base + nthr >= cur.ne) {
+            if (base + nthr >= cur.ne()) {
                 if (fuse) { load_node_tables(A, cur, tid, nthr, ntv); nt_loaded = true; }
-                if (has_nn) load_halo_ids(A, nn, tid, nthr, hid);
+                if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
             }
             // A node is corner j of at most one element (leaf octants do not overlap), so within
             // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
@@ -414,9 +454,9 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
                 __syncthreads();
             }
         }
-        if (cur.ne == 0) {                    // a tile of element-less nodes: keep the pipeline fed
-            if (has_next && tid < nxt.ne) enext = load_entry<U2E>(A, nxt.eb + tid);
-            if (has_nn) { nn = load_meta(A, tn + G); load_halo_ids(A, nn, tid, nthr, hid); }
+        if (cur.ne() == 0) {                    // a tile of element-less nodes: keep the pipeline fed
+            if (tid < nxt_ne) enext = load_entry<U2E>(A, nxt_eb + tid);
+            if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
         }
 
         // ---- owned nodes: fused update, or hand the force on ------------------------------------
@@ -428,9 +468,9 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
 #pragma unroll
                 for (int q = 0; q < NT_PRE; q++) {
                     const int i = tid + q * nthr;
-                    if (i < cur.nown) advance_node(A, acc, su1, su2, g0, i, ntv[q][0], ntv[q][1], ntv[q][2]);
+                    if (i < cur.nown()) advance_node(A, acc, su1, su2, g0, i, ntv[q][0], ntv[q][1], ntv[q][2]);
                 }
-                for (int i = tid + NT_PRE * nthr; i < cur.nown; i += nthr) {
+                for (int i = tid + NT_PRE * nthr; i < cur.nown(); i += nthr) {
                     const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + i);
                     advance_node(A, acc, su1, su2, g0, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
                 }
@@ -452,8 +492,6 @@ __global__ void __launch_bounds__(256, 2) step_kernel(const StepArgs A)
         }
         if (!has_next) break;
         t = tn;
-        cur = nxt;
-        nxt = nn;
     }
 }
 

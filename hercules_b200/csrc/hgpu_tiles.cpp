@@ -71,6 +71,9 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
     const char *e3 = getenv("HGPU_PLAN_PACK");
     const bool opt_sort = !(e1 && atoi(e1) == 0), opt_greedy = !(e2 && atoi(e2) == 0), opt_pack = !(e3 && atoi(e3) == 0);
     std::unordered_map<std::string, std::vector<int32_t>> pack_cache;
+    std::vector<uint8_t> g_cnt;
+    std::vector<int32_t> g_roff, g_rval, g_rcur, g_order, g_hslot;
+    std::vector<int32_t> freeslots[16];
     std::vector<int32_t> stamp_e((size_t)E, -1), stamp_n((size_t)N, -1), slot_of((size_t)N, 0);
     std::vector<int32_t> elems, halo;
     plan.node_off.push_back(0);
@@ -192,31 +195,50 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
         {
             const int32_t ne = (int32_t)elems.size(), ngrp = (ne + 15) / 16;
             const int32_t limit = std::min(max_slots, (nown + (int32_t)halo.size() + 31) & ~15);
-            std::vector<uint8_t> cnt((size_t)ngrp * 8 * 16, 0);
-            std::vector<std::vector<int32_t>> refs(halo.size());     // (group * 8 + corner) per halo node
-            for (size_t h = 0; h < halo.size(); h++) slot_of[halo[h]] = -1 - (int32_t)h;   // index while unassigned
+            // scratch reused from tile to tile: cnt[group][corner][residue], CSR of the accesses
+            // (group * 8 + corner) every halo node takes part in
+            g_cnt.assign((size_t)ngrp * 8 * 16, 0);
+            std::vector<uint8_t> &cnt = g_cnt;
+            const size_t nhalo = halo.size();
+            g_roff.assign(nhalo + 1, 0);
+            for (size_t h = 0; h < nhalo; h++) slot_of[halo[h]] = -1 - (int32_t)h;   // index while unassigned
             for (int32_t k = 0; k < ne; k++) {
                 const int32_t *ln = lnid + 8 * (size_t)elems[k];
                 for (int j = 0; j < 8; j++) {
                     const int32_t n = ln[j];
                     if (n >= a && n < b) cnt[((size_t)(k / 16) * 8 + j) * 16 + ((n - a) & 15)]++;
-                    else refs[(size_t)(-1 - slot_of[n])].push_back((k / 16) * 8 + j);
+                    else g_roff[(size_t)(-1 - slot_of[n]) + 1]++;
                 }
             }
-            std::vector<int32_t> order(halo.size());
-            for (size_t h = 0; h < halo.size(); h++) order[h] = (int32_t)h;
+            for (size_t h = 0; h < nhalo; h++) g_roff[h + 1] += g_roff[h];
+            g_rval.resize((size_t)g_roff[nhalo]);
+            g_rcur.assign(g_roff.begin(), g_roff.end() - 1);
+            for (int32_t k = 0; k < ne; k++) {
+                const int32_t *ln = lnid + 8 * (size_t)elems[k];
+                for (int j = 0; j < 8; j++) {
+                    const int32_t n = ln[j];
+                    if (!(n >= a && n < b)) g_rval[(size_t)g_rcur[(size_t)(-1 - slot_of[n])]++] = (k / 16) * 8 + j;
+                }
+            }
+            struct Refs { const int32_t *b, *e; const int32_t *begin() const { return b; } const int32_t *end() const { return e; }
+                          size_t size() const { return (size_t)(e - b); } };
+            auto refs_of = [&](int32_t h) { return Refs{g_rval.data() + g_roff[(size_t)h], g_rval.data() + g_roff[(size_t)h + 1]}; };
+            std::vector<int32_t> &order = g_order;
+            order.resize(nhalo);
+            for (size_t h = 0; h < nhalo; h++) order[h] = (int32_t)h;
             std::stable_sort(order.begin(), order.end(),
-                             [&](int32_t x, int32_t y) { return refs[x].size() > refs[y].size(); });
-            std::vector<std::vector<int32_t>> freeslots(16);
+                             [&](int32_t x, int32_t y) { return refs_of(x).size() > refs_of(y).size(); });
+            for (int r = 0; r < 16; r++) freeslots[r].clear();
             for (int32_t sl = limit - 1; sl >= nown; sl--) freeslots[sl & 15].push_back(sl);   // pop_back = lowest
-            std::vector<int32_t> hslot(halo.size(), -1);
+            std::vector<int32_t> &hslot = g_hslot;
+            hslot.assign(nhalo, -1);
             nslots = nown;
             for (int32_t h : order) {
                 int best = -1; int64_t best_cost = 0; int32_t best_slot = 0;
                 for (int r = 0; r < 16; r++) {
                     if (freeslots[r].empty()) continue;
                     int64_t cost = 0;
-                    if (opt_greedy) for (int32_t gj : refs[h]) cost += cnt[(size_t)gj * 16 + r];
+                    if (opt_greedy) for (int32_t gj : refs_of(h)) cost += cnt[(size_t)gj * 16 + r];
                     const int32_t sl = freeslots[r].back();
                     // equal cost: keep the staged range compact
                     if (best < 0 || cost < best_cost || (cost == best_cost && sl < best_slot)) {
@@ -226,7 +248,7 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_blo
                 if (best < 0) { err = "internal: no free halo slot"; return false; }
                 freeslots[best].pop_back();
                 hslot[h] = best_slot;
-                for (int32_t gj : refs[h]) cnt[(size_t)gj * 16 + best]++;
+                for (int32_t gj : refs_of(h)) cnt[(size_t)gj * 16 + best]++;
                 nslots = std::max(nslots, best_slot + 1);
             }
             // halo list in slot order, -1 marks an unused slot
