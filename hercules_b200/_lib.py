@@ -46,7 +46,7 @@ class Layout(C.Structure):
     _fields_ = [("tile_nodes", i32), ("ntiles", i32), ("max_tile_nodes", i32),
                 ("max_tile_elems", i32), ("tile_elems_total", i64), ("tile_halo_total", i64),
                 ("n_regular", i64), ("n_special", i64), ("device_bytes", i64),
-                ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32),
+                ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32), ("early_tiles", i32),
                 ("est_gather_wavefronts", f64), ("est_scatter_wavefronts", f64)]
 
 
@@ -59,6 +59,8 @@ SYMBOLS = {
     "hgpu_init": (C.c_int, [C.POINTER(_H), C.POINTER(Mesh), C.POINTER(Params)]),
     "hgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
     "hgpu_comm_init": (C.c_int, [_H, C.c_void_p]),
+    "hgpu_comm_p2p_export": (C.c_int, [_H, C.c_void_p, i32, C.POINTER(i32)]),
+    "hgpu_comm_p2p_connect": (C.c_int, [_H, C.POINTER(C.c_void_p), C.POINTER(i32)]),
     "hgpu_finalize": (C.c_int, [_H]),
     "hgpu_step_begin": (C.c_int, [_H, i32]),
     "hgpu_force_source": (C.c_int, [_H, C.c_void_p]),

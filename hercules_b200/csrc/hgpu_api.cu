@@ -96,7 +96,16 @@ struct MsgList {
     std::vector<int32_t> peer, nodes, off;   // off = prefix sum of nodes
     int32_t total = 0;
     int32_t *d_map = nullptr;                // concatenated mapping[]
-    double *d_send = nullptr, *d_recv = nullptr;   // [total][3] staging
+    double *d_send = nullptr, *d_recv = nullptr;   // [total][3] staging (NCCL transport)
+    // peer-memory transport: this list's receive area inside my mailbox, and where each of my
+    // messengers writes in its peer's mailbox
+    size_t mb_data_off = 0, mb_flag_off = 0;       // bytes from the mailbox base
+    std::vector<double *> remote_data;             // [messenger] peer segment (parity 0)
+    std::vector<unsigned long long *> remote_flag; // [messenger] peer flags (2 parities)
+    unsigned int *d_counters = nullptr;            // [messenger]
+    PushSeg *d_push = nullptr;                     // [2 parities][messenger]
+    PullSeg *d_pull = nullptr;                     // [2 parities][messenger]
+    unsigned long long seq_out = 0, seq_in = 0;
 };
 
 enum ForceState { F_CLEAN = 0, F_PENDING = 1, F_MATERIALIZED = 2, F_FUSED_DONE = 3 };
@@ -112,6 +121,8 @@ struct hgpu_solver {
     int32_t E = 0, N = 0, D = 0;
     int dev = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t comm_stream = nullptr;      // halo exchange + hanging-node transfer while late tiles run
+    cudaEvent_t ev_early = nullptr, ev_comm = nullptr;
     // node arrays
     double *u[3] = {nullptr, nullptr, nullptr};
     int i1 = 0, i2 = 1, i3 = 2;          // which buffer plays tm1 / tm2 / tm3
@@ -122,11 +133,13 @@ struct hgpu_solver {
     double *Kd = nullptr;
     // tiles
     TilePlan plan;
-    int32_t *t_node_off = nullptr, *t_elem_off = nullptr, *t_halo_off = nullptr, *t_halo_id = nullptr;
+    int4 *t_meta = nullptr;              // per tile in processing order (early tiles first)
+    int32_t n_early = 0;                 // tiles whose nodes take part in the halo / hanging-node phases
+    int32_t *t_halo_id = nullptr;
     uint4 *t_ent_slot = nullptr;         // per entry 8 x uint16 = 3 * slot
     double *t_ent_coef = nullptr;        // per entry c1, c2, beta
     double *nt3 = nullptr;               // [N][3] {+-1/mass, m2, m1} for the fused update
-    int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, cap_slots = 0, cap_owned = 0, ctas_per_sm = 0;
+    int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, grid_late = 0, cap_slots = 0, cap_owned = 0, ctas_per_sm = 0;
     // special-node path
     int32_t nS = 0; int32_t *d_slist = nullptr;
     int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
@@ -141,6 +154,11 @@ struct hgpu_solver {
     // halo
     MsgList dn_c, dn_s, an_c, an_s;
     ncclComm_t comm = nullptr;
+    // peer-memory transport
+    char *mailbox = nullptr; size_t mailbox_bytes = 0;
+    std::vector<void *> peer_base;           // [rank] IPC-mapped mailbox of each peer
+    bool p2p_ready = false;
+    int *d_p2p_err = nullptr;
     // step state
     bool want_stiff = false, want_damp = false;
     ForceState fstate = F_CLEAN;
@@ -201,6 +219,7 @@ static void drain_events(hgpu_solver *s)
 {
     if (!s->ev_used) return;
     cudaStreamSynchronize(s->stream);
+    if (s->comm_stream) cudaStreamSynchronize(s->comm_stream);
     for (size_t i = 0; i < s->ev_used; i++) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->evpool[i].a, s->evpool[i].b) == cudaSuccess)
@@ -212,7 +231,8 @@ static void drain_events(hgpu_solver *s)
 // Brackets the launches of one phase with a CUDA event pair on the solver's stream.
 struct PhaseTimer {
     hgpu_solver *s; EvPair *p = nullptr;
-    PhaseTimer(hgpu_solver *s_, int phase) : s(s_)
+    cudaStream_t st;
+    PhaseTimer(hgpu_solver *s_, int phase, cudaStream_t stream = nullptr) : s(s_), st(stream ? stream : s_->stream)
     {
         if (!(s->P.flags & HGPU_FLAG_TIMERS)) return;
         if (s->ev_used == s->evpool.size()) {
@@ -225,9 +245,9 @@ struct PhaseTimer {
         }
         p = &s->evpool[s->ev_used++];
         p->phase = phase;
-        cudaEventRecord(p->a, s->stream);
+        cudaEventRecord(p->a, st);
     }
-    ~PhaseTimer() { if (p) cudaEventRecord(p->b, s->stream); }
+    ~PhaseTimer() { if (p) cudaEventRecord(p->b, st); }
 };
 
 extern "C" const char *hgpu_last_error(void) { return g_err.c_str(); }
@@ -372,6 +392,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
     for (int i = 0; i < hgpu_solver::SRC_RING; i++)
         TRYCU(cudaEventCreateWithFlags(&s->src_done[i], cudaEventDisableTiming));
 
+    std::vector<uint8_t> early_node((size_t)N, 0);   // nodes the exchange / hanging-node phases touch
     // ---- node classes -----------------------------------------------------------------------------
     // A node is advanced inside the fused step kernel unless something else must see or change its
     // force first (source assignment, hanging-node transfer, halo exchange), or unless its
@@ -381,16 +402,18 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         std::vector<uint8_t> cls((size_t)N, NODE_REGULAR);
         if (params->flags & HGPU_FLAG_NO_FUSE) std::fill(cls.begin(), cls.end(), (uint8_t)NODE_SPECIAL);
         for (int32_t i = 0; i < params->nloaded; i++) cls[params->loaded_lnid[i]] = NODE_SPECIAL;
+        const bool multi = params->nranks > 1;
         for (int32_t d = 0; d < D; d++) {
             const int32_t *dn = mesh->dnode + 6 * (size_t)d;
             cls[dn[0]] = NODE_SPECIAL;
-            for (int a = 0; a < 4 && dn[2 + a] >= 0; a++) cls[dn[2 + a]] = NODE_SPECIAL;
+            if (multi) early_node[dn[0]] = 1;
+            for (int a = 0; a < 4 && dn[2 + a] >= 0; a++) { cls[dn[2 + a]] = NODE_SPECIAL; if (multi) early_node[dn[2 + a]] = 1; }
         }
         const hgpu_msglist_t *lists[4] = {&mesh->dn_c, &mesh->dn_s, &mesh->an_c, &mesh->an_s};
         for (const hgpu_msglist_t *l : lists) {
             int32_t tot = 0;
             for (int32_t i = 0; i < l->count; i++) tot += l->nodes[i];
-            for (int32_t i = 0; i < tot; i++) cls[l->mapping[i]] = NODE_SPECIAL;
+            for (int32_t i = 0; i < tot; i++) { cls[l->mapping[i]] = NODE_SPECIAL; early_node[l->mapping[i]] = 1; }
         }
         std::vector<double> nt3(n3);
         for (int32_t n = 0; n < N; n++) {
@@ -431,11 +454,31 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             coef[3 * k] = et[0]; coef[3 * k + 1] = et[1];
             coef[3 * k + 2] = et[0] != 0.0 ? et[2] / et[0] : 0.0;
         }
-        TRY(upload(s, &s->t_node_off, pl.node_off.data(), pl.node_off.size()));
-        TRY(upload(s, &s->t_elem_off, pl.elem_off.data(), pl.elem_off.size()));
+        // processing order: tiles owning a node that the exchange / hanging-node phases read or
+        // write come first, so those phases can run while the remaining tiles are evaluated
+        {
+            std::vector<int32_t> order;
+            order.reserve((size_t)pl.ntiles);
+            std::vector<uint8_t> is_early((size_t)pl.ntiles, 0);
+            for (int32_t t = 0; t < pl.ntiles; t++)
+                for (int32_t n = pl.node_off[t]; n < pl.node_off[(size_t)t + 1]; n++)
+                    if (early_node[n]) { is_early[t] = 1; break; }
+            for (int32_t t = 0; t < pl.ntiles; t++) if (is_early[t]) order.push_back(t);
+            s->n_early = (int32_t)order.size();
+            for (int32_t t = 0; t < pl.ntiles; t++) if (!is_early[t]) order.push_back(t);
+            std::vector<int32_t> meta(8 * (size_t)pl.ntiles, 0);
+            for (int32_t i = 0; i < pl.ntiles; i++) {
+                const int32_t t = order[i];
+                int32_t *m = meta.data() + 8 * (size_t)i;
+                m[0] = pl.node_off[t]; m[1] = pl.node_off[(size_t)t + 1];
+                m[2] = pl.halo_off[t]; m[3] = pl.halo_off[(size_t)t + 1];
+                m[4] = pl.elem_off[t]; m[5] = pl.elem_off[(size_t)t + 1];
+                m[6] = t;
+            }
+            TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
+        }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
-        TRY(upload(s, &s->t_halo_off, pl.halo_off.data(), pl.halo_off.size()));
         TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
         // shared memory actually needed by this plan
         s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_owned = (pl.max_tile_owned + 15) & ~15;
@@ -459,6 +502,12 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
         s->ctas_per_sm = occ;
         s->grid = std::max(1, std::min(pl.ntiles, nsm * occ));
+        {
+            int reserve = 2;
+            const char *renv = getenv("HGPU_COMM_SMS");
+            if (renv && atoi(renv) >= 0) reserve = atoi(renv);
+            s->grid_late = std::max(1, (nsm - reserve) * occ);
+        }
         const char *genv = getenv("HGPU_GRID");
         if (genv && atoi(genv) > 0) s->grid = std::min(pl.ntiles, atoi(genv));
     }
@@ -473,7 +522,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
 template <typename T>
 static void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
 
-static void free_msglist(MsgList &m) { dfree(m.d_map); dfree(m.d_send); dfree(m.d_recv); }
+static void free_msglist(MsgList &m) { dfree(m.d_map); dfree(m.d_send); dfree(m.d_recv); dfree(m.d_counters); dfree(m.d_push); dfree(m.d_pull); }
 
 extern "C" int hgpu_finalize(hgpu_solver_t *s)
 {
@@ -481,10 +530,11 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     cudaSetDevice(s->dev);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (size_t r = 0; r < s->peer_base.size(); r++) if (s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
+    dfree(s->mailbox); dfree(s->d_p2p_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_node_off); dfree(s->t_elem_off); dfree(s->t_ent_slot); dfree(s->t_ent_coef);
-    dfree(s->t_halo_off); dfree(s->t_halo_id);
+    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
     dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
@@ -492,6 +542,9 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     for (int i = 0; i < hgpu_solver::SRC_RING; i++) if (s->src_done[i]) cudaEventDestroy(s->src_done[i]);
     for (EvPair &e : s->evpool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
     if (s->h_F) cudaFreeHost(s->h_F);
+    if (s->ev_early) cudaEventDestroy(s->ev_early);
+    if (s->ev_comm) cudaEventDestroy(s->ev_comm);
+    if (s->comm_stream) cudaStreamDestroy(s->comm_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return HGPU_OK;
@@ -499,51 +552,62 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
 
 // ---- force evaluation ---------------------------------------------------------------------------
 
-// Launch the step kernel for whatever force terms were requested since the last update.
-// fuse = advance REGULAR nodes in the same launch (their force never reaches HBM).
-// Returns through *launched whether a kernel ran (no term requested = nothing to add).
-static int launch_tiles(hgpu_solver *s, bool fuse, bool *launched)
+// The force terms requested since the last update (hgpu_force_stiffness / hgpu_force_damping).
+struct Terms { bool stiff, need_u2; bool any() const { return stiff || need_u2; } };
+
+static Terms consume_terms(hgpu_solver *s)
 {
-    const bool stiff = s->want_stiff, damp = s->want_damp;
-    const bool rayleigh = s->P.damping == HGPU_DAMPING_RAYLEIGH;
+    Terms t;
+    t.stiff = s->want_stiff;
     // MASS damping has b = 0, hence c3 = c4 = 0 (psolve.c:5866-5867): damping_addforce adds nothing
-    const bool need_u2 = damp && rayleigh;
+    t.need_u2 = s->want_damp && s->P.damping == HGPU_DAMPING_RAYLEIGH;
     s->want_stiff = s->want_damp = false;
-    *launched = false;
-    if (!stiff && !need_u2) return HGPU_OK;
+    return t;
+}
+
+// Launch the step kernel over tiles [begin, end) of the processing order.
+// fuse = advance REGULAR nodes in the same launch (their force never reaches HBM).
+static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int32_t end, int max_grid = 0)
+{
+    if (end <= begin || !tm.any()) return HGPU_OK;
     StepArgs A{};
     A.u1 = s->u[s->i1]; A.u2 = s->u[s->i2]; A.unext = s->u[s->i3]; A.force = s->force;
     A.nt3 = s->nt3; A.Kd = s->Kd;
-    A.node_off = s->t_node_off; A.elem_off = s->t_elem_off; A.halo_off = s->t_halo_off; A.halo_id = s->t_halo_id;
+    A.tile_meta = s->t_meta; A.halo_id = s->t_halo_id;
     A.ent_slot = s->t_ent_slot; A.ent_coef = s->t_ent_coef;
-    A.ntiles = s->plan.ntiles; A.cap_slots = s->cap_slots; A.cap_owned = s->cap_owned;
+    A.tile_begin = begin; A.ntiles = end; A.cap_slots = s->cap_slots; A.cap_owned = s->cap_owned;
     A.fuse_update = fuse ? 1 : 0;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
-    const int mode = stiff ? (need_u2 ? 1 : 0) : 2;
+    const int mode = tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
-    PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (stiff ? PH_ADDFORCE_E : PH_DAMPING));
-    if (s->plan.ntiles > 0) {
-        const int G = s->grid, B = s->block;
-#define LAUNCH(T)                                                                                    \
-        do {                                                                                         \
-            if (dense) {                                                                             \
-                if (mode == 0)      step_kernel<0, true, T><<<G, B, s->smem_nou2, s->stream>>>(A);   \
-                else if (mode == 1) step_kernel<1, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
-                else                step_kernel<2, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
-            } else {                                                                                 \
-                if (mode == 0)      step_kernel<0, false, T><<<G, B, s->smem_nou2, s->stream>>>(A);  \
-                else if (mode == 1) step_kernel<1, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
-                else                step_kernel<2, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
-            }                                                                                        \
-        } while (0)
-        if (B == 384) LAUNCH(384); else LAUNCH(256);
+    PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
+    const int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin), B = s->block;
+#define LAUNCH(T)                                                                                \
+    do {                                                                                         \
+        if (dense) {                                                                             \
+            if (mode == 0)      step_kernel<0, true, T><<<G, B, s->smem_nou2, s->stream>>>(A);   \
+            else if (mode == 1) step_kernel<1, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
+            else                step_kernel<2, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
+        } else {                                                                                 \
+            if (mode == 0)      step_kernel<0, false, T><<<G, B, s->smem_nou2, s->stream>>>(A);  \
+            else if (mode == 1) step_kernel<1, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
+            else                step_kernel<2, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
+        }                                                                                        \
+    } while (0)
+    if (B == 384) LAUNCH(384); else LAUNCH(256);
 #undef LAUNCH
-        CK(cudaGetLastError());
-        s->tm.launches++;
-        *launched = true;
-    }
+    CK(cudaGetLastError());
+    s->tm.launches++;
     return HGPU_OK;
+}
+
+// All tiles in one launch.  *launched: whether a kernel ran (no term requested = nothing to add).
+static int launch_tiles(hgpu_solver *s, bool fuse, bool *launched)
+{
+    const Terms tm = consume_terms(s);
+    *launched = tm.any() && s->plan.ntiles > 0;
+    return launch_range(s, tm, fuse, 0, s->plan.ntiles);
 }
 
 // Make force[] hold the sum of every requested term for EVERY node (unfused semantics).
@@ -628,38 +692,89 @@ extern "C" int hgpu_force_damping(hgpu_solver_t *s)
 // schedule_senddata (psolve.c:4945-5079) for one schedule and one direction.
 //   contribution: c-list packs v -> owner; owner's s-list unpacks with += (one messenger after another)
 //   sharing     : s-list packs v -> sharers; c-list unpacks with =
-static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool contribution)
+static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool contribution, cudaStream_t st)
 {
     if (s->P.nranks == 1 || (c.total == 0 && sl.total == 0)) return HGPU_OK;
-    if (!s->comm) return fail(HGPU_ECOMM, "halo exchange needs hgpu_comm_init first");
     MsgList &snd = contribution ? c : sl;
     MsgList &rcv = contribution ? sl : c;
+    if (s->p2p_ready) {
+        const unsigned long long so = ++snd.seq_out, si = ++rcv.seq_in;
+        const int nsnd = (int)snd.peer.size(), nrcv = (int)rcv.peer.size();
+        if (nsnd) {
+            int maxn = 1;
+            for (int32_t n : snd.nodes) maxn = std::max(maxn, n);
+            const int gx = std::max(1, std::min(8, (3 * maxn + 255) / 256));
+            p2p_push_kernel<<<dim3(gx, nsnd), 256, 0, st>>>(snd.d_push + (so & 1) * nsnd, v, so);
+            CK(cudaGetLastError());
+            s->tm.launches++;
+        }
+        if (nrcv && contribution) {
+            for (int i = 0; i < nrcv; i++) {
+                const int gx = std::max(1, std::min(8, (3 * rcv.nodes[i] + 255) / 256));
+                p2p_pull_kernel<<<dim3(gx, 1), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv + i, v, si, 1, s->d_p2p_err);
+                CK(cudaGetLastError());
+                s->tm.launches++;
+            }
+        } else if (nrcv) {
+            int maxn = 1;
+            for (int32_t n : rcv.nodes) maxn = std::max(maxn, n);
+            const int gx = std::max(1, std::min(8, (3 * maxn + 255) / 256));
+            p2p_pull_kernel<<<dim3(gx, nrcv), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv, v, si, 0, s->d_p2p_err);
+            CK(cudaGetLastError());
+            s->tm.launches++;
+        }
+        return HGPU_OK;
+    }
+    if (!s->comm) return fail(HGPU_ECOMM, "halo exchange needs hgpu_comm_init or hgpu_comm_p2p_connect first");
     if (snd.total) {
-        pack_kernel<<<grid_for(3LL * snd.total, 256), 256, 0, s->stream>>>(snd.total, snd.d_map, v, snd.d_send);
+        pack_kernel<<<grid_for(3LL * snd.total, 256), 256, 0, st>>>(snd.total, snd.d_map, v, snd.d_send);
         CK(cudaGetLastError());
         s->tm.launches++;
     }
     NK(g_nccl.GroupStart());
     for (size_t i = 0; i < rcv.peer.size(); i++)
-        NK(g_nccl.Recv(rcv.d_recv + 3 * (size_t)rcv.off[i], 3 * (size_t)rcv.nodes[i], ncclFloat64, rcv.peer[i], s->comm, s->stream));
+        NK(g_nccl.Recv(rcv.d_recv + 3 * (size_t)rcv.off[i], 3 * (size_t)rcv.nodes[i], ncclFloat64, rcv.peer[i], s->comm, st));
     for (size_t i = 0; i < snd.peer.size(); i++)
-        NK(g_nccl.Send(snd.d_send + 3 * (size_t)snd.off[i], 3 * (size_t)snd.nodes[i], ncclFloat64, snd.peer[i], s->comm, s->stream));
+        NK(g_nccl.Send(snd.d_send + 3 * (size_t)snd.off[i], 3 * (size_t)snd.nodes[i], ncclFloat64, snd.peer[i], s->comm, st));
     NK(g_nccl.GroupEnd());
     if (contribution) {
         // messengers applied one after another, as the reference's unpack loop does
         for (size_t i = 0; i < rcv.peer.size(); i++) {
             if (!rcv.nodes[i]) continue;
-            unpack_kernel<<<grid_for(3LL * rcv.nodes[i], 256), 256, 0, s->stream>>>(
+            unpack_kernel<<<grid_for(3LL * rcv.nodes[i], 256), 256, 0, st>>>(
                 rcv.nodes[i], rcv.d_map + rcv.off[i], rcv.d_recv + 3 * (size_t)rcv.off[i], v, 1);
             CK(cudaGetLastError());
             s->tm.launches++;
         }
     } else if (rcv.total) {
         // a harbored node has exactly one owner, so the overwrite lists are disjoint
-        unpack_kernel<<<grid_for(3LL * rcv.total, 256), 256, 0, s->stream>>>(rcv.total, rcv.d_map, rcv.d_recv, v, 0);
+        unpack_kernel<<<grid_for(3LL * rcv.total, 256), 256, 0, st>>>(rcv.total, rcv.d_map, rcv.d_recv, v, 0);
         CK(cudaGetLastError());
         s->tm.launches++;
     }
+    return HGPU_OK;
+}
+
+// phases 8-10 on stream st
+static int force_phases(hgpu_solver *s, cudaStream_t st)
+{
+    int rc;
+    // phase 8: dangling-node forces to their owners
+    {
+        PhaseTimer pt(s, PH_SEND_DN_FORCE, st);
+        if ((rc = exchange(s, s->dn_c, s->dn_s, s->force, true, st))) return rc;
+    }
+    // phase 9: owned dangling nodes hand force/deps to their anchors
+    if (s->nA > 0) {
+        PhaseTimer pt(s, PH_ADJUST_FORCE, st);
+        adjust_dist_kernel<<<grid_for(3LL * s->nA, 128), 128, 0, st>>>(
+            s->nA, s->d_anchor_id, s->d_anchor_off, s->d_anchor_dn, s->d_anchor_deps, s->force);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    // phase 10: anchored-node forces to their owners
+    PhaseTimer pt(s, PH_SEND_AN_FORCE, st);
+    if ((rc = exchange(s, s->an_c, s->an_s, s->force, true, st))) return rc;
     return HGPU_OK;
 }
 
@@ -670,27 +785,26 @@ extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
     int rc;
     if (s->fstate == F_PENDING) {
         const bool fuse = !(s->P.flags & HGPU_FLAG_NO_FUSE);
-        bool ran;
-        if ((rc = launch_tiles(s, fuse, &ran))) return rc;
+        const Terms tm = consume_terms(s);
+        const int32_t T = s->plan.ntiles, Te = s->n_early;
+        const bool ran = tm.any() && T > 0;
         s->fstate = (fuse && ran) ? F_FUSED_DONE : F_MATERIALIZED;
+        if (ran && s->P.nranks > 1 && s->comm_stream && Te > 0 && Te < T && !(s->P.flags & HGPU_FLAG_NO_OVERLAP)) {
+            // tiles owning nodes of the exchange / hanging-node phases first; those phases then run
+            // on the communication stream while the remaining tiles are evaluated
+            if ((rc = launch_range(s, tm, fuse, 0, Te))) return rc;
+            CK(cudaEventRecord(s->ev_early, s->stream));
+            CK(cudaStreamWaitEvent(s->comm_stream, s->ev_early, 0));
+            if ((rc = force_phases(s, s->comm_stream))) return rc;
+            CK(cudaEventRecord(s->ev_comm, s->comm_stream));
+            // the step kernel fills every SM's registers: leave a few SMs to the exchange kernels
+            if ((rc = launch_range(s, tm, fuse, Te, T, s->grid_late))) return rc;
+            CK(cudaStreamWaitEvent(s->stream, s->ev_comm, 0));
+            return HGPU_OK;
+        }
+        if ((rc = launch_range(s, tm, fuse, 0, T))) return rc;
     }
-    // phase 8: dangling-node forces to their owners
-    {
-        PhaseTimer pt(s, PH_SEND_DN_FORCE);
-        if ((rc = exchange(s, s->dn_c, s->dn_s, s->force, true))) return rc;
-    }
-    // phase 9: owned dangling nodes hand force/deps to their anchors
-    if (s->nA > 0) {
-        PhaseTimer pt(s, PH_ADJUST_FORCE);
-        adjust_dist_kernel<<<grid_for(3LL * s->nA, 128), 128, 0, s->stream>>>(
-            s->nA, s->d_anchor_id, s->d_anchor_off, s->d_anchor_dn, s->d_anchor_deps, s->force);
-        CK(cudaGetLastError());
-        s->tm.launches++;
-    }
-    // phase 10: anchored-node forces to their owners
-    PhaseTimer pt(s, PH_SEND_AN_FORCE);
-    if ((rc = exchange(s, s->an_c, s->an_s, s->force, true))) return rc;
-    return HGPU_OK;
+    return force_phases(s, s->stream);
 }
 
 extern "C" int hgpu_update(hgpu_solver_t *s)
@@ -740,7 +854,7 @@ extern "C" int hgpu_disp_exchange(hgpu_solver_t *s)
     // phase 13: owners publish anchored-node displacements
     {
         PhaseTimer pt(s, PH_SEND_AN_DISP);
-        if ((rc = exchange(s, s->an_c, s->an_s, tm2, false))) return rc;
+        if ((rc = exchange(s, s->an_c, s->an_s, tm2, false, s->stream))) return rc;
     }
     // phase 14: dangling nodes interpolate from their anchors
     if (s->D > 0) {
@@ -751,7 +865,7 @@ extern "C" int hgpu_disp_exchange(hgpu_solver_t *s)
     }
     // phase 15: owners publish dangling-node displacements
     PhaseTimer pt(s, PH_SEND_DN_DISP);
-    if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false))) return rc;
+    if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false, s->stream))) return rc;
     return HGPU_OK;
 }
 
@@ -899,6 +1013,12 @@ extern "C" int hgpu_sync(hgpu_solver_t *s)
     if (!s) return fail(HGPU_EINVAL, "null solver");
     CK(cudaSetDevice(s->dev));
     CK(cudaStreamSynchronize(s->stream));
+    if (s->comm_stream) CK(cudaStreamSynchronize(s->comm_stream));
+    if (s->d_p2p_err) {
+        int e = 0;
+        CK(cudaMemcpy(&e, s->d_p2p_err, sizeof e, cudaMemcpyDeviceToHost));
+        if (e) return fail(HGPU_ECOMM, "halo exchange timed out waiting for a peer");
+    }
     return HGPU_OK;
 }
 
@@ -951,11 +1071,159 @@ extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
     out->n_regular = s->n_regular; out->n_special = s->n_special;
     out->device_bytes = s->device_bytes;
     out->smem_bytes = s->smem_u2; out->block_threads = s->block;
-    out->grid_ctas = s->grid; out->ctas_per_sm = s->ctas_per_sm;
+    out->grid_ctas = s->grid; out->ctas_per_sm = s->ctas_per_sm; out->early_tiles = s->n_early;
     return HGPU_OK;
 }
 
 // ---- multi-GPU ------------------------------------------------------------------------------------
+
+static int make_comm_stream(hgpu_solver *s)
+{
+    if (!s->comm_stream) {
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamNonBlocking, hi));
+        CK(cudaEventCreateWithFlags(&s->ev_early, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming));
+    }
+    return HGPU_OK;
+}
+
+// ---- peer-memory transport: CUDA IPC mailboxes ------------------------------------------------
+//
+// blob = { int32 magic, rank, nranks, nseg; cudaIpcMemHandle_t (64 B); uint64 mailbox_bytes;
+//          nseg x { int32 list, peer, count, pad; uint64 data_off, flag_off } }
+// list: 0 dn_c, 1 dn_s, 2 an_c, 3 an_s.  A contribution travels c-list -> the peer's s-list
+// segment; a sharing travels s-list -> the peer's c-list segment (psolve.c:4945-5079).
+struct BlobSeg { int32_t list, peer, count, pad; uint64_t data_off, flag_off; };
+static const int32_t BLOB_MAGIC = 0x48475055;
+
+static MsgList *list_of(hgpu_solver *s, int l) { return l == 0 ? &s->dn_c : l == 1 ? &s->dn_s : l == 2 ? &s->an_c : &s->an_s; }
+
+static int p2p_alloc_mailbox(hgpu_solver *s)
+{
+    if (s->mailbox) return HGPU_OK;
+    size_t off = 0;
+    for (int l = 0; l < 4; l++) {
+        MsgList *m = list_of(s, l);
+        m->mb_data_off = off;
+        off += 2 * 3 * (size_t)m->total * sizeof(double);       // two parities
+        off = (off + 255) & ~(size_t)255;
+    }
+    for (int l = 0; l < 4; l++) {
+        MsgList *m = list_of(s, l);
+        m->mb_flag_off = off;
+        off += 2 * m->peer.size() * sizeof(unsigned long long);
+        off = (off + 255) & ~(size_t)255;
+    }
+    s->mailbox_bytes = std::max<size_t>(off, 256);
+    cudaError_t e = cudaMalloc((void **)&s->mailbox, s->mailbox_bytes);
+    if (e != cudaSuccess) return fail(HGPU_ENOMEM, "cudaMalloc(mailbox): %s", cudaGetErrorString(e));
+    s->device_bytes += (int64_t)s->mailbox_bytes;
+    CK(cudaMemset(s->mailbox, 0, s->mailbox_bytes));
+    CK(cudaDeviceSynchronize());
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_comm_p2p_export(hgpu_solver_t *s, void *blob, int32_t capacity, int32_t *size_out)
+{
+    if (!s || !size_out) return fail(HGPU_EINVAL, "null argument");
+    CK(cudaSetDevice(s->dev));
+    int rc = p2p_alloc_mailbox(s);
+    if (rc) return rc;
+    int32_t nseg = 0;
+    for (int l = 0; l < 4; l++) nseg += (int32_t)list_of(s, l)->peer.size();
+    const int32_t need = 16 + 64 + 8 + (int32_t)sizeof(BlobSeg) * nseg;
+    *size_out = need;
+    if (!blob || capacity < need) return blob ? fail(HGPU_EINVAL, "blob buffer too small (%d < %d)", capacity, need) : HGPU_OK;
+    char *p = (char *)blob;
+    int32_t hdr[4] = {BLOB_MAGIC, s->P.rank, s->P.nranks, nseg};
+    memcpy(p, hdr, 16); p += 16;
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->mailbox));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(p, &h, 64); p += 64;
+    const uint64_t mb = s->mailbox_bytes;
+    memcpy(p, &mb, 8); p += 8;
+    for (int l = 0; l < 4; l++) {
+        MsgList *m = list_of(s, l);
+        for (size_t i = 0; i < m->peer.size(); i++) {
+            BlobSeg sg{l, m->peer[i], m->nodes[i], 0,
+                       (uint64_t)(m->mb_data_off + 2 * 3 * (size_t)m->off[i] * sizeof(double)),
+                       (uint64_t)(m->mb_flag_off + 2 * i * sizeof(unsigned long long))};
+            memcpy(p, &sg, sizeof sg); p += sizeof sg;
+        }
+    }
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_comm_p2p_connect(hgpu_solver_t *s, const void *const *blobs, const int32_t *sizes)
+{
+    if (!s || !blobs || !sizes) return fail(HGPU_EINVAL, "null argument");
+    if (s->P.nranks == 1) return HGPU_OK;
+    CK(cudaSetDevice(s->dev));
+    int rc = p2p_alloc_mailbox(s);
+    if (rc) return rc;
+    const int R = s->P.nranks;
+    s->peer_base.assign((size_t)R, nullptr);
+    std::vector<std::vector<BlobSeg>> segs((size_t)R);
+    // which peers do I talk to at all
+    std::vector<uint8_t> need((size_t)R, 0);
+    for (int l = 0; l < 4; l++) for (int32_t p : list_of(s, l)->peer) need[p] = 1;
+    for (int r = 0; r < R; r++) {
+        if (r == s->P.rank || !need[r]) continue;
+        const char *p = (const char *)blobs[r];
+        if (!p || sizes[r] < 88) return fail(HGPU_ECOMM, "missing or short p2p blob of rank %d", r);
+        int32_t hdr[4];
+        memcpy(hdr, p, 16);
+        if (hdr[0] != BLOB_MAGIC || hdr[1] != r || hdr[2] != R || sizes[r] < 88 + (int32_t)sizeof(BlobSeg) * hdr[3])
+            return fail(HGPU_ECOMM, "malformed p2p blob of rank %d", r);
+        cudaIpcMemHandle_t h;
+        memcpy(&h, p + 16, 64);
+        cudaError_t e = cudaIpcOpenMemHandle(&s->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(HGPU_ECOMM, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        segs[r].resize((size_t)hdr[3]);
+        memcpy(segs[r].data(), p + 88, sizeof(BlobSeg) * (size_t)hdr[3]);
+    }
+    for (int l = 0; l < 4; l++) {
+        MsgList *m = list_of(s, l);
+        const int comp = l ^ 1;                       // dn_c <-> dn_s, an_c <-> an_s
+        const size_t nm = m->peer.size();
+        m->remote_data.assign(nm, nullptr);
+        m->remote_flag.assign(nm, nullptr);
+        for (size_t i = 0; i < nm; i++) {
+            const int p = m->peer[i];
+            const BlobSeg *hit = nullptr;
+            for (const BlobSeg &sg : segs[p]) if (sg.list == comp && sg.peer == s->P.rank) hit = &sg;
+            if (!hit || hit->count != m->nodes[i])
+                return fail(HGPU_ECOMM, "rank %d has no matching segment for list %d of rank %d (%d nodes)",
+                            p, l, s->P.rank, m->nodes[i]);
+            m->remote_data[i] = (double *)((char *)s->peer_base[p] + hit->data_off);
+            m->remote_flag[i] = (unsigned long long *)((char *)s->peer_base[p] + hit->flag_off);
+        }
+        if ((rc = dalloc(s, &m->d_counters, std::max<size_t>(nm, 1)))) return rc;
+        CK(cudaMemset(m->d_counters, 0, std::max<size_t>(nm, 1) * sizeof(unsigned int)));
+        std::vector<PushSeg> push(2 * nm);
+        std::vector<PullSeg> pull(2 * nm);
+        for (int par = 0; par < 2; par++)
+            for (size_t i = 0; i < nm; i++) {
+                const size_t n3 = 3 * (size_t)m->nodes[i];
+                push[par * nm + i] = PushSeg{m->d_map + m->off[i], m->remote_data[i] + par * n3,
+                                             m->remote_flag[i] + par, m->d_counters + i, m->nodes[i]};
+                const double *loc = (const double *)(s->mailbox + m->mb_data_off) + 2 * 3 * (size_t)m->off[i] + par * n3;
+                const unsigned long long *fl = (const unsigned long long *)(s->mailbox + m->mb_flag_off) + 2 * i + par;
+                pull[par * nm + i] = PullSeg{m->d_map + m->off[i], loc, fl, m->nodes[i]};
+            }
+        if ((rc = upload(s, &m->d_push, push.data(), push.size()))) return rc;
+        if ((rc = upload(s, &m->d_pull, pull.data(), pull.size()))) return rc;
+    }
+    if ((rc = dalloc(s, &s->d_p2p_err, 1))) return rc;
+    CK(cudaMemset(s->d_p2p_err, 0, sizeof(int)));
+    if ((rc = make_comm_stream(s))) return rc;
+    s->p2p_ready = true;
+    return HGPU_OK;
+}
 
 extern "C" int hgpu_comm_unique_id(void *unique_id_128)
 {
@@ -978,5 +1246,5 @@ extern "C" int hgpu_comm_init(hgpu_solver_t *s, const void *unique_id_128)
     ncclUniqueId id;
     memcpy(&id, unique_id_128, sizeof id);
     NK(g_nccl.CommInitRank(&s->comm, s->P.nranks, id, s->P.rank));
-    return HGPU_OK;
+    return make_comm_stream(s);
 }

@@ -128,13 +128,11 @@ struct StepArgs {
     const double *__restrict__ nt3;     // [N][3] {1/mass_simple, mass2_minusaM, mass_minusaM} of nodes the
                                         // fused update may advance; first entry negative = hand the force on
     const double *__restrict__ Kd;      // dense K1|K2 as [2][24][24] (conventional only)
-    const int32_t *__restrict__ node_off;
-    const int32_t *__restrict__ elem_off;
-    const int32_t *__restrict__ halo_off;
+    const int4 *__restrict__ tile_meta; // per tile, in processing order: {n0, n1, hb, h1}, {eb, e1, -, -}
     const int32_t *__restrict__ halo_id;
     const uint4 *__restrict__ ent_slot; // per entry 8 x uint16: 3 * tile-local slot of each corner
     const double *__restrict__ ent_coef;// per entry c1, c2, beta
-    int32_t ntiles;
+    int32_t tile_begin, ntiles;         // this launch processes tile_meta[tile_begin .. ntiles)
     int32_t cap_slots;                  // staged nodes per stage
     int32_t cap_owned;                  // accumulator nodes
     int32_t fuse_update;                // 1: advance owned nodes flagged in nt3 here
@@ -187,16 +185,11 @@ struct TileMeta {
 
 // Tile offsets travel through a 4-deep shared-memory ring filled by cp.async (no registers, no
 // scoreboard): slot i & 3 holds the offsets of the CTA's i-th tile.
-__device__ __forceinline__ void cp_async4(int *smem_dst, const int32_t *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
 __device__ __forceinline__ void fetch_meta_async(const StepArgs &A, int t, int *slot, int tid)
 {
-    if (tid < 6) {
-        const int32_t *src = (tid < 2 ? A.node_off : tid < 4 ? A.halo_off : A.elem_off) + t + (tid & 1);
-        cp_async4(slot + tid, src);
+    if (tid < 2) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(slot + 4 * tid);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(A.tile_meta + 2 * (size_t)t + tid) : "memory");
     }
 }
 __device__ __forceinline__ TileMeta read_meta(const int *slot)
@@ -324,9 +317,9 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     //   halo ids      : registers; requested before the accumulation passes of a tile's last round
     //                   for the tile that is staged at the top of the next iteration
     //   node tables   : registers; requested before the accumulation passes of the last round
-    __shared__ int smeta[4][8];
+    __shared__ __align__(16) int smeta[4][8];
     const int G = gridDim.x;
-    int t = blockIdx.x;
+    int t = A.tile_begin + blockIdx.x;
     if (t >= A.ntiles) return;
     for (int k = tid; k < O3; k += nthr) acc[k] = 0.0;
     fetch_meta_async(A, t, smeta[0], tid);
@@ -586,6 +579,70 @@ __global__ void unpack_kernel(int n, const int32_t *__restrict__ mapping, const 
     if (k >= 3 * n) return;
     const size_t g = 3 * (size_t)mapping[k / 3] + (k % 3);
     v[g] = add ? v[g] + buf[k] : buf[k];
+}
+
+// ------------------------------------------------------------------------------------------
+// Halo exchange over peer memory (CUDA IPC mailboxes, NVLink between GPUs): the sender packs
+// straight into the receiver's mailbox and raises a sequence flag; the receiver's kernel waits
+// for the flag and applies the data.  One kernel on each side per exchange, no host round trip.
+// ------------------------------------------------------------------------------------------
+struct PushSeg {
+    const int32_t *mapping;     // local node ids, messenger order (psolve.c:4806-4860)
+    double *remote;             // peer mailbox segment for this exchange parity
+    unsigned long long *remote_flag;
+    unsigned int *counter;      // local: blocks done
+    int32_t n;
+};
+
+// schedule_senddata pack + send (psolve.c:4985-5025): blockIdx.y = messenger
+__global__ void p2p_push_kernel(const PushSeg *__restrict__ segs, const double *__restrict__ v,
+                                unsigned long long seq)
+{
+    const PushSeg sg = segs[blockIdx.y];
+    const int n3 = 3 * sg.n;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += gridDim.x * blockDim.x)
+        sg.remote[k] = v[3 * (size_t)sg.mapping[k / 3] + (k % 3)];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(sg.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *sg.counter = 0;
+            __threadfence_system();
+            *reinterpret_cast<volatile unsigned long long *>(sg.remote_flag) = seq;
+        }
+    }
+}
+
+struct PullSeg {
+    const int32_t *mapping;
+    const double *local;        // my mailbox segment for this exchange parity
+    const unsigned long long *flag;
+    int32_t n;
+};
+
+// recv + unpack (psolve.c:5032-5073).  add = 1: CONTRIBUTION (+=), 0: SHARING (=).  blockIdx.y =
+// messenger (sharing only: the overwrite lists of different owners are disjoint; contributions are
+// applied one messenger per launch, in list order, so sums keep the reference's order).
+__global__ void p2p_pull_kernel(const PullSeg *__restrict__ segs, double *__restrict__ v,
+                                unsigned long long seq, int add, int *__restrict__ err)
+{
+    const PullSeg sg = segs[blockIdx.y];
+    if (threadIdx.x == 0) {
+        const volatile unsigned long long *f = sg.flag;
+        const long long t0 = clock64();
+        while (*f < seq) {
+            __nanosleep(200);
+            if (clock64() - t0 > 20000000000LL) { atomicExch(err, 1); break; }   // ~10 s: peer lost
+        }
+    }
+    __syncthreads();
+    const int n3 = 3 * sg.n;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += gridDim.x * blockDim.x) {
+        const size_t g = 3 * (size_t)sg.mapping[k / 3] + (k % 3);
+        const double x = __ldcg(sg.local + k);
+        v[g] = add ? v[g] + x : x;
+    }
 }
 
 __global__ void gather_nodes_kernel(int n, const int32_t *__restrict__ lnid, const double *__restrict__ v,

@@ -29,6 +29,7 @@ CONVENTIONAL, EFFECTIVE = 0, 1              # stiffness_type_t, stiffness.h:24
 TM1, TM2, TM3, FORCE = 1, 2, 3, 4
 FLAG_NO_FUSE = 1
 FLAG_TIMERS = 2
+FLAG_NO_OVERLAP = 4
 
 
 class HerculesGpuError(RuntimeError):
@@ -152,6 +153,21 @@ class Solver:
     def comm_init(self, unique_id: bytes) -> None:
         buf = C.create_string_buffer(unique_id, 128)
         _chk(self._L.hgpu_comm_init(self._h, buf))
+
+    def p2p_export(self) -> bytes:
+        """This rank's mailbox description for the peer-memory halo transport."""
+        n = C.c_int32()
+        _chk(self._L.hgpu_comm_p2p_export(self._h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        _chk(self._L.hgpu_comm_p2p_export(self._h, buf, n.value, C.byref(n)))
+        return buf.raw[:n.value]
+
+    def p2p_connect(self, blobs) -> None:
+        """blobs[r] = p2p_export() of rank r (all-gathered by the host)."""
+        bufs = [C.create_string_buffer(b, len(b)) for b in blobs]
+        ptrs = (C.c_void_p * len(bufs))(*[C.cast(b, C.c_void_p) for b in bufs])
+        sizes = (C.c_int32 * len(bufs))(*[len(b) for b in blobs])
+        _chk(self._L.hgpu_comm_p2p_connect(self._h, ptrs, sizes))
 
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -102,6 +102,7 @@ typedef struct hgpu_params {
 
 #define HGPU_FLAG_NO_FUSE 1     /* keep force evaluation and update as separate kernels */
 #define HGPU_FLAG_TIMERS  2     /* bracket every phase with CUDA events (hgpu_get_timers)   */
+#define HGPU_FLAG_NO_OVERLAP 4  /* multi-GPU: run the force exchange after all tiles, on one stream */
 
 typedef struct hgpu_solver hgpu_solver_t;
 
@@ -138,6 +139,15 @@ int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgpu_params_t 
  * hgpu_comm_unique_id on rank 0 and broadcast by the host (MPI_Bcast / torch.distributed). */
 int hgpu_comm_unique_id(void *unique_id_128);
 int hgpu_comm_init(hgpu_solver_t *s, const void *unique_id_128);
+
+/* Multi-GPU, peer-memory transport (one process per GPU on one node): every rank exports a blob
+ * describing its mailbox (CUDA IPC handle + where each neighbour writes), the host all-gathers
+ * the blobs (MPI_Allgather / torch.distributed), every rank connects.  After that the four
+ * schedule_senddata calls run as device kernels that store straight into the peer's memory over
+ * NVLink and wait on sequence flags; NCCL is not used.  hgpu_comm_p2p_export with blob == NULL
+ * only reports the size needed. */
+int hgpu_comm_p2p_export(hgpu_solver_t *s, void *blob, int32_t capacity, int32_t *size_out);
+int hgpu_comm_p2p_connect(hgpu_solver_t *s, const void *const *blobs, const int32_t *sizes);
 
 /* local_finalize / solver_delete (psolve.c:488, 3627) */
 int hgpu_finalize(hgpu_solver_t *s);
@@ -197,6 +207,7 @@ typedef struct hgpu_layout {
     int64_t device_bytes;
     int32_t smem_bytes, block_threads;
     int32_t grid_ctas, ctas_per_sm;   /* persistent step kernel: CTAs launched, resident per SM */
+    int32_t early_tiles;              /* tiles evaluated before the halo exchange starts (multi-GPU) */
     /* modelled shared-memory wavefronts per 32-lane 8-byte access (2.0 = conflict-free) */
     double est_gather_wavefronts, est_scatter_wavefronts;
 } hgpu_layout_t;
