@@ -203,14 +203,14 @@ def block_grid(world: int) -> tuple[int, int, int]:
     return bx, by, bz
 
 
-def workload_config(world: int, n: int) -> dict:
+def workload_config(world: int, n: int, halo: str = "p2p") -> dict:
     bx, by, bz = block_grid(world)
     return {"workload": f"configs[1]: layered half-space (LOH.1 values), uniform octree mesh {n}^3 elements "
                         f"per GPU (h={H_M:g} m), rayleigh damping, effective stiffness, point source, 5 stations",
             "elements_per_gpu": n ** 3, "global_elements": n ** 3 * world,
             "global_grid": [n * bx, n * by, n * bz], "dt": DT,
-            "partition": f"{world} Morton-contiguous block(s) (octor_partitiontree rule), halo via NCCL send/recv"
-            if world > 1 else "single rank",
+            "partition": f"{world} Morton-contiguous block(s) (octor_partitiontree rule), halo exchange over "
+                         f"{halo} overlapped with interior tiles" if world > 1 else "single rank",
             "l2": "inputs larger than L2 (node arrays >= 400 MB each step); no explicit flush"}
 
 
@@ -220,10 +220,13 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="elements per edge per GPU")
+    ap.add_argument("--edge", dest="n", type=int, default=256, help="elements per edge per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after all tiles, one stream")
     ap.add_argument("--tile-nodes", type=int, default=0)
+    ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
+                    help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -244,6 +247,11 @@ def main() -> None:
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU path)")
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (NCCL's version
+    # banner, for one) is sent to stderr by pointing fd 1 there until the line is ready
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not hb.SO.exists():
@@ -280,11 +288,16 @@ def main() -> None:
     t0 = time.time()
     s = hb.Solver(mesh, dt=DT, damping=hb.RAYLEIGH, stiffness=hb.EFFECTIVE, freq=FREQ,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
-                  tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS)
+                  tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0))
     if world > 1:
-        uid = [hb.Solver.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        s.comm_init(uid[0])
+        if args.halo == "nccl":
+            uid = [hb.Solver.comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            s.comm_init(uid[0])
+        else:
+            blobs = [None] * world
+            dist.all_gather_object(blobs, s.p2p_export())
+            s.p2p_connect(blobs)
     t_init = time.time() - t0
     layout = s.layout()
     stream = torch.cuda.ExternalStream(s.stream, device=torch.device("cuda", local))
@@ -365,7 +378,7 @@ def main() -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n),
+            "config": workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv"),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "tile_kernel<true,false> (element force + update, fused)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -377,7 +390,8 @@ def main() -> None:
             "cpu_baseline": cpu,
             "layout": {k: layout[k] for k in ("tile_nodes", "ntiles", "max_tile_nodes", "tile_elems_total",
                                               "tile_halo_total", "n_regular", "n_special", "device_bytes",
-                                              "smem_bytes", "block_threads")},
+                                              "smem_bytes", "block_threads", "grid_ctas", "ctas_per_sm",
+                                              "early_tiles")},
             "setup_s": {"mesh": round(t_mesh, 1), "hgpu_init": round(t_init, 1)},
         }
         traffic_file = ROOT / "profiles" / "traffic.json"
@@ -386,7 +400,10 @@ def main() -> None:
                 line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("tile_kernel_bytes_per_launch")
             except Exception:
                 pass
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
