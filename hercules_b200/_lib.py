@@ -47,7 +47,9 @@ class Layout(C.Structure):
                 ("max_tile_elems", i32), ("tile_elems_total", i64), ("tile_halo_total", i64),
                 ("n_regular", i64), ("n_special", i64), ("device_bytes", i64),
                 ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32), ("early_tiles", i32),
-                ("est_gather_wavefronts", f64), ("est_scatter_wavefronts", f64)]
+                ("est_gather_wavefronts", f64), ("est_scatter_wavefronts", f64),
+                ("max_tile_acc", i32), ("max_tile_recs", i32), ("max_tile_srcs", i32), ("pad_", i32),
+                ("partial_slots", i64), ("deps_total", i64)]
 
 
 # every symbol include/hercules_gpu.h declares: name -> (restype, argtypes)

@@ -138,8 +138,15 @@ struct hgpu_solver {
     int32_t *t_halo_id = nullptr;
     uint4 *t_ent_slot = nullptr;         // per entry 8 x uint16 = 3 * slot
     double *t_ent_coef = nullptr;        // per entry c1, c2, beta
+    uint2 *t_rec = nullptr;              // finish records
+    int32_t *t_src = nullptr, *t_dep = nullptr;
+    double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
+    unsigned int *t_flag = nullptr;      // [ntiles] epoch of each tile's last publish
+    unsigned int epoch = 0;              // one per pass over all tiles
+    int32_t n_self = 0;
     double *nt3 = nullptr;               // [N][3] {+-1/mass, m2, m1} for the fused update
-    int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, grid_late = 0, cap_slots = 0, cap_owned = 0, ctas_per_sm = 0;
+    int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, grid_late = 0, cap_slots = 0, cap_acc = 0, cap_owned = 0,
+        cap_recs = 0, cap_srcs = 0, ctas_per_sm = 0;
     // special-node path
     int32_t nS = 0; int32_t *d_slist = nullptr;
     int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
@@ -261,27 +268,44 @@ extern "C" int hgpu_device_count(void)
     return n;
 }
 
+// Shared memory of the step kernel, in bytes, for given capacities (u2e: the elements read u2).
+static int finish_buf_bytes(int32_t cap_recs, int32_t cap_srcs) { return 8 * cap_recs + 4 * cap_srcs + 4 * CAP_DEPS; }
+// bytes besides the stages and the accumulator: pend [recs][3] + spart [srcs][3] + srm [recs]
+// doubles, and two buffers of finish data
+static int finish_smem_bytes(int32_t cap_recs, int32_t cap_srcs)
+{
+    return (4 * cap_recs + 3 * cap_srcs) * (int)sizeof(double) + 2 * finish_buf_bytes(cap_recs, cap_srcs);
+}
+static int step_smem_bytes(bool u2e, int32_t cap_slots, int32_t cap_acc, int32_t cap_owned, int32_t cap_recs, int32_t cap_srcs)
+{
+    const int stage = 3 * cap_slots + 3 * (u2e ? cap_slots : cap_owned);
+    return (2 * stage + 3 * cap_acc) * (int)sizeof(double) + finish_smem_bytes(cap_recs, cap_srcs);
+}
+
 // Tile capacities for a device with max_smem bytes of opt-in shared memory per CTA.
 // Two CTAs per SM: each may use half of the SM's shared memory minus the 1 KB the system reserves
-// per CTA.  Per CTA: 2 stages x (u1 + u2) x cap_slots nodes + cap_owned accumulator nodes.
-static void tile_caps(int max_smem, int32_t tile_nodes, int32_t *cap_owned_o, int32_t *cap_slots_o,
-                      int32_t *elem_block_o)
+// per CTA.  Per CTA: 2 stages x (u1 + u2) x cap_slots nodes + the accumulator (owned + published
+// nodes) + the pending buffer (owned nodes) + 2 finish buffers.
+static TileCaps tile_caps(int max_smem, int32_t tile_nodes)
 {
     const int per_cta = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
+    TileCaps c;
+    c.max_recs = 256; c.max_srcs = 320;      // multiples of 16
     int32_t cap_owned = tile_nodes > 0 ? tile_nodes : 730;
     const char *env = getenv("HGPU_TILE_NODES");
     if (tile_nodes <= 0 && env && atoi(env) > 0) cap_owned = atoi(env);
     cap_owned = std::max(2, cap_owned & ~1);
-    int32_t elem_block = 512;
+    c.elem_block = 512;
     const char *eenv = getenv("HGPU_ELEM_BLOCK");
-    if (eenv && atoi(eenv) > 0) elem_block = atoi(eenv);
-    int32_t cap_slots = (per_cta / 8 - 3 * cap_owned) / 12;
-    if (cap_slots <= cap_owned) {
-        cap_owned = (per_cta / 8 / 18) & ~1;       // owned : staged about 1 : 1.25
-        cap_slots = (per_cta / 8 - 3 * cap_owned) / 12;
-    }
-    cap_slots = std::min(cap_slots, 65535 / 3) & ~15;  // 3*cap_slots doubles = whole 128-byte rows per array
-    *cap_owned_o = cap_owned; *cap_slots_o = cap_slots; *elem_block_o = elem_block;
+    if (eenv && atoi(eenv) > 0) c.elem_block = atoi(eenv);
+    const int budget = (per_cta - finish_smem_bytes(c.max_recs, c.max_srcs)) / 8;     // doubles
+    // an interior tile of a uniform region stages and accumulates 9^3 nodes and owns 8^3 of them
+    const int32_t rest = budget / 15;                      // 12 S + 3 A with S = A
+    c.max_owned = cap_owned;
+    c.max_acc = std::max(16, std::min(rest, 65535 / 3) & ~15);
+    c.max_slots = c.max_acc;
+    c.max_owned = std::min(c.max_owned, c.max_acc);
+    return c;
 }
 
 static inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
@@ -398,8 +422,8 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
     // force first (source assignment, hanging-node transfer, halo exchange), or unless its
     // mass2_minusaM / mass_minusaM differ between components (absorbing-boundary dashpots,
     // psolve.c:3445-3473): the fused path keeps one scalar of each per node.
+    std::vector<uint8_t> cls((size_t)N, NODE_REGULAR);
     {
-        std::vector<uint8_t> cls((size_t)N, NODE_REGULAR);
         if (params->flags & HGPU_FLAG_NO_FUSE) std::fill(cls.begin(), cls.end(), (uint8_t)NODE_SPECIAL);
         for (int32_t i = 0; i < params->nloaded; i++) cls[params->loaded_lnid[i]] = NODE_SPECIAL;
         const bool multi = params->nranks > 1;
@@ -438,9 +462,13 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         int max_smem = 0, nsm = 0;
         TRYCU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev));
         TRYCU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->dev));
-        int32_t cap_owned, cap_slots, elem_block;
-        tile_caps(max_smem, params->tile_nodes, &cap_owned, &cap_slots, &elem_block);
-        if (!build_tile_plan(E, N, mesh->elem_lnid, elem_block, cap_owned, cap_slots, s->plan, err)) {
+        const TileCaps caps = tile_caps(max_smem, params->tile_nodes);
+        // tiles owning a node of the exchange / hanging-node phases must not wait for anybody
+        // ("self" tiles); without the fused update every node's force goes to the force array and
+        // no node needs a record of its own
+        const bool fused = !(params->flags & HGPU_FLAG_NO_FUSE);
+        if (!build_tile_plan(E, N, mesh->elem_lnid, caps, params->nranks > 1 ? early_node.data() : nullptr,
+                             fused ? cls.data() : nullptr, s->plan, err)) {
             hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
         }
         TilePlan &pl = s->plan;
@@ -454,53 +482,76 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             coef[3 * k] = et[0]; coef[3 * k + 1] = et[1];
             coef[3 * k + 2] = et[0] != 0.0 ? et[2] / et[0] : 0.0;
         }
-        // processing order: tiles owning a node that the exchange / hanging-node phases read or
-        // write come first, so those phases can run while the remaining tiles are evaluated
+        // processing order: self tiles (they own the nodes the exchange / hanging-node phases read
+        // or write) first, so those phases can run while the remaining tiles are evaluated; the
+        // rest in ascending order, which is also the order of their dependencies
         {
             std::vector<int32_t> order;
             order.reserve((size_t)pl.ntiles);
-            std::vector<uint8_t> is_early((size_t)pl.ntiles, 0);
-            for (int32_t t = 0; t < pl.ntiles; t++)
-                for (int32_t n = pl.node_off[t]; n < pl.node_off[(size_t)t + 1]; n++)
-                    if (early_node[n]) { is_early[t] = 1; break; }
-            for (int32_t t = 0; t < pl.ntiles; t++) if (is_early[t]) order.push_back(t);
-            s->n_early = (int32_t)order.size();
-            for (int32_t t = 0; t < pl.ntiles; t++) if (!is_early[t]) order.push_back(t);
-            std::vector<int32_t> meta(8 * (size_t)pl.ntiles, 0);
+            for (int32_t t = 0; t < pl.ntiles; t++) if (pl.tile_self[t]) order.push_back(t);
+            s->n_early = s->n_self = (int32_t)order.size();
+            for (int32_t t = 0; t < pl.ntiles; t++) if (!pl.tile_self[t]) order.push_back(t);
+            std::vector<int32_t> meta((size_t)META_INTS * (size_t)pl.ntiles, 0);
             for (int32_t i = 0; i < pl.ntiles; i++) {
                 const int32_t t = order[i];
-                int32_t *m = meta.data() + 8 * (size_t)i;
+                int32_t *m = meta.data() + (size_t)META_INTS * (size_t)i;
                 m[0] = pl.node_off[t]; m[1] = pl.node_off[(size_t)t + 1];
                 m[2] = pl.halo_off[t]; m[3] = pl.halo_off[(size_t)t + 1];
                 m[4] = pl.elem_off[t]; m[5] = pl.elem_off[(size_t)t + 1];
-                m[6] = t;
+                m[6] = pl.elem_core[t]; m[7] = pl.halo_pub[t];
+                m[8] = pl.rec_off[t]; m[9] = pl.rec_off[(size_t)t + 1];
+                m[10] = pl.src_off[t]; m[11] = pl.src_off[(size_t)t + 1];
+                m[12] = pl.dep_off[t]; m[13] = pl.dep_off[(size_t)t + 1];
+                m[14] = t;
             }
             TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
         TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
+        {
+            std::vector<uint2> rec(pl.rec.size());
+            for (size_t i = 0; i < pl.rec.size(); i++)
+                rec[i] = make_uint2((uint32_t)pl.rec[i].slot3 | ((uint32_t)pl.rec[i].cnt << 16) | ((uint32_t)pl.rec[i].flags << 24),
+                                    (uint32_t)pl.rec[i].first);
+            TRY(upload(s, &s->t_rec, rec.data(), rec.size()));
+        }
+        TRY(upload(s, &s->t_src, pl.src.data(), pl.src.size()));
+        TRY(upload(s, &s->t_dep, pl.dep.data(), pl.dep.size()));
+        TRY(dalloc(s, &s->t_partial, 3 * pl.halo_id.size()));
+        TRYCU(cudaMemset(s->t_partial, 0, std::max<size_t>(1, 3 * pl.halo_id.size()) * sizeof(double)));
+        TRY(dalloc(s, &s->t_flag, (size_t)pl.ntiles));
+        TRYCU(cudaMemset(s->t_flag, 0, std::max<size_t>(1, (size_t)pl.ntiles) * sizeof(unsigned int)));
         // shared memory actually needed by this plan
-        s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_owned = (pl.max_tile_owned + 15) & ~15;
-        s->smem_u2 = (12 * s->cap_slots + 3 * s->cap_owned) * (int)sizeof(double);
-        s->smem_nou2 = (6 * s->cap_slots + 9 * s->cap_owned) * (int)sizeof(double);
+        s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_acc = (pl.max_tile_acc + 15) & ~15;
+        s->cap_owned = (pl.max_tile_owned + 15) & ~15;
+        s->cap_recs = std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15);
+        s->cap_srcs = std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15);
+        s->smem_u2 = step_smem_bytes(true, s->cap_slots, s->cap_acc, s->cap_owned, s->cap_recs, s->cap_srcs);
+        s->smem_nou2 = step_smem_bytes(false, s->cap_slots, s->cap_acc, s->cap_owned, s->cap_recs, s->cap_srcs);
         const char *benv = getenv("HGPU_BLOCK");
         if (benv && atoi(benv) == 384) s->block = 384;
         int occ = 0;
+        // the attribute belongs to the kernel, not to this solver: always ask for the whole per-CTA
+        // share so that solvers with different plans can coexist in one process
+        const int smem_cap = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
+        if (s->smem_u2 > smem_cap) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan needs %d bytes of shared memory (> %d)", s->smem_u2, smem_cap); }
 #define SETUP(T)                                                                                             \
         do {                                                                                                 \
-            TRYCU(cudaFuncSetAttribute(step_kernel<0, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2)); \
-            TRYCU(cudaFuncSetAttribute(step_kernel<1, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));   \
-            TRYCU(cudaFuncSetAttribute(step_kernel<2, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));   \
-            TRYCU(cudaFuncSetAttribute(step_kernel<0, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_nou2));  \
-            TRYCU(cudaFuncSetAttribute(step_kernel<1, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));    \
-            TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_u2));    \
+            TRYCU(cudaFuncSetAttribute(step_kernel<0, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            TRYCU(cudaFuncSetAttribute(step_kernel<1, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            TRYCU(cudaFuncSetAttribute(step_kernel<2, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            TRYCU(cudaFuncSetAttribute(step_kernel<0, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
+            TRYCU(cudaFuncSetAttribute(step_kernel<1, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
+            TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
 #undef SETUP
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
         s->ctas_per_sm = occ;
+        // every CTA of a launch must be resident: a tile's finish phase spins on flags raised by
+        // CTAs of the same launch
         s->grid = std::max(1, std::min(pl.ntiles, nsm * occ));
         {
             int reserve = 2;
@@ -509,7 +560,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             s->grid_late = std::max(1, (nsm - reserve) * occ);
         }
         const char *genv = getenv("HGPU_GRID");
-        if (genv && atoi(genv) > 0) s->grid = std::min(pl.ntiles, atoi(genv));
+        if (genv && atoi(genv) > 0) s->grid = std::min(std::min(pl.ntiles, atoi(genv)), nsm * occ);
     }
     TRYCU(cudaStreamSynchronize(s->stream));
     TRYCU(cudaDeviceSynchronize());
@@ -535,6 +586,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
     dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id);
+    dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
     dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
@@ -575,7 +627,10 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.nt3 = s->nt3; A.Kd = s->Kd;
     A.tile_meta = s->t_meta; A.halo_id = s->t_halo_id;
     A.ent_slot = s->t_ent_slot; A.ent_coef = s->t_ent_coef;
-    A.tile_begin = begin; A.ntiles = end; A.cap_slots = s->cap_slots; A.cap_owned = s->cap_owned;
+    A.rec = s->t_rec; A.src = s->t_src; A.dep = s->t_dep; A.partial = s->t_partial; A.flag = s->t_flag;
+    A.epoch = s->epoch;
+    A.tile_begin = begin; A.ntiles = end; A.cap_slots = s->cap_slots; A.cap_acc = s->cap_acc; A.cap_owned = s->cap_owned;
+    A.cap_recs = s->cap_recs; A.cap_srcs = s->cap_srcs;
     A.fuse_update = fuse ? 1 : 0;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
     const int mode = tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
@@ -583,6 +638,7 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
     const int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin), B = s->block;
+    if (begin == 0) A.epoch = ++s->epoch;       // a new pass over the tiles (a split pass shares one epoch)
 #define LAUNCH(T)                                                                                \
     do {                                                                                         \
         if (dense) {                                                                             \
@@ -1040,11 +1096,32 @@ extern "C" void *hgpu_stream(hgpu_solver_t *s) { return s ? (void *)s->stream : 
 extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu_layout_t *out)
 {
     if (!mesh || !out || !mesh->elem_lnid) return fail(HGPU_EINVAL, "null argument");
+    if (mesh->lenum < 0 || mesh->nharbored <= 0) return fail(HGPU_EINVAL, "bad mesh counts");
     TilePlan pl;
     std::string err;
-    int32_t cap_owned, cap_slots, elem_block;
-    tile_caps(232448, tile_nodes, &cap_owned, &cap_slots, &elem_block);
-    if (!build_tile_plan(mesh->lenum, mesh->nharbored, mesh->elem_lnid, elem_block, cap_owned, cap_slots, pl, err))
+    const TileCaps caps = tile_caps(232448, tile_nodes);
+    // nodes of the halo schedules and the hanging-node lists (when given) make their tiles "self"
+    // tiles, as hgpu_init does on a multi-rank mesh
+    std::vector<uint8_t> self_node;
+    {
+        const hgpu_msglist_t *lists[4] = {&mesh->dn_c, &mesh->dn_s, &mesh->an_c, &mesh->an_s};
+        for (const hgpu_msglist_t *l : lists) {
+            int32_t tot = 0;
+            for (int32_t i = 0; i < l->count; i++) tot += l->nodes[i];
+            if (tot > 0 && self_node.empty()) self_node.assign((size_t)mesh->nharbored, 0);
+            for (int32_t i = 0; i < tot; i++) {
+                if (l->mapping[i] < 0 || l->mapping[i] >= mesh->nharbored) return fail(HGPU_EINVAL, "mapping entry out of range");
+                self_node[l->mapping[i]] = 1;
+            }
+        }
+        if (!self_node.empty() && mesh->dnode)
+            for (int32_t d = 0; d < mesh->ldnnum; d++) {
+                const int32_t *dn = mesh->dnode + 6 * (size_t)d;
+                for (int a = 0; a < 6; a++) if (a != 1 && dn[a] >= 0 && dn[a] < mesh->nharbored) self_node[dn[a]] = 1;
+            }
+    }
+    if (!build_tile_plan(mesh->lenum, mesh->nharbored, mesh->elem_lnid, caps,
+                         self_node.empty() ? nullptr : self_node.data(), nullptr, pl, err))
         return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
     if (!validate_tile_plan(mesh->lenum, mesh->nharbored, mesh->elem_lnid, pl, err))
         return fail(HGPU_EINVAL, "tile plan check: %s", err.c_str());
@@ -1054,8 +1131,13 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     out->tile_elems_total = (int64_t)pl.elem_id.size();
     out->tile_halo_total = pl.halo_nodes_total;
     estimate_wavefronts(pl, &out->est_gather_wavefronts, &out->est_scatter_wavefronts);
-    out->smem_bytes = (12 * ((pl.max_tile_nodes + 15) & ~15) + 3 * ((pl.max_tile_owned + 15) & ~15)) * (int)sizeof(double);
+    out->smem_bytes = step_smem_bytes(true, (pl.max_tile_nodes + 15) & ~15, (pl.max_tile_acc + 15) & ~15,
+                                      (pl.max_tile_owned + 15) & ~15, std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15),
+                                      std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15));
     out->block_threads = 256;
+    for (int32_t t = 0; t < pl.ntiles; t++) out->early_tiles += pl.tile_self[t];
+    out->max_tile_acc = pl.max_tile_acc; out->max_tile_recs = pl.max_tile_recs; out->max_tile_srcs = pl.max_tile_srcs;
+    out->partial_slots = (int64_t)pl.halo_id.size(); out->deps_total = (int64_t)pl.dep.size();
     return HGPU_OK;
 }
 
@@ -1063,6 +1145,7 @@ extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
 {
     if (!s || !out) return fail(HGPU_EINVAL, "null argument");
     const TilePlan &pl = s->plan;
+    memset(out, 0, sizeof *out);
     out->tile_nodes = pl.max_tile_owned; out->ntiles = pl.ntiles;
     out->max_tile_nodes = pl.max_tile_nodes; out->max_tile_elems = pl.max_tile_elems;
     out->tile_elems_total = (int64_t)pl.elem_id.size();
@@ -1072,6 +1155,8 @@ extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
     out->device_bytes = s->device_bytes;
     out->smem_bytes = s->smem_u2; out->block_threads = s->block;
     out->grid_ctas = s->grid; out->ctas_per_sm = s->ctas_per_sm; out->early_tiles = s->n_early;
+    out->max_tile_acc = pl.max_tile_acc; out->max_tile_recs = pl.max_tile_recs; out->max_tile_srcs = pl.max_tile_srcs;
+    out->partial_slots = (int64_t)pl.halo_id.size(); out->deps_total = (int64_t)pl.dep.size();
     return HGPU_OK;
 }
 

@@ -14,27 +14,64 @@ namespace hgpu {
 // the force array and the reference's adjust/exchange/update sequence.
 enum : uint8_t { NODE_REGULAR = 0, NODE_SPECIAL = 1 };
 
-// Owner-computes tiling of the node range.  Tile t owns the contiguous node
-// ids [node_off[t], node_off[t+1]) (even start); it evaluates every element incident to an owned
-// node, so the force on an owned node is complete inside the tile and no atomics are needed.
+// One owned node of a tile that needs more than "advance what the tile accumulated": it receives
+// partial forces published by other tiles (cnt of them, src[first .. first+cnt) relative to the
+// tile's src range) and / or it is a SPECIAL node whose force is handed to the force array.
+struct FinishRec {
+    uint16_t slot3;     // 3 * tile-local slot of the owned node
+    uint8_t  cnt;       // incoming partial forces (0..8)
+    uint8_t  flags;     // bit 0: SPECIAL node
+    int32_t  first;     // into the tile's src range
+};
+static_assert(sizeof(FinishRec) == 8, "FinishRec is staged as 8-byte records");
+
+// Tiling of the mesh (DESIGN.md sections 3-4).  Tile t OWNS the contiguous node ids
+// [node_off[t], node_off[t+1]) (even start) and is the one tile that evaluates its CORE elements
+// -- those whose corner 0 it owns -- so every element is evaluated exactly once.  What a core
+// element adds to nodes of other tiles is PUBLISHED as a per-(tile, node) partial force and summed
+// by the owner ("shared" tiles).  A "self" tile does not wait for anybody: it additionally
+// evaluates the foreign elements incident to its nodes (EXTRA entries, accumulated on owned nodes
+// only) and ignores what others publish for it; tiles whose forces the halo exchange needs first
+// are built that way.
 struct TilePlan {
-    int32_t tile_nodes = 0;       // cap on owned nodes per tile
     int32_t ntiles = 0;
     int32_t max_tile_owned = 0;
-    int32_t max_tile_nodes = 0;   // owned + gathered
+    int32_t max_tile_acc = 0;     // owned + publishable halo slots
+    int32_t max_tile_nodes = 0;   // all staged slots
     int32_t max_tile_elems = 0;
+    int32_t max_tile_recs = 0, max_tile_srcs = 0;
     std::vector<int32_t>  node_off;   // [ntiles+1]
+    std::vector<uint8_t>  tile_self;  // [ntiles]
     std::vector<int32_t>  elem_off;   // [ntiles+1] into elem_id / elem_slot
+    std::vector<int32_t>  elem_core;  // [ntiles] the first elem_core[t] entries of a tile are its core elements
     std::vector<int32_t>  elem_id;    // element evaluated by this tile entry
     std::vector<uint16_t> elem_slot;  // [entries][8] tile-local slot of each corner node
-    std::vector<int32_t>  halo_off;   // [ntiles+1] into halo_id
+    std::vector<int32_t>  halo_off;   // [ntiles+1] into halo_id; also the numbering of published partial forces
+    std::vector<int32_t>  halo_pub;   // [ntiles] the first halo_pub[t] halo slots are published
     std::vector<int32_t>  halo_id;    // gathered (non-owned) node ids; slot = owned_count + index; -1 = unused slot
+    std::vector<int32_t>  rec_off;    // [ntiles+1]
+    std::vector<FinishRec> rec;
+    std::vector<int32_t>  src_off;    // [ntiles+1]
+    std::vector<int32_t>  src;        // index (halo_id numbering) of a published partial force
+    std::vector<int32_t>  dep_off;    // [ntiles+1]
+    std::vector<int32_t>  dep;        // tiles whose partial forces this tile reads (all lower-numbered)
     int64_t halo_nodes_total = 0;     // gathered nodes over all tiles (unused slots not counted)
+    int64_t core_total = 0;           // = number of elements
 };
 
-// Builds the plan; returns false and sets err on inconsistent input.
-bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, int32_t elem_block,
-                     int32_t max_owned, int32_t max_slots, TilePlan &plan, std::string &err);
+struct TileCaps {
+    int32_t elem_block;   // elements per block of the Morton-ordered element list that seeds a tile
+    int32_t max_owned;    // owned nodes per tile
+    int32_t max_acc;      // owned + published slots (shared-memory accumulator)
+    int32_t max_slots;    // staged nodes
+    int32_t max_recs, max_srcs;
+};
+
+// Builds the plan; returns false and sets err on inconsistent input.  self_node (may be null):
+// tiles owning a flagged node become "self" tiles.  special_node (may be null): SPECIAL flags.
+bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &caps,
+                     const uint8_t *self_node, const uint8_t *special_node, TilePlan &plan,
+                     std::string &err);
 
 bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePlan &plan, std::string &err);
 

@@ -108,13 +108,24 @@ __device__ __forceinline__ void scale_modes(const double (&tx)[8], const double 
 }
 
 // ------------------------------------------------------------------------------------------
-// step_kernel: persistent, software-pipelined owner-computes kernel.
+// step_kernel: persistent, software-pipelined tile kernel.
 //
-// One CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...  While tile i is being computed out
-// of shared-memory stage i&1, the displacements of tile i+1 stream into the other stage with
-// cp.async (LDGSTS): 16-byte copies for the owned node range (contiguous, even start), 8-byte
-// copies for the gathered halo nodes.  The per-entry element data (8 slot offsets + c1, c2, beta)
-// is prefetched into registers one round ahead.  Two CTAs per SM hide each other's barriers.
+// One CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the processing order.  Per tile:
+//
+//   stage     displacements of the tile's nodes arrive in shared memory by cp.async (LDGSTS), one
+//             tile ahead: 16-byte copies for the owned node range (contiguous, even start), 8-byte
+//             copies for the gathered halo nodes
+//   elements  one thread per entry: gather 8 corners, factored operator, accumulate into the
+//             tile's shared-memory accumulator in eight corner passes (a node is corner j of at
+//             most one element, so no two threads touch one accumulator within a pass)
+//   publish   what the tile's core elements added to nodes of HIGHER tiles goes to partial[]
+//             (one slot per (tile, node)), then the tile's flag is raised to this pass's epoch
+//   finish    one tile LATER (so nobody waits in practice): wait for the flags of the lower tiles
+//             that publish for this tile's nodes, add their partial forces in a fixed order, and
+//             advance the owned nodes (central difference, psolve.c:4078-4108) -- or hand the
+//             force of SPECIAL nodes to the force array
+//
+// Every element is evaluated once, every sum has a fixed order: no atomics, bit-reproducible.
 //
 //   MODE 0: w = u1                     stiffness term only            (damping none / mass)
 //   MODE 1: w = u1 + beta (u1 - u2)    stiffness + Rayleigh damping   beta = c3/c1 = c4/c2 = b/dt
@@ -128,22 +139,39 @@ struct StepArgs {
     const double *__restrict__ nt3;     // [N][3] {1/mass_simple, mass2_minusaM, mass_minusaM} of nodes the
                                         // fused update may advance; first entry negative = hand the force on
     const double *__restrict__ Kd;      // dense K1|K2 as [2][24][24] (conventional only)
-    const int4 *__restrict__ tile_meta; // per tile, in processing order: {n0, n1, hb, h1}, {eb, e1, -, -}
+    const int4 *__restrict__ tile_meta; // per tile, in processing order: 4 x int4, see TileMeta
     const int32_t *__restrict__ halo_id;
     const uint4 *__restrict__ ent_slot; // per entry 8 x uint16: 3 * tile-local slot of each corner
     const double *__restrict__ ent_coef;// per entry c1, c2, beta
+    const uint2 *__restrict__ rec;      // FinishRec {slot3 | cnt << 16 | flags << 24, first}
+    const int32_t *__restrict__ src;    // partial index per incoming contribution
+    const int32_t *__restrict__ dep;    // tile ids whose flags a tile waits for
+    double *partial;                    // [halo slots][3] published partial forces
+    unsigned int *flag;                 // [ntiles] epoch of the tile's last publish
+    unsigned int epoch;
     int32_t tile_begin, ntiles;         // this launch processes tile_meta[tile_begin .. ntiles)
     int32_t cap_slots;                  // staged nodes per stage
-    int32_t cap_owned;                  // accumulator nodes
-    int32_t fuse_update;                // 1: advance owned nodes flagged in nt3 here
+    int32_t cap_acc;                    // accumulator nodes (owned + published)
+    int32_t cap_owned;                  // owned nodes (pending buffer)
+    int32_t cap_recs, cap_srcs;         // finish records / sources staged per tile
+    int32_t fuse_update;                // 1: advance owned REGULAR nodes here
 };
 
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc)
+constexpr int META_INTS = 16;           // per tile
+constexpr int META_RING = 8;
+constexpr int CAP_DEPS = 64;            // dependency ids staged in shared memory per tile
+
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
 }
-__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc)
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
@@ -173,30 +201,46 @@ __device__ __forceinline__ int ldg_i32_pinned(const int32_t *p)
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
+// Flags are polled with relaxed loads and raised with a relaxed store after a gpu-scope fence;
+// the data they guard (partial forces) is written with st.cg and read with cp.async.cg / ld.cg,
+// i.e. at L2, where the fence has made it visible -- no L1 invalidation is needed on either side.
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void publish_flag(unsigned int *p, unsigned int v)
+{
+    asm volatile("fence.acq_rel.gpu;\n\tst.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Raw offsets as loaded (differences are taken where they are used, so that nothing consumes a
 // freshly requested value early).
 struct TileMeta {
-    int n0, n1, hb, h1, eb, e1;
+    int n0, n1, hb, h1;         // owned node range; halo_id range
+    int eb, e1, ncore, npub;    // entry range; core entries; published halo slots
+    int rb, r1, sb, s1;         // finish records; sources
+    int db, d1, id;             // dependencies; tile id (flag index)
     __device__ __forceinline__ int nown() const { return n1 - n0; }
     __device__ __forceinline__ int nh() const { return h1 - hb; }
     __device__ __forceinline__ int ne() const { return e1 - eb; }
 };
 
-// Tile offsets travel through a 4-deep shared-memory ring filled by cp.async (no registers, no
-// scoreboard): slot i & 3 holds the offsets of the CTA's i-th tile.
+// Tile offsets travel through a shared-memory ring filled by cp.async (no registers, no
+// scoreboard): slot i & (META_RING-1) holds the offsets of the CTA's i-th tile.
 __device__ __forceinline__ void fetch_meta_async(const StepArgs &A, int t, int *slot, int tid)
 {
-    if (tid < 2) {
-        const unsigned d = (unsigned)__cvta_generic_to_shared(slot + 4 * tid);
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(A.tile_meta + 2 * (size_t)t + tid) : "memory");
-    }
+    if (tid < 4) cp_async16(slot + 4 * tid, A.tile_meta + 4 * (size_t)t + tid);
 }
 __device__ __forceinline__ TileMeta read_meta(const int *slot)
 {
     const volatile int *v = slot;
     TileMeta m;
-    m.n0 = v[0]; m.n1 = v[1]; m.hb = v[2]; m.h1 = v[3]; m.eb = v[4]; m.e1 = v[5];
+    m.n0 = v[0]; m.n1 = v[1]; m.hb = v[2]; m.h1 = v[3];
+    m.eb = v[4]; m.e1 = v[5]; m.ncore = v[6]; m.npub = v[7];
+    m.rb = v[8]; m.r1 = v[9]; m.sb = v[10]; m.s1 = v[11];
+    m.db = v[12]; m.d1 = v[13]; m.id = v[14];
     return m;
 }
 
@@ -261,6 +305,19 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m,
     }
 }
 
+// Finish data of one tile (records, sources, dependency ids) -> shared memory, by cp.async.
+// Layout of one buffer: uint2 rec[cap_recs] | int src[cap_srcs] | int dep[CAP_DEPS].
+__device__ __forceinline__ void stage_finish(const StepArgs &A, const TileMeta &m, char *buf, int tid, int nthr)
+{
+    uint2 *srec = reinterpret_cast<uint2 *>(buf);
+    int *ssrc = reinterpret_cast<int *>(buf + 8 * (size_t)A.cap_recs);
+    int *sdep = ssrc + A.cap_srcs;
+    const int nr = min(m.r1 - m.rb, A.cap_recs), ns = min(m.s1 - m.sb, A.cap_srcs), ndp = min(m.d1 - m.db, CAP_DEPS);
+    for (int i = tid; i < nr; i += nthr) cp_async8(srec + i, A.rec + m.rb + i);
+    for (int i = tid; i < ns; i += nthr) cp_async4(ssrc + i, A.src + m.sb + i);
+    if (tid < ndp) cp_async4(sdep + tid, A.dep + m.db + tid);
+}
+
 constexpr int NT_PRE = 3;
 
 __device__ __forceinline__ void load_node_tables(const StepArgs &A, const TileMeta &m, int tid, int nthr,
@@ -278,20 +335,94 @@ __device__ __forceinline__ void load_node_tables(const StepArgs &A, const TileMe
     }
 }
 
-// solver_compute_displacement (psolve.c:4078-4108) for one owned node whose force is complete in
-// acc: acc <- u(t+dt).  rm <= 0 flags a node that is advanced later from the force array.
-__device__ __forceinline__ void advance_node(const StepArgs &A, double *acc, const double *su1,
-                                             const double *su2, size_t g0, int i, double rm, double m2,
-                                             double m1)
+// The tile's own share of solver_compute_displacement (psolve.c:4078-4108) for one owned node, in
+// place: acc <- (acc + m2 u1 - m1 u2) / mass for a REGULAR node (rm > 0), the plain force otherwise;
+// partial forces of other tiles are added, scaled alike, when the tile is finished.
+__device__ __forceinline__ void settle_node(double *acc, const double *su1, const double *su2, int i,
+                                            double rm, double m2, double m1)
 {
     const int k = 3 * i;
     if (rm > 0.0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++)
-            acc[k + c] = (acc[k + c] + (m2 * su1[k + c] - m1 * su2[k + c])) * rm;
-    } else {
-#pragma unroll
-        for (int c = 0; c < 3; c++) A.force[g0 + k + c] += acc[k + c];
+        for (int c = 0; c < 3; c++) acc[k + c] = (acc[k + c] + (m2 * su1[k + c] - m1 * su2[k + c])) * rm;
+    }
+}
+
+// Shared-memory buffers of the finish phase.
+struct FinishBufs {
+    double *pend;       // [cap_recs][3] own share of the record nodes of the tile being finished
+    double *spart;      // [cap_srcs][3] partial forces published by lower tiles
+    double *srm;        // [cap_recs]    nt3[node][0] of the record nodes
+};
+
+// Poll the flags of the lower tiles that publish for tile m's nodes (dependency ids in buf).
+__device__ __forceinline__ void poll_deps(const StepArgs &A, const TileMeta &m, const char *buf, int tid, int nthr)
+{
+    const int *sdep = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs) + A.cap_srcs;
+    const int ndep = m.d1 - m.db;
+    for (int d = tid; d < ndep; d += nthr) {
+        const int dt = d < CAP_DEPS ? sdep[d] : __ldg(A.dep + m.db + d);
+        const unsigned int *f = A.flag + dt;
+        while ((int)(ld_relaxed_u32(f) - A.epoch) < 0) __nanosleep(32);
+    }
+}
+
+// Request the partial forces tile m reads, and the node-table entry of its record nodes
+// (cp.async.cg: served by L2, where the publishers' fences made them visible).
+__device__ __forceinline__ void request_partials(const StepArgs &A, const TileMeta &m, const char *buf,
+                                                 const FinishBufs &fb, int tid, int nthr)
+{
+    const uint2 *srec = reinterpret_cast<const uint2 *>(buf);
+    const int *ssrc = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs);
+    const int ns = min(m.s1 - m.sb, A.cap_srcs), nr = min(m.r1 - m.rb, A.cap_recs);
+    for (int q = tid; q < ns; q += nthr) {
+        const double *pp = A.partial + 3 * (size_t)ssrc[q];
+        cp_async8(fb.spart + 3 * q, pp); cp_async8(fb.spart + 3 * q + 1, pp + 1); cp_async8(fb.spart + 3 * q + 2, pp + 2);
+    }
+    const double *nt = A.nt3 + 3 * (size_t)m.n0;
+    for (int r = tid; r < nr; r += nthr) cp_async8(fb.srm + r, nt + (srec[r].x & 0xffff));
+}
+
+// Finish a tile: add the partial forces of the lower tiles to the record nodes' own share (pend)
+// in a fixed order and store the result -- u(t+dt) of a REGULAR node, or the force of a SPECIAL
+// node (source term, hanging-node transfer, halo exchange and the list update follow).
+__device__ __forceinline__ void finish_tile(const StepArgs &A, const TileMeta &m, const char *buf,
+                                            const FinishBufs &fb, int tid, int nthr, bool fuse)
+{
+    const uint2 *srec = reinterpret_cast<const uint2 *>(buf);
+    const int *ssrc = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs);
+    const int nrec = m.r1 - m.rb;
+    const size_t g0 = 3 * (size_t)m.n0;
+    for (int r = tid; r < nrec; r += nthr) {
+        const bool in_smem = r < A.cap_recs;
+        const uint2 rc = in_smem ? srec[r] : __ldg(A.rec + m.rb + r);
+        const int slot3 = rc.x & 0xffff, cnt = (rc.x >> 16) & 0xff, first = (int)rc.y;
+        const double rmv = in_smem ? fb.srm[r] : __ldg(A.nt3 + g0 + slot3);
+        const bool regular = fuse && rmv > 0.0;
+        const double scale = regular ? rmv : 1.0;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (in_smem && fuse) { s0 = fb.pend[3 * r]; s1 = fb.pend[3 * r + 1]; s2 = fb.pend[3 * r + 2]; }
+        for (int k = 0; k < cnt; k++) {
+            const int q = first + k;
+            double v0, v1, v2;
+            if (q < A.cap_srcs) { v0 = fb.spart[3 * q]; v1 = fb.spart[3 * q + 1]; v2 = fb.spart[3 * q + 2]; }
+            else {
+                const double *pp = A.partial + 3 * (size_t)__ldg(A.src + m.sb + q);
+                v0 = __ldcg(pp); v1 = __ldcg(pp + 1); v2 = __ldcg(pp + 2);
+            }
+            s0 = fma(v0, scale, s0); s1 = fma(v1, scale, s1); s2 = fma(v2, scale, s2);
+        }
+        if (regular) {
+            double *o = A.unext + g0 + slot3;
+            // a record beyond the staged ones kept its own share in unext
+            if (!in_smem) { s0 += o[0]; s1 += o[1]; s2 += o[2]; }
+            o[0] = s0; o[1] = s1; o[2] = s2;
+        } else {
+            // fused launch: the own share waited in pend; unfused: it is in the force array already
+            double *fo = A.force + g0 + slot3;
+            if (fuse && !in_smem) { const double *o = A.unext + g0 + slot3; s0 += o[0]; s1 += o[1]; s2 += o[2]; }
+            fo[0] += s0; fo[1] += s1; fo[2] += s2;
+        }
     }
 }
 
@@ -301,9 +432,15 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     constexpr bool U2E = MODE != 0;          // elements read u2
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const int S3 = 3 * A.cap_slots, O3 = 3 * A.cap_owned;
+    const int S3 = 3 * A.cap_slots, O3 = 3 * A.cap_owned, A3 = 3 * A.cap_acc;
     const int stage_doubles = S3 + (U2E ? S3 : O3);
     double *acc = smem + 2 * stage_doubles;
+    FinishBufs fb;
+    fb.pend = acc + A3;
+    fb.spart = fb.pend + 3 * A.cap_recs;
+    fb.srm = fb.spart + 3 * A.cap_srcs;
+    char *fbuf = reinterpret_cast<char *>(fb.srm + A.cap_recs);
+    const int fbuf_bytes = 8 * A.cap_recs + 4 * A.cap_srcs + 4 * CAP_DEPS;
     const bool fuse = A.fuse_update != 0;
 
     // Pipeline.  All global loads of a warp share one hardware scoreboard, so a consumer waits
@@ -311,17 +448,20 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     // consumed right BEFORE the next batch of loads is issued, and everything that can avoid
     // registers does:
     //   displacements : cp.async into the other stage, one tile ahead
-    //   tile offsets  : cp.async into a 4-slot ring, three tiles ahead
+    //   tile offsets  : cp.async into a ring, three tiles ahead
+    //   finish data   : cp.async when the tile's element phase starts (records, sources, deps)
+    //   partial forces: cp.async during the accumulation passes of the NEXT tile's last round,
+    //                   after the publishers' flags have been seen
     //   entries       : registers; enext -> ecur at the top of a round, then the following round's
     //                   entry is requested
     //   halo ids      : registers; requested before the accumulation passes of a tile's last round
     //                   for the tile that is staged at the top of the next iteration
     //   node tables   : registers; requested before the accumulation passes of the last round
-    __shared__ __align__(16) int smeta[4][8];
+    __shared__ __align__(16) int smeta[META_RING][META_INTS];
     const int G = gridDim.x;
     int t = A.tile_begin + blockIdx.x;
     if (t >= A.ntiles) return;
-    for (int k = tid; k < O3; k += nthr) acc[k] = 0.0;
+    for (int k = tid; k < A3; k += nthr) acc[k] = 0.0;
     fetch_meta_async(A, t, smeta[0], tid);
     if (t + G < A.ntiles) fetch_meta_async(A, t + G, smeta[1], tid);
     if (t + 2 * G < A.ntiles) fetch_meta_async(A, t + 2 * G, smeta[2], tid);
@@ -350,33 +490,47 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         const int tn = t + G;
         const bool has_next = tn < A.ntiles;
         const bool has_nn = tn + G < A.ntiles;
-        const int *m_cur = smeta[it & 3], *m_nxt = smeta[(it + 1) & 3], *m_nn = smeta[(it + 2) & 3];
+        const int *m_cur = smeta[it & (META_RING - 1)], *m_nxt = smeta[(it + 1) & (META_RING - 1)];
+        const int *m_nn = smeta[(it + 2) & (META_RING - 1)], *m_prv = smeta[(it - 1) & (META_RING - 1)];
+        const char *fb_prv = fbuf + ((it - 1) & 1) * fbuf_bytes;
         cp_async_wait_all();
-        __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1
+        __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1's stage
+        stage_finish(A, read_meta(m_cur), fbuf + (it & 1) * fbuf_bytes, tid, nthr);
         if (has_next) {
             double *n1 = smem + ((it + 1) & 1) * stage_doubles;
             const TileMeta nxt = read_meta(m_nxt);
             if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
-            if (tn + 2 * G < A.ntiles) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & 3], tid);
-            cp_async_commit();
+            if (tn + 2 * G < A.ntiles) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & (META_RING - 1)], tid);
         }
-        const TileMeta cur = read_meta(m_cur);
+        cp_async_commit();
+        // only what the element phase needs stays in registers; the rest of the tile's offsets is
+        // read again from the ring where it is used
+        struct { int n0, n1, eb, e1, ncore;
+                 __device__ __forceinline__ int nown() const { return n1 - n0; }
+                 __device__ __forceinline__ int ne() const { return e1 - eb; } } cur;
+        {
+            const volatile int *v = m_cur;
+            cur.n0 = v[0]; cur.n1 = v[1]; cur.eb = v[4]; cur.e1 = v[5]; cur.ncore = v[6];
+        }
         const int nown3 = 3 * cur.nown();
         const int nxt_eb = has_next ? ((const volatile int *)m_nxt)[4] : 0;
         const int nxt_ne = has_next ? ((const volatile int *)m_nxt)[5] - nxt_eb : 0;
-
-        // node tables of the (up to NT_PRE) owned nodes this thread advances, prefetched into
-        // registers before the last round's accumulation passes
+        // the previous tile is finished during this one: its publishers' flags are polled and its
+        // partial forces requested between the accumulation passes of the last round
+        bool prv_pending = it > 0;
         double ntv[NT_PRE][3];
-        bool nt_loaded = false;
 
-        // ---- element forces, accumulated per owned node ------------------------------------
+        // ---- element forces, accumulated per staged node ----------------------------------------
         for (int base = 0; base < cur.ne(); base += nthr) {
             const bool act = base + tid < cur.ne();
+            const bool last = base + nthr >= cur.ne();
+            // a core entry adds to every corner (owned or published); an extra entry of a self
+            // tile only to the owned ones
+            const uint32_t lim = base + tid < cur.ncore ? 0xffffffffu : (uint32_t)nown3;
             ecur = enext;
             // next round's entry (or the first round of the next tile) rides along with the math
-            if (base + nthr < cur.ne()) {
+            if (!last) {
                 if (base + nthr + tid < cur.ne()) enext = load_entry<U2E>(A, cur.eb + base + nthr + tid);
             } else if (tid < nxt_ne) {
                 enext = load_entry<U2E>(A, nxt_eb + tid);
@@ -432,58 +586,105 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                     }
                 }
             }
-            if (base + nthr >= cur.ne()) {
-                if (fuse) { load_node_tables(A, cur, tid, nthr, ntv); nt_loaded = true; }
+            if (last) {
+                if (fuse) load_node_tables(A, read_meta(m_cur), tid, nthr, ntv);
                 if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
             }
             // A node is corner j of at most one element (leaf octants do not overlap), so within
             // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
 #pragma unroll
             for (int j = 0; j < 8; j++) {
-                if (act && sl[j] < (uint32_t)nown3) {
+                if (act && sl[j] < lim) {
                     const int o = sl[j];
                     acc[o] += fx[j]; acc[o + 1] += fy[j]; acc[o + 2] += fz[j];
                 }
+                if (j == 2 && last && prv_pending) poll_deps(A, read_meta(m_prv), fb_prv, tid, nthr);
                 __syncthreads();
+                if (j == 2 && last && prv_pending) {
+                    request_partials(A, read_meta(m_prv), fb_prv, fb, tid, nthr);
+                    cp_async_commit();
+                }
             }
         }
         if (cur.ne() == 0) {                    // a tile of element-less nodes: keep the pipeline fed
             if (tid < nxt_ne) enext = load_entry<U2E>(A, nxt_eb + tid);
             if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
-        }
-
-        // ---- owned nodes: fused update, or hand the force on ------------------------------------
-        {
-            const size_t g0 = 3 * (size_t)cur.n0;
-            if (fuse) {
-                if (!nt_loaded) load_node_tables(A, cur, tid, nthr, ntv);
-                // node-wise: u(t+dt) replaces the force in acc; nodes flagged in nt3 keep their force
-#pragma unroll
-                for (int q = 0; q < NT_PRE; q++) {
-                    const int i = tid + q * nthr;
-                    if (i < cur.nown()) advance_node(A, acc, su1, su2, g0, i, ntv[q][0], ntv[q][1], ntv[q][2]);
-                }
-                for (int i = tid + NT_PRE * nthr; i < cur.nown(); i += nthr) {
-                    const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + i);
-                    advance_node(A, acc, su1, su2, g0, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
-                }
+            if (fuse) load_node_tables(A, read_meta(m_cur), tid, nthr, ntv);
+            if (prv_pending) {
+                poll_deps(A, read_meta(m_prv), fb_prv, tid, nthr);
                 __syncthreads();
-                // coalesced 128-bit copy-out (g0 is even); rows of flagged nodes carry their force,
-                // which the special-node update overwrites afterwards
-                double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);
-                for (int v = tid; v < (nown3 >> 1); v += nthr) {
-                    dst[v] = make_double2(acc[2 * v], acc[2 * v + 1]);
-                    acc[2 * v] = 0.0; acc[2 * v + 1] = 0.0;
-                }
-                if ((nown3 & 1) && tid == 0) { A.unext[g0 + nown3 - 1] = acc[nown3 - 1]; acc[nown3 - 1] = 0.0; }
-            } else {
-                for (int k = tid; k < nown3; k += nthr) {
-                    A.force[g0 + k] += acc[k];
-                    acc[k] = 0.0;
-                }
+                request_partials(A, read_meta(m_prv), fb_prv, fb, tid, nthr);
+                cp_async_commit();
             }
         }
-        if (!has_next) break;
+
+        // ---- publish what the core elements added to nodes of higher tiles ----------------------
+        {
+            const volatile int *v = m_cur;
+            const int np3 = 3 * v[7];
+            double *dst = A.partial + 3 * (size_t)v[2];
+            for (int k = tid; k < np3; k += nthr) {
+                __stcg(dst + k, acc[nown3 + k]);
+                acc[nown3 + k] = 0.0;
+            }
+        }
+        // ---- this tile's own share of the update, in place ---------------------------------------
+        if (fuse) {
+#pragma unroll
+            for (int q = 0; q < NT_PRE; q++) {
+                const int i = tid + q * nthr;
+                if (i < cur.nown()) settle_node(acc, su1, su2, i, ntv[q][0], ntv[q][1], ntv[q][2]);
+            }
+            for (int i = tid + NT_PRE * nthr; i < cur.nown(); i += nthr) {
+                const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + i);
+                settle_node(acc, su1, su2, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
+            }
+        }
+        cp_async_wait_all();                    // partial forces of the previous tile, this tile's finish data
+        __syncthreads();                        // ... and every thread's published partial forces are written
+        if (tid == 0) publish_flag(A.flag + ((const volatile int *)m_cur)[14], A.epoch);
+
+        // ---- finish the previous tile -------------------------------------------------------------
+        if (prv_pending) {
+            finish_tile(A, read_meta(m_prv), fb_prv, fb, tid, nthr, fuse);
+            __syncthreads();                    // pend is free again
+        }
+        // ---- hand this tile on: record nodes keep their own share in pend, the rest is final ----
+        {
+            const uint2 *srec = reinterpret_cast<const uint2 *>(fbuf + (it & 1) * fbuf_bytes);
+            const volatile int *v = m_cur;
+            const int nrec = min(v[9] - v[8], A.cap_recs);
+            if (fuse)
+                for (int r = tid; r < nrec; r += nthr) {
+                    const int slot3 = srec[r].x & 0xffff;
+                    fb.pend[3 * r] = acc[slot3]; fb.pend[3 * r + 1] = acc[slot3 + 1]; fb.pend[3 * r + 2] = acc[slot3 + 2];
+                }
+            const size_t g0 = 3 * (size_t)cur.n0;
+            if (fuse) {
+                // coalesced 128-bit copy-out (g0 is even); rows of record nodes are rewritten when
+                // the tile is finished, rows of SPECIAL nodes by the special-node update
+                double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);
+                for (int k = tid; k < (nown3 >> 1); k += nthr) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+                if ((nown3 & 1) && tid == 0) A.unext[g0 + nown3 - 1] = acc[nown3 - 1];
+            } else {
+                for (int k = tid; k < nown3; k += nthr) A.force[g0 + k] += acc[k];
+            }
+            __syncthreads();
+            for (int k = tid; k < nown3; k += nthr) acc[k] = 0.0;
+        }
+        if (!has_next) {
+            // the last tile of this CTA is finished right away
+            const TileMeta me = read_meta(m_cur);
+            const char *fb_cur = fbuf + (it & 1) * fbuf_bytes;
+            poll_deps(A, me, fb_cur, tid, nthr);
+            __syncthreads();
+            request_partials(A, me, fb_cur, fb, tid, nthr);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncthreads();
+            finish_tile(A, me, fb_cur, fb, tid, nthr, fuse);
+            break;
+        }
         t = tn;
     }
 }

@@ -261,13 +261,28 @@ class Solver:
         return {n: getattr(t, n) for n, _ in t._fields_}
 
 
-def plan_build(elem_lnid, nharbored: int, tile_nodes: int = 0) -> dict:
-    """Host-only: build and self-check the tile plan for a mesh (no GPU needed); returns its sizes."""
+def plan_build(elem_lnid, nharbored: int, tile_nodes: int = 0, mesh: "HostMesh | None" = None) -> dict:
+    """Host-only: build and self-check the tile plan for a mesh (no GPU needed); returns its sizes.
+    With ``mesh`` (a rank's HostMesh) the nodes of its halo schedules and hanging-node lists make
+    their tiles "self" tiles, as hgpu_init does on a multi-rank mesh."""
     L = _lib.lib()
     lnid = np.ascontiguousarray(elem_lnid, np.int32).reshape(-1, 8)
     m = _lib.Mesh()
     m.lenum, m.nharbored, m.ldnnum = lnid.shape[0], int(nharbored), 0
     m.elem_lnid = _p(lnid, C.c_int32)
+    keep = []
+    if mesh is not None:
+        if mesh.dnode is not None and len(mesh.dnode):
+            dn = np.ascontiguousarray(mesh.dnode, np.int32).reshape(-1, 6)
+            keep.append(dn)
+            m.ldnnum, m.dnode = dn.shape[0], _p(dn, C.c_int32)
+        for name in ("dn_c", "dn_s", "an_c", "an_s"):
+            ml = getattr(mesh, name)
+            arrs = [np.ascontiguousarray(a, np.int32) for a in (ml.peer, ml.nodes, ml.mapping)]
+            keep += arrs
+            c = getattr(m, name)
+            c.count = arrs[0].size
+            c.peer, c.nodes, c.mapping = (_p(a, C.c_int32) for a in arrs)
     out = _lib.Layout()
     _chk(L.hgpu_plan_build(C.byref(m), tile_nodes, C.byref(out)))
     return {n: getattr(out, n) for n, _ in out._fields_}

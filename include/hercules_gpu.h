@@ -201,15 +201,20 @@ void *hgpu_stream(hgpu_solver_t *s);
 /* Sizes of the device data structures, for DESIGN.md / bench reporting. */
 typedef struct hgpu_layout {
     int32_t tile_nodes, ntiles, max_tile_nodes, max_tile_elems;
-    int64_t tile_elems_total;   /* sum over tiles of elements evaluated (>= lenum: halo recompute) */
+    int64_t tile_elems_total;   /* sum over tiles of elements evaluated (= lenum + the extra entries of self tiles) */
     int64_t tile_halo_total;    /* sum over tiles of gathered non-owned nodes */
     int64_t n_regular, n_special;
     int64_t device_bytes;
     int32_t smem_bytes, block_threads;
     int32_t grid_ctas, ctas_per_sm;   /* persistent step kernel: CTAs launched, resident per SM */
-    int32_t early_tiles;              /* tiles evaluated before the halo exchange starts (multi-GPU) */
+    int32_t early_tiles;              /* self tiles: evaluated before the halo exchange starts (multi-GPU) */
     /* modelled shared-memory wavefronts per 32-lane 8-byte access (2.0 = conflict-free) */
     double est_gather_wavefronts, est_scatter_wavefronts;
+    int32_t max_tile_acc;             /* owned + published nodes of the largest tile (shared-memory accumulator) */
+    int32_t max_tile_recs, max_tile_srcs;
+    int32_t pad_;
+    int64_t partial_slots;            /* (tile, node) partial forces exchanged between tiles per pass */
+    int64_t deps_total;               /* sum over tiles of the lower tiles they wait for */
 } hgpu_layout_t;
 int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out);
 /* Host-only (no device needed): build and self-check the tile plan hgpu_init would use for this

@@ -1,7 +1,8 @@
-"""CPU tests of the host-side index builders behind hgpu_init (no GPU needed): the owner-computes
-tile plan is built and independently re-checked against the mesh inside hgpu_plan_build (every
-node owned once, every incident element evaluated once per owner tile, slots decode to the
-element's own corners)."""
+"""CPU tests of the host-side index builders behind hgpu_init (no GPU needed): the tile plan is
+built and independently re-checked against the mesh inside hgpu_plan_build (every node owned once,
+every element the core element of exactly one tile, slots decode to the element's own corners, and
+for every owned node the tile's own entries plus the partial forces it reads from lower tiles
+account for each incident element exactly once)."""
 import numpy as np
 import pytest
 
@@ -16,19 +17,40 @@ def test_tile_plan_valid_on_octor_meshes(name, tile_nodes):
     g = rank_view(load_golden(name), 1)
     E, N = g["elem_lnid"].shape[0], g["nTable"].shape[0]
     r = solver.plan_build(g["elem_lnid"], N, tile_nodes)
-    assert r["ntiles"] >= 1 and r["tile_elems_total"] >= E
+    assert r["ntiles"] >= 1 and r["tile_elems_total"] == E      # every element evaluated exactly once
+    assert r["early_tiles"] == 0
     assert r["smem_bytes"] <= 115712                      # two CTAs per SM on a B200
     if tile_nodes:
         assert r["tile_nodes"] <= max(2, tile_nodes)
 
 
-def test_tile_plan_uniform_redundancy():
-    """Aligned 8x8x8 node cells on a uniform mesh: 9^3 elements per 8^3 owned nodes at most."""
+@pytest.mark.parametrize("tile_nodes", [0, 64])
+@pytest.mark.parametrize("name,nranks", [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4),
+                                         ("uniform_rayleigh_eff_np3", 3)])
+def test_tile_plan_self_tiles_on_partitioned_meshes(name, nranks, tile_nodes):
+    """Multi-rank meshes: tiles that own a node of a halo schedule or of the hanging-node lists
+    evaluate the foreign elements incident to their nodes themselves and wait for nobody."""
+    from hercules_b200 import solver
+    for rank in range(nranks):
+        g = rank_view(load_golden(name), rank)
+        hm = solver.HostMesh.from_dump(g)
+        E, N = g["elem_lnid"].shape[0], g["nTable"].shape[0]
+        r = solver.plan_build(g["elem_lnid"], N, tile_nodes, mesh=hm)
+        assert r["early_tiles"] >= 1 and r["tile_elems_total"] >= E
+        assert r["smem_bytes"] <= 115712
+
+
+def test_tile_plan_uniform_layout():
+    """Aligned 8x8x8 element blocks on a uniform mesh: 8^3 core elements, 9^3 staged nodes of which
+    8^3 are owned (interior tiles), no element evaluated twice, near conflict-free slots."""
     from hercules_b200 import meshgen, solver
     mesh, info = meshgen.uniform_halfspace(32, 32, 32, h=25.0, dt=0.002)
     r = solver.plan_build(mesh.elem_lnid, info["N"])
-    assert r["max_tile_elems"] <= 729 and r["max_tile_nodes"] <= 1008   # 10^3 staged + conflict-avoiding slack
-    assert r["tile_elems_total"] / info["E"] < 1.43
+    assert r["max_tile_elems"] == 512
+    assert r["tile_elems_total"] == info["E"]
+    assert r["max_tile_nodes"] <= 752 and r["max_tile_acc"] <= 752
+    assert r["tile_halo_total"] == r["partial_slots"] or r["partial_slots"] >= r["tile_halo_total"]
+    assert r["est_gather_wavefronts"] < 3.3 and r["est_scatter_wavefronts"] < 3.3
 
 
 def test_tile_plan_rejects_bad_mesh():
