@@ -215,33 +215,23 @@ __device__ __forceinline__ void publish_flag(unsigned int *p, unsigned int v)
     asm volatile("fence.acq_rel.gpu;\n\tst.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Raw offsets as loaded (differences are taken where they are used, so that nothing consumes a
-// freshly requested value early).
-struct TileMeta {
-    int n0, n1, hb, h1;         // owned node range; halo_id range
-    int eb, e1, ncore, npub;    // entry range; core entries; published halo slots
-    int rb, r1, sb, s1;         // finish records; sources
-    int db, d1, id;             // dependencies; tile id (flag index)
-    __device__ __forceinline__ int nown() const { return n1 - n0; }
-    __device__ __forceinline__ int nh() const { return h1 - hb; }
-    __device__ __forceinline__ int ne() const { return e1 - eb; }
-};
-
 // Tile offsets travel through a shared-memory ring filled by cp.async (no registers, no
-// scoreboard): slot i & (META_RING-1) holds the offsets of the CTA's i-th tile.
+// scoreboard): slot i & (META_RING-1) holds the offsets of the CTA's i-th tile, four int4 groups:
+//   0: n0, n1, hb, h1        owned node range; halo_id range
+//   1: eb, e1, ncore, npub   entry range; core entries; published halo slots
+//   2: rb, r1, sb, s1        finish records; sources
+//   3: db, d1, id, -         dependencies; tile id (flag index)
+// A group is read (one 128-bit broadcast load) where it is used instead of being kept in registers.
 __device__ __forceinline__ void fetch_meta_async(const StepArgs &A, int t, int *slot, int tid)
 {
     if (tid < 4) cp_async16(slot + 4 * tid, A.tile_meta + 4 * (size_t)t + tid);
 }
-__device__ __forceinline__ TileMeta read_meta(const int *slot)
+__device__ __forceinline__ int4 meta_group(const int *slot, int g)
 {
-    const volatile int *v = slot;
-    TileMeta m;
-    m.n0 = v[0]; m.n1 = v[1]; m.hb = v[2]; m.h1 = v[3];
-    m.eb = v[4]; m.e1 = v[5]; m.ncore = v[6]; m.npub = v[7];
-    m.rb = v[8]; m.r1 = v[9]; m.sb = v[10]; m.s1 = v[11];
-    m.db = v[12]; m.d1 = v[13]; m.id = v[14];
-    return m;
+    int4 v;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(slot + 4 * g);
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
 }
 
 template <bool NEED_BETA>
@@ -258,24 +248,26 @@ __device__ __forceinline__ Entry load_entry(const StepArgs &A, int idx)
 // Stage the displacements of one tile: su1 (and su2) <- owned range + gathered halo nodes.
 // U2_OWNED: copy the owned part of u2; U2_HALO: also its halo part.  The ids of the first
 // HALO_PRE * blockDim.x halo nodes are loaded by the caller ahead of time (hid[]).
+// m = meta group 0 {n0, n1, hb, h1}.
 constexpr int HALO_PRE = 2;
 
-__device__ __forceinline__ void load_halo_ids(const StepArgs &A, const TileMeta &m, int tid, int nthr,
+__device__ __forceinline__ void load_halo_ids(const StepArgs &A, const int4 m, int tid, int nthr,
                                               int (&hid)[HALO_PRE])
 {
+    const int nh = m.w - m.z;
 #pragma unroll
     for (int q = 0; q < HALO_PRE; q++) {
         const int h = tid + q * nthr;
-        hid[q] = h < m.nh() ? ldg_i32_pinned(A.halo_id + m.hb + h) : -1;
+        hid[q] = h < nh ? ldg_i32_pinned(A.halo_id + m.z + h) : -1;
     }
 }
 
 template <bool U2_OWNED, bool U2_HALO>
-__device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m, double *su1, double *su2,
+__device__ __forceinline__ void stage_tile(const StepArgs &A, const int4 m, double *su1, double *su2,
                                            int tid, int nthr, const int (&hid)[HALO_PRE])
 {
-    const int nd = 3 * m.nown(), nv = nd >> 1;
-    const double *g1 = A.u1 + 3 * (size_t)m.n0, *g2 = A.u2 + 3 * (size_t)m.n0;
+    const int nd = 3 * (m.y - m.x), nv = nd >> 1, nh = m.w - m.z;
+    const double *g1 = A.u1 + 3 * (size_t)m.x, *g2 = A.u2 + 3 * (size_t)m.x;
     for (int i = tid; i < nv; i += nthr) {
         cp_async16(su1 + 2 * i, g1 + 2 * i);
         if (U2_OWNED) cp_async16(su2 + 2 * i, g2 + 2 * i);
@@ -288,15 +280,15 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m,
 #pragma unroll
     for (int q = 0; q < HALO_PRE; q++) {
         const int h = tid + q * nthr;
-        if (h < m.nh() && hid[q] >= 0) {        // -1 = slot left unused by the plan
+        if (h < nh && hid[q] >= 0) {            // -1 = slot left unused by the plan
             const size_t g = 3 * (size_t)hid[q];
             double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
             cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
             if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
         }
     }
-    for (int h = tid + HALO_PRE * nthr; h < m.nh(); h += nthr) {
-        const int id = __ldg(A.halo_id + m.hb + h);
+    for (int h = tid + HALO_PRE * nthr; h < nh; h += nthr) {
+        const int id = __ldg(A.halo_id + m.z + h);
         if (id < 0) continue;
         const size_t g = 3 * (size_t)id;
         double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
@@ -307,27 +299,28 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const TileMeta &m,
 
 // Finish data of one tile (records, sources, dependency ids) -> shared memory, by cp.async.
 // Layout of one buffer: uint2 rec[cap_recs] | int src[cap_srcs] | int dep[CAP_DEPS].
-__device__ __forceinline__ void stage_finish(const StepArgs &A, const TileMeta &m, char *buf, int tid, int nthr)
+// mc = meta group 2 {rb, r1, sb, s1}, md = group 3 {db, d1, id, -}.
+__device__ __forceinline__ void stage_finish(const StepArgs &A, const int4 mc, const int4 md, char *buf, int tid, int nthr)
 {
     uint2 *srec = reinterpret_cast<uint2 *>(buf);
     int *ssrc = reinterpret_cast<int *>(buf + 8 * (size_t)A.cap_recs);
     int *sdep = ssrc + A.cap_srcs;
-    const int nr = min(m.r1 - m.rb, A.cap_recs), ns = min(m.s1 - m.sb, A.cap_srcs), ndp = min(m.d1 - m.db, CAP_DEPS);
-    for (int i = tid; i < nr; i += nthr) cp_async8(srec + i, A.rec + m.rb + i);
-    for (int i = tid; i < ns; i += nthr) cp_async4(ssrc + i, A.src + m.sb + i);
-    if (tid < ndp) cp_async4(sdep + tid, A.dep + m.db + tid);
+    const int nr = min(mc.y - mc.x, A.cap_recs), ns = min(mc.w - mc.z, A.cap_srcs), ndp = min(md.y - md.x, CAP_DEPS);
+    for (int i = tid; i < nr; i += nthr) cp_async8(srec + i, A.rec + mc.x + i);
+    for (int i = tid; i < ns; i += nthr) cp_async4(ssrc + i, A.src + mc.z + i);
+    if (tid < ndp) cp_async4(sdep + tid, A.dep + md.x + tid);
 }
 
 constexpr int NT_PRE = 3;
 
-__device__ __forceinline__ void load_node_tables(const StepArgs &A, const TileMeta &m, int tid, int nthr,
+__device__ __forceinline__ void load_node_tables(const StepArgs &A, int n0, int nown, int tid, int nthr,
                                                  double (&ntv)[NT_PRE][3])
 {
 #pragma unroll
     for (int q = 0; q < NT_PRE; q++) {
         const int i = tid + q * nthr;
-        if (i < m.nown()) {
-            const double *nt = A.nt3 + 3 * (size_t)(m.n0 + i);
+        if (i < nown) {
+            const double *nt = A.nt3 + 3 * (size_t)(n0 + i);
             ntv[q][0] = ldg_f64_pinned(nt); ntv[q][1] = ldg_f64_pinned(nt + 1); ntv[q][2] = ldg_f64_pinned(nt + 2);
         } else {
             ntv[q][0] = ntv[q][1] = ntv[q][2] = 0.0;
@@ -355,74 +348,68 @@ struct FinishBufs {
     double *srm;        // [cap_recs]    nt3[node][0] of the record nodes
 };
 
-// Poll the flags of the lower tiles that publish for tile m's nodes (dependency ids in buf).
-__device__ __forceinline__ void poll_deps(const StepArgs &A, const TileMeta &m, const char *buf, int tid, int nthr)
+// Flags of the lower tiles that publish for a tile's nodes (dependency ids in buf; md = meta
+// group 3): request this thread's flag / wait until every flag this thread watches is raised.
+__device__ __forceinline__ const unsigned int *dep_flag(const StepArgs &A, const int4 md, const char *buf, int d)
 {
     const int *sdep = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs) + A.cap_srcs;
-    const int ndep = m.d1 - m.db;
+    return A.flag + (d < CAP_DEPS ? sdep[d] : __ldg(A.dep + md.x + d));
+}
+__device__ __forceinline__ void wait_deps(const StepArgs &A, const int4 md, const char *buf, int tid, int nthr,
+                                          unsigned int first_value)
+{
+    const int ndep = md.y - md.x;
+    unsigned int v = first_value;
     for (int d = tid; d < ndep; d += nthr) {
-        const int dt = d < CAP_DEPS ? sdep[d] : __ldg(A.dep + m.db + d);
-        const unsigned int *f = A.flag + dt;
-        while ((int)(ld_relaxed_u32(f) - A.epoch) < 0) __nanosleep(32);
+        const unsigned int *f = dep_flag(A, md, buf, d);
+        if (d != tid) v = ld_relaxed_u32(f);
+        while ((int)(v - A.epoch) < 0) { __nanosleep(32); v = ld_relaxed_u32(f); }
     }
 }
 
-// Request the partial forces tile m reads, and the node-table entry of its record nodes
-// (cp.async.cg: served by L2, where the publishers' fences made them visible).
-__device__ __forceinline__ void request_partials(const StepArgs &A, const TileMeta &m, const char *buf,
+// Request the partial forces a tile reads, and the node-table entry of its record nodes
+// (cp.async from L2, where the publishers' fences made them visible; no 128-byte line of
+// partial[] is shared by two publishers, so a line cached in L1 is never stale).
+__device__ __forceinline__ void request_partials(const StepArgs &A, int n0, const int4 mc, const char *buf,
                                                  const FinishBufs &fb, int tid, int nthr)
 {
     const uint2 *srec = reinterpret_cast<const uint2 *>(buf);
     const int *ssrc = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs);
-    const int ns = min(m.s1 - m.sb, A.cap_srcs), nr = min(m.r1 - m.rb, A.cap_recs);
+    const int ns = min(mc.w - mc.z, A.cap_srcs), nr = min(mc.y - mc.x, A.cap_recs);
     for (int q = tid; q < ns; q += nthr) {
         const double *pp = A.partial + 3 * (size_t)ssrc[q];
         cp_async8(fb.spart + 3 * q, pp); cp_async8(fb.spart + 3 * q + 1, pp + 1); cp_async8(fb.spart + 3 * q + 2, pp + 2);
     }
-    const double *nt = A.nt3 + 3 * (size_t)m.n0;
+    const double *nt = A.nt3 + 3 * (size_t)n0;
     for (int r = tid; r < nr; r += nthr) cp_async8(fb.srm + r, nt + (srec[r].x & 0xffff));
 }
 
-// Finish a tile: add the partial forces of the lower tiles to the record nodes' own share (pend)
-// in a fixed order and store the result -- u(t+dt) of a REGULAR node, or the force of a SPECIAL
-// node (source term, hanging-node transfer, halo exchange and the list update follow).
-__device__ __forceinline__ void finish_tile(const StepArgs &A, const TileMeta &m, const char *buf,
-                                            const FinishBufs &fb, int tid, int nthr, bool fuse)
+// Finish record r of a tile: add the partial forces of the lower tiles to the node's own share
+// (own[]) in a fixed order and store the result -- u(t+dt) of a REGULAR node, or the force of a
+// SPECIAL node (source term, hanging-node transfer, halo exchange and the list update follow).
+__device__ __forceinline__ void finish_record(const StepArgs &A, int n0, const int4 mc, const char *buf,
+                                              const FinishBufs &fb, int r, const double (&own)[3], bool fuse)
 {
     const uint2 *srec = reinterpret_cast<const uint2 *>(buf);
-    const int *ssrc = reinterpret_cast<const int *>(buf + 8 * (size_t)A.cap_recs);
-    const int nrec = m.r1 - m.rb;
-    const size_t g0 = 3 * (size_t)m.n0;
-    for (int r = tid; r < nrec; r += nthr) {
-        const bool in_smem = r < A.cap_recs;
-        const uint2 rc = in_smem ? srec[r] : __ldg(A.rec + m.rb + r);
-        const int slot3 = rc.x & 0xffff, cnt = (rc.x >> 16) & 0xff, first = (int)rc.y;
-        const double rmv = in_smem ? fb.srm[r] : __ldg(A.nt3 + g0 + slot3);
-        const bool regular = fuse && rmv > 0.0;
-        const double scale = regular ? rmv : 1.0;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        if (in_smem && fuse) { s0 = fb.pend[3 * r]; s1 = fb.pend[3 * r + 1]; s2 = fb.pend[3 * r + 2]; }
-        for (int k = 0; k < cnt; k++) {
-            const int q = first + k;
-            double v0, v1, v2;
-            if (q < A.cap_srcs) { v0 = fb.spart[3 * q]; v1 = fb.spart[3 * q + 1]; v2 = fb.spart[3 * q + 2]; }
-            else {
-                const double *pp = A.partial + 3 * (size_t)__ldg(A.src + m.sb + q);
-                v0 = __ldcg(pp); v1 = __ldcg(pp + 1); v2 = __ldcg(pp + 2);
-            }
-            s0 = fma(v0, scale, s0); s1 = fma(v1, scale, s1); s2 = fma(v2, scale, s2);
-        }
-        if (regular) {
-            double *o = A.unext + g0 + slot3;
-            // a record beyond the staged ones kept its own share in unext
-            if (!in_smem) { s0 += o[0]; s1 += o[1]; s2 += o[2]; }
-            o[0] = s0; o[1] = s1; o[2] = s2;
-        } else {
-            // fused launch: the own share waited in pend; unfused: it is in the force array already
-            double *fo = A.force + g0 + slot3;
-            if (fuse && !in_smem) { const double *o = A.unext + g0 + slot3; s0 += o[0]; s1 += o[1]; s2 += o[2]; }
-            fo[0] += s0; fo[1] += s1; fo[2] += s2;
-        }
+    const size_t g0 = 3 * (size_t)n0;
+    const uint2 rc = srec[r];
+    const int slot3 = rc.x & 0xffff, cnt = (rc.x >> 16) & 0xff, first = (int)rc.y;
+    const double rmv = fb.srm[r];
+    const bool regular = fuse && rmv > 0.0;
+    const double scale = regular ? rmv : 1.0;
+    double s0 = own[0], s1 = own[1], s2 = own[2];
+    for (int k = 0; k < cnt; k++) {
+        const int q = first + k;
+        s0 = fma(fb.spart[3 * q], scale, s0); s1 = fma(fb.spart[3 * q + 1], scale, s1); s2 = fma(fb.spart[3 * q + 2], scale, s2);
+    }
+    if (regular) {
+        double *o = A.unext + g0 + slot3;
+        o[0] = s0; o[1] = s1; o[2] = s2;
+    } else {
+        // fused launch: own[] is the plain force the tile accumulated; unfused: the tile's share is
+        // in the force array already and own[] is zero
+        double *fo = A.force + g0 + slot3;
+        fo[0] += s0; fo[1] += s1; fo[2] += s2;
     }
 }
 
@@ -450,8 +437,10 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     //   displacements : cp.async into the other stage, one tile ahead
     //   tile offsets  : cp.async into a ring, three tiles ahead
     //   finish data   : cp.async when the tile's element phase starts (records, sources, deps)
-    //   partial forces: cp.async during the accumulation passes of the NEXT tile's last round,
-    //                   after the publishers' flags have been seen
+    //   flags         : of the PREVIOUS tile's publishers; requested at accumulation pass 0 of this
+    //                   tile's last round, checked at pass 3
+    //   partial forces: cp.async after pass 3, used when the previous tile is finished at the end
+    //                   of this iteration
     //   entries       : registers; enext -> ecur at the top of a round, then the following round's
     //                   entry is requested
     //   halo ids      : registers; requested before the accumulation passes of a tile's last round
@@ -470,18 +459,18 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     __syncthreads();
     int hid[HALO_PRE];
     {
-        const TileMeta cur = read_meta(smeta[0]);
-        load_halo_ids(A, cur, tid, nthr, hid);
-        if (U2E || fuse) stage_tile<true, U2E>(A, cur, smem, smem + S3, tid, nthr, hid);
-        else             stage_tile<false, false>(A, cur, smem, smem + S3, tid, nthr, hid);
+        const int4 ma = meta_group(smeta[0], 0);
+        load_halo_ids(A, ma, tid, nthr, hid);
+        if (U2E || fuse) stage_tile<true, U2E>(A, ma, smem, smem + S3, tid, nthr, hid);
+        else             stage_tile<false, false>(A, ma, smem, smem + S3, tid, nthr, hid);
         cp_async_commit();
-        if (t + G < A.ntiles) load_halo_ids(A, read_meta(smeta[1]), tid, nthr, hid);
+        if (t + G < A.ntiles) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
     }
     Entry ecur, enext;
     enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
     {
-        const TileMeta cur = read_meta(smeta[0]);
-        if (tid < cur.ne()) enext = load_entry<U2E>(A, cur.eb + tid);
+        const int4 mb = meta_group(smeta[0], 1);
+        if (tid < mb.y - mb.x) enext = load_entry<U2E>(A, mb.x + tid);
     }
 
     for (int it = 0;; it++) {
@@ -493,45 +482,48 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         const int *m_cur = smeta[it & (META_RING - 1)], *m_nxt = smeta[(it + 1) & (META_RING - 1)];
         const int *m_nn = smeta[(it + 2) & (META_RING - 1)], *m_prv = smeta[(it - 1) & (META_RING - 1)];
         const char *fb_prv = fbuf + ((it - 1) & 1) * fbuf_bytes;
+        char *fb_cur = fbuf + (it & 1) * fbuf_bytes;
         cp_async_wait_all();
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1's stage
-        stage_finish(A, read_meta(m_cur), fbuf + (it & 1) * fbuf_bytes, tid, nthr);
+        if (it > 0 && tid == 0) publish_flag(A.flag + meta_group(m_prv, 3).z, A.epoch);
+        stage_finish(A, meta_group(m_cur, 2), meta_group(m_cur, 3), fb_cur, tid, nthr);
         if (has_next) {
             double *n1 = smem + ((it + 1) & 1) * stage_doubles;
-            const TileMeta nxt = read_meta(m_nxt);
+            const int4 nxt = meta_group(m_nxt, 0);
             if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             if (tn + 2 * G < A.ntiles) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & (META_RING - 1)], tid);
         }
         cp_async_commit();
-        // only what the element phase needs stays in registers; the rest of the tile's offsets is
-        // read again from the ring where it is used
-        struct { int n0, n1, eb, e1, ncore;
-                 __device__ __forceinline__ int nown() const { return n1 - n0; }
-                 __device__ __forceinline__ int ne() const { return e1 - eb; } } cur;
+        // what the element phase needs of this tile's offsets
+        int n0, nown, eb, ne, ncore, nxt_eb = 0, nxt_ne = 0;
         {
-            const volatile int *v = m_cur;
-            cur.n0 = v[0]; cur.n1 = v[1]; cur.eb = v[4]; cur.e1 = v[5]; cur.ncore = v[6];
+            const int4 ma = meta_group(m_cur, 0), mb = meta_group(m_cur, 1);
+            n0 = ma.x; nown = ma.y - ma.x; eb = mb.x; ne = mb.y - mb.x; ncore = mb.z;
+            if (has_next) { const int4 nb = meta_group(m_nxt, 1); nxt_eb = nb.x; nxt_ne = nb.y - nb.x; }
         }
-        const int nown3 = 3 * cur.nown();
-        const int nxt_eb = has_next ? ((const volatile int *)m_nxt)[4] : 0;
-        const int nxt_ne = has_next ? ((const volatile int *)m_nxt)[5] - nxt_eb : 0;
+        const int nown3 = 3 * nown;
         // the previous tile is finished during this one: its publishers' flags are polled and its
         // partial forces requested between the accumulation passes of the last round
-        bool prv_pending = it > 0;
+        const bool prv_pending = it > 0;
         double ntv[NT_PRE][3];
+        unsigned int flag_value = A.epoch;
 
         // ---- element forces, accumulated per staged node ----------------------------------------
-        for (int base = 0; base < cur.ne(); base += nthr) {
-            const bool act = base + tid < cur.ne();
-            const bool last = base + nthr >= cur.ne();
+        for (int base = 0; base < ne; base += nthr) {
+            const bool act = base + tid < ne;
+            const bool last = base + nthr >= ne;
             // a core entry adds to every corner (owned or published); an extra entry of a self
             // tile only to the owned ones
-            const uint32_t lim = base + tid < cur.ncore ? 0xffffffffu : (uint32_t)nown3;
+            const uint32_t lim = base + tid < ncore ? 0xffffffffu : (uint32_t)nown3;
             ecur = enext;
+            if (last && prv_pending) {           // flags of the previous tile's publishers: needed at pass 3
+                const int4 md = meta_group(m_prv, 3);
+                if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_prv, tid));
+            }
             // next round's entry (or the first round of the next tile) rides along with the math
             if (!last) {
-                if (base + nthr + tid < cur.ne()) enext = load_entry<U2E>(A, cur.eb + base + nthr + tid);
+                if (base + nthr + tid < ne) enext = load_entry<U2E>(A, eb + base + nthr + tid);
             } else if (tid < nxt_ne) {
                 enext = load_entry<U2E>(A, nxt_eb + tid);
             }
@@ -587,8 +579,8 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 }
             }
             if (last) {
-                if (fuse) load_node_tables(A, read_meta(m_cur), tid, nthr, ntv);
-                if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
+                if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
+                if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
             }
             // A node is corner j of at most one element (leaf octants do not overlap), so within
             // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
@@ -598,31 +590,32 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                     const int o = sl[j];
                     acc[o] += fx[j]; acc[o + 1] += fy[j]; acc[o + 2] += fz[j];
                 }
-                if (j == 2 && last && prv_pending) poll_deps(A, read_meta(m_prv), fb_prv, tid, nthr);
+                if (j == 3 && last && prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
                 __syncthreads();
-                if (j == 2 && last && prv_pending) {
-                    request_partials(A, read_meta(m_prv), fb_prv, fb, tid, nthr);
+                if (j == 3 && last && prv_pending) {
+                    request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
                     cp_async_commit();
                 }
             }
         }
-        if (cur.ne() == 0) {                    // a tile of element-less nodes: keep the pipeline fed
+        if (ne == 0) {                          // a tile of element-less nodes: keep the pipeline fed
             if (tid < nxt_ne) enext = load_entry<U2E>(A, nxt_eb + tid);
-            if (has_nn) load_halo_ids(A, read_meta(m_nn), tid, nthr, hid);
-            if (fuse) load_node_tables(A, read_meta(m_cur), tid, nthr, ntv);
+            if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
+            if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
             if (prv_pending) {
-                poll_deps(A, read_meta(m_prv), fb_prv, tid, nthr);
+                const int4 md = meta_group(m_prv, 3);
+                if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_prv, tid));
+                wait_deps(A, md, fb_prv, tid, nthr, flag_value);
                 __syncthreads();
-                request_partials(A, read_meta(m_prv), fb_prv, fb, tid, nthr);
+                request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
                 cp_async_commit();
             }
         }
 
         // ---- publish what the core elements added to nodes of higher tiles ----------------------
         {
-            const volatile int *v = m_cur;
-            const int np3 = 3 * v[7];
-            double *dst = A.partial + 3 * (size_t)v[2];
+            const int np3 = 3 * meta_group(m_cur, 1).w;
+            double *dst = A.partial + 3 * (size_t)meta_group(m_cur, 0).z;
             for (int k = tid; k < np3; k += nthr) {
                 __stcg(dst + k, acc[nown3 + k]);
                 acc[nown3 + k] = 0.0;
@@ -633,56 +626,69 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 #pragma unroll
             for (int q = 0; q < NT_PRE; q++) {
                 const int i = tid + q * nthr;
-                if (i < cur.nown()) settle_node(acc, su1, su2, i, ntv[q][0], ntv[q][1], ntv[q][2]);
+                if (i < nown) settle_node(acc, su1, su2, i, ntv[q][0], ntv[q][1], ntv[q][2]);
             }
-            for (int i = tid + NT_PRE * nthr; i < cur.nown(); i += nthr) {
-                const double *nt = A.nt3 + 3 * (size_t)(cur.n0 + i);
+            for (int i = tid + NT_PRE * nthr; i < nown; i += nthr) {
+                const double *nt = A.nt3 + 3 * (size_t)(n0 + i);
                 settle_node(acc, su1, su2, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
             }
         }
         cp_async_wait_all();                    // partial forces of the previous tile, this tile's finish data
         __syncthreads();                        // ... and every thread's published partial forces are written
-        if (tid == 0) publish_flag(A.flag + ((const volatile int *)m_cur)[14], A.epoch);
+        // (the flag is raised at the top of the next iteration: by then the stores have long been
+        // acknowledged and the fence in front of the flag costs thread 0 next to nothing)
 
-        // ---- finish the previous tile -------------------------------------------------------------
-        if (prv_pending) {
-            finish_tile(A, read_meta(m_prv), fb_prv, fb, tid, nthr, fuse);
-            __syncthreads();                    // pend is free again
-        }
-        // ---- hand this tile on: record nodes keep their own share in pend, the rest is final ----
+        // ---- record nodes: the previous tile's own share leaves pend, this tile's enters ---------
+        // (records are at most one per thread: TileCaps.max_recs <= blockDim.x)
+        double own_prv[3] = {0.0, 0.0, 0.0};
+        const int nrec_prv = prv_pending ? min(meta_group(m_prv, 2).y - meta_group(m_prv, 2).x, A.cap_recs) : 0;
         {
-            const uint2 *srec = reinterpret_cast<const uint2 *>(fbuf + (it & 1) * fbuf_bytes);
-            const volatile int *v = m_cur;
-            const int nrec = min(v[9] - v[8], A.cap_recs);
-            if (fuse)
-                for (int r = tid; r < nrec; r += nthr) {
-                    const int slot3 = srec[r].x & 0xffff;
-                    fb.pend[3 * r] = acc[slot3]; fb.pend[3 * r + 1] = acc[slot3 + 1]; fb.pend[3 * r + 2] = acc[slot3 + 2];
-                }
-            const size_t g0 = 3 * (size_t)cur.n0;
+            const int4 mc = meta_group(m_cur, 2);
+            const int nrec = min(mc.y - mc.x, A.cap_recs);
             if (fuse) {
-                // coalesced 128-bit copy-out (g0 is even); rows of record nodes are rewritten when
-                // the tile is finished, rows of SPECIAL nodes by the special-node update
-                double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);
-                for (int k = tid; k < (nown3 >> 1); k += nthr) dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-                if ((nown3 & 1) && tid == 0) A.unext[g0 + nown3 - 1] = acc[nown3 - 1];
-            } else {
-                for (int k = tid; k < nown3; k += nthr) A.force[g0 + k] += acc[k];
+                if (tid < nrec_prv) { own_prv[0] = fb.pend[3 * tid]; own_prv[1] = fb.pend[3 * tid + 1]; own_prv[2] = fb.pend[3 * tid + 2]; }
+                if (tid < nrec) {
+                    const int slot3 = reinterpret_cast<const uint2 *>(fb_cur)[tid].x & 0xffff;
+                    fb.pend[3 * tid] = acc[slot3]; fb.pend[3 * tid + 1] = acc[slot3 + 1]; fb.pend[3 * tid + 2] = acc[slot3 + 2];
+                }
             }
-            __syncthreads();
-            for (int k = tid; k < nown3; k += nthr) acc[k] = 0.0;
         }
+        __syncthreads();
+        // ---- hand this tile on: rows of record nodes are rewritten when the tile is finished,
+        //      rows of SPECIAL nodes by the special-node update --------------------------------
+        {
+            const size_t g0 = 3 * (size_t)n0;
+            if (fuse) {
+                double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);         // g0 is even
+                for (int k = tid; k < (nown3 >> 1); k += nthr) {
+                    dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+                    acc[2 * k] = 0.0; acc[2 * k + 1] = 0.0;
+                }
+                if ((nown3 & 1) && tid == 0) { A.unext[g0 + nown3 - 1] = acc[nown3 - 1]; acc[nown3 - 1] = 0.0; }
+            } else {
+                for (int k = tid; k < nown3; k += nthr) { A.force[g0 + k] += acc[k]; acc[k] = 0.0; }
+            }
+        }
+        // ---- finish the previous tile (nobody waits for this) ------------------------------------
+        if (tid < nrec_prv)
+            finish_record(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, own_prv, fuse);
         if (!has_next) {
             // the last tile of this CTA is finished right away
-            const TileMeta me = read_meta(m_cur);
-            const char *fb_cur = fbuf + (it & 1) * fbuf_bytes;
-            poll_deps(A, me, fb_cur, tid, nthr);
-            __syncthreads();
-            request_partials(A, me, fb_cur, fb, tid, nthr);
+            const int4 md = meta_group(m_cur, 3), mc = meta_group(m_cur, 2);
+            if (tid == 0) publish_flag(A.flag + md.z, A.epoch);
+            if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_cur, tid));
+            wait_deps(A, md, fb_cur, tid, nthr, flag_value);
+            __syncthreads();                    // ... also: the previous tile's records are done with spart
+            request_partials(A, n0, mc, fb_cur, fb, tid, nthr);
             cp_async_commit();
             cp_async_wait_all();
             __syncthreads();
-            finish_tile(A, me, fb_cur, fb, tid, nthr, fuse);
+            const int nrec = min(mc.y - mc.x, A.cap_recs);
+            if (tid < nrec) {
+                double own[3] = {0.0, 0.0, 0.0};
+                if (fuse) { own[0] = fb.pend[3 * tid]; own[1] = fb.pend[3 * tid + 1]; own[2] = fb.pend[3 * tid + 2]; }
+                finish_record(A, n0, mc, fb_cur, fb, tid, own, fuse);
+            }
             break;
         }
         t = tn;
