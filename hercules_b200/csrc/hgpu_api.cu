@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -144,6 +145,9 @@ struct hgpu_solver {
     unsigned int *t_flag = nullptr;      // [ntiles] epoch of each tile's last publish
     unsigned int epoch = 0;              // one per pass over all tiles
     int32_t n_self = 0;
+    // BKT: memory variables (entry-chunked), per-entry coefficient records, element -> entry
+    double *conv = nullptr; double *t_ent_bkt = nullptr; int32_t *entry_of_elem = nullptr;
+    double *conv_scratch = nullptr;      // [8 E][3] staging for hgpu_fetch_all / hgpu_store_all of a conv array
     double *nt3 = nullptr;               // [N][3] {+-1/mass, m2, m1} for the fused update
     int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, grid_late = 0, cap_slots = 0, cap_acc = 0, cap_owned = 0,
         cap_recs = 0, cap_srcs = 0, ctas_per_sm = 0;
@@ -320,8 +324,8 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         return fail(HGPU_EINVAL, "hgpu_init: elem_lnid, eTable and nTable are required");
     if (params->damping < 0 || params->damping > 3 || params->stiffness < 0 || params->stiffness > 1)
         return fail(HGPU_EINVAL, "hgpu_init: bad damping/stiffness type");
-    if (params->damping == HGPU_DAMPING_BKT)
-        return fail(HGPU_EINVAL, "hgpu_init: BKT damping is not available in this build");
+    if (params->damping == HGPU_DAMPING_BKT && !mesh->edata)
+        return fail(HGPU_EINVAL, "hgpu_init: BKT damping needs edata (psolve.h:95-97)");
     if (params->stiffness == HGPU_STIFFNESS_CONVENTIONAL && (!mesh->K1 || !mesh->K2))
         return fail(HGPU_EINVAL, "hgpu_init: conventional stiffness needs K1 and K2");
     if (params->nranks < 1 || params->rank < 0 || params->rank >= params->nranks)
@@ -467,7 +471,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // ("self" tiles); without the fused update every node's force goes to the force array and
         // no node needs a record of its own
         const bool fused = !(params->flags & HGPU_FLAG_NO_FUSE);
-        if (!build_tile_plan(E, N, mesh->elem_lnid, caps, params->nranks > 1 ? early_node.data() : nullptr,
+        // BKT: an element's memory variables are advanced by its one core evaluation, so no tile may
+        // re-evaluate foreign elements: no self tiles, the exchange follows the whole pass
+        const bool bkt = params->damping == HGPU_DAMPING_BKT;
+        if (!build_tile_plan(E, N, mesh->elem_lnid, caps, (params->nranks > 1 && !bkt) ? early_node.data() : nullptr,
                              fused ? cls.data() : nullptr, s->plan, err)) {
             hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
         }
@@ -509,6 +516,24 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
         TRY(upload(s, &s->t_halo_id, pl.halo_id.data(), pl.halo_id.size()));
+        if (bkt) {
+            if (entries != (size_t)E) { hgpu_finalize(s); return fail(HGPU_EINVAL, "internal: BKT plan with extra entries"); }
+            // record: c1, c2, then edata[4..13] = a0s a1s bs g0s g1s a0k a1k bk g0k g1k (psolve.h:95-97)
+            std::vector<double> rec8(8 * entries, 0.0);
+            std::vector<int32_t> eoe((size_t)E, -1);
+            for (size_t k = 0; k < entries; k++) {
+                const int32_t e = pl.elem_id[k];
+                const double *et = mesh->eTable + 4 * (size_t)e;
+                rec8[8 * k] = et[0]; rec8[8 * k + 1] = et[1];
+                memcpy(&rec8[8 * k + 2], mesh->edata + 14 * (size_t)e + 4, 10 * sizeof(float));
+                eoe[e] = (int32_t)k;
+            }
+            TRY(upload(s, &s->t_ent_bkt, rec8.data(), rec8.size()));
+            TRY(upload(s, &s->entry_of_elem, eoe.data(), eoe.size()));
+            const size_t nconv = ((entries + 31) / 32) * (size_t)CONV_PER_ENTRY * 32;
+            TRY(dalloc(s, &s->conv, nconv));
+            TRYCU(cudaMemset(s->conv, 0, std::max<size_t>(1, nconv) * sizeof(double)));   // calloc, psolve.c:3322-3325
+        }
         {
             std::vector<uint2> rec(pl.rec.size());
             for (size_t i = 0; i < pl.rec.size(); i++)
@@ -544,6 +569,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaFuncSetAttribute(step_kernel<0, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<1, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
+            TRYCU(cudaFuncSetAttribute(step_kernel<3, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
@@ -586,6 +612,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
     dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id);
+    dfree(s->conv); dfree(s->t_ent_bkt); dfree(s->entry_of_elem); dfree(s->conv_scratch);
     dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
@@ -605,7 +632,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
 // ---- force evaluation ---------------------------------------------------------------------------
 
 // The force terms requested since the last update (hgpu_force_stiffness / hgpu_force_damping).
-struct Terms { bool stiff, need_u2; bool any() const { return stiff || need_u2; } };
+struct Terms { bool stiff, need_u2, bkt; bool any() const { return stiff || need_u2 || bkt; } };
 
 static Terms consume_terms(hgpu_solver *s)
 {
@@ -613,6 +640,8 @@ static Terms consume_terms(hgpu_solver *s)
     t.stiff = s->want_stiff;
     // MASS damping has b = 0, hence c3 = c4 = 0 (psolve.c:5866-5867): damping_addforce adds nothing
     t.need_u2 = s->want_damp && s->P.damping == HGPU_DAMPING_RAYLEIGH;
+    // BKT: calc_conv + constant_Q_addforce, which carries the elastic term too (psolve.c:3969, 4003-4010)
+    t.bkt = s->want_damp && s->P.damping == HGPU_DAMPING_BKT;
     s->want_stiff = s->want_damp = false;
     return t;
 }
@@ -632,8 +661,10 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.tile_begin = begin; A.ntiles = end; A.cap_slots = s->cap_slots; A.cap_acc = s->cap_acc; A.cap_owned = s->cap_owned;
     A.cap_recs = s->cap_recs; A.cap_srcs = s->cap_srcs;
     A.fuse_update = fuse ? 1 : 0;
-    const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL;
-    const int mode = tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
+    A.conv = s->conv; A.ent_bkt = s->t_ent_bkt;
+    A.rmax = 2.0 * M_PI * s->P.freq * s->P.dt;                     // damping.c:114, 234
+    const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt;
+    const int mode = tm.bkt ? 3 : tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
@@ -645,6 +676,8 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
             if (mode == 0)      step_kernel<0, true, T><<<G, B, s->smem_nou2, s->stream>>>(A);   \
             else if (mode == 1) step_kernel<1, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
             else                step_kernel<2, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
+        } else if (mode == 3) {                                                                  \
+            step_kernel<3, false, T><<<G, B, s->smem_u2, s->stream>>>(A);                        \
         } else {                                                                                 \
             if (mode == 0)      step_kernel<0, false, T><<<G, B, s->smem_nou2, s->stream>>>(A);  \
             else if (mode == 1) step_kernel<1, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
@@ -1011,8 +1044,28 @@ static int resolve(hgpu_solver *s, int32_t which, double **p, size_t *count)
                                      "read it before hgpu_force_exchange or use HGPU_FLAG_NO_FUSE");
         *p = s->force; return HGPU_OK;
     }
+    case HGPU_CONV_SHEAR_1: case HGPU_CONV_SHEAR_2: case HGPU_CONV_KAPPA_1: case HGPU_CONV_KAPPA_2: {
+        if (!s->conv) return fail(HGPU_EINVAL, "conv arrays exist with BKT damping only");
+        *count = 24 * (size_t)s->E;
+        if (!s->conv_scratch) { int rc = dalloc(s, &s->conv_scratch, *count); if (rc) return rc; }
+        *p = s->conv_scratch;       // the caller converts between the layouts (conv_to_ref / conv_from_ref)
+        return HGPU_OK;
+    }
     default: return fail(HGPU_EINVAL, "unknown array selector %d", which);
     }
+}
+
+static bool is_conv(int32_t which) { return which >= HGPU_CONV_SHEAR_1 && which <= HGPU_CONV_KAPPA_2; }
+// reference layout <-> entry-chunked device layout of one conv array, through conv_scratch
+static int conv_convert(hgpu_solver *s, int32_t which, int to_ref)
+{
+    const int k0 = (which - HGPU_CONV_SHEAR_1) * 24;        // shear_1, shear_2, kappa_1, kappa_2
+    if (s->E == 0) return HGPU_OK;
+    conv_convert_kernel<<<grid_for(24LL * s->E, 256), 256, 0, s->stream>>>(s->E, s->entry_of_elem, k0, s->conv,
+                                                                            s->conv_scratch, to_ref);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    return HGPU_OK;
 }
 
 extern "C" int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out)
@@ -1022,6 +1075,7 @@ extern "C" int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out)
     double *p; size_t cnt;
     int rc = resolve(s, which, &p, &cnt);
     if (rc) return rc;
+    if (is_conv(which) && (rc = conv_convert(s, which, 1))) return rc;
     CK(cudaMemcpyAsync(out, p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
     return HGPU_OK;
@@ -1035,6 +1089,7 @@ extern "C" int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in)
     int rc = resolve(s, which, &p, &cnt);
     if (rc) return rc;
     CK(cudaMemcpyAsync(p, in, cnt * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    if (is_conv(which) && (rc = conv_convert(s, which, 0))) return rc;
     CK(cudaStreamSynchronize(s->stream));
     return HGPU_OK;
 }
@@ -1043,6 +1098,7 @@ extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *
 {
     if (!s || (n > 0 && (!lnid || !out)) || n < 0) return fail(HGPU_EINVAL, "bad argument");
     if (n == 0) return HGPU_OK;
+    if (is_conv(which)) return fail(HGPU_EINVAL, "hgpu_fetch_nodes addresses node arrays only");
     CK(cudaSetDevice(s->dev));
     double *p; size_t cnt;
     int rc = resolve(s, which, &p, &cnt);

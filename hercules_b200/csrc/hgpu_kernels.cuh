@@ -130,6 +130,8 @@ __device__ __forceinline__ void scale_modes(const double (&tx)[8], const double 
 //   MODE 0: w = u1                     stiffness term only            (damping none / mass)
 //   MODE 1: w = u1 + beta (u1 - u2)    stiffness + Rayleigh damping   beta = c3/c1 = c4/c2 = b/dt
 //   MODE 2: w = beta (u1 - u2)         Rayleigh damping only          (psolve.c:3387-3409)
+//   MODE 3: BKT: memory variables advanced (calc_conv) and the constant-Q force, which includes
+//           the elastic term (constant_Q_addforce), in one pass over the element's 768 B of state
 // ------------------------------------------------------------------------------------------
 struct StepArgs {
     const double *__restrict__ u1;      // tm1  [N][3]
@@ -155,7 +157,22 @@ struct StepArgs {
     int32_t cap_owned;                  // owned nodes (pending buffer)
     int32_t cap_recs, cap_srcs;         // finish records / sources staged per tile
     int32_t fuse_update;                // 1: advance owned REGULAR nodes here
+    // BKT (MODE 3): per-entry memory variables and coefficients
+    double *conv;                       // conv_shear_1|2, conv_kappa_1|2 in entry-chunked layout, see conv_index
+    const double *__restrict__ ent_bkt; // per entry 8 doubles: c1, c2, then 10 floats a0s a1s bs g0s g1s a0k a1k bk g0k g1k, pad
+    double rmax;                        // 2 pi f_max dt (damping.c:114)
 };
+
+// BKT memory variables (psolve.h:308-311: conv_shear_1, conv_shear_2, conv_kappa_1, conv_kappa_2,
+// each [8 E][3] in the reference) are stored per tile ENTRY in chunks of 32 entries so that the 32
+// lanes of a warp read 256 contiguous bytes per value:
+//   index(entry, k) = ((entry / 32) * 96 + k) * 32 + entry % 32,  k = family * 48 + which * 24 + 3 * node + comp
+// (family 0 = shear, 1 = kappa; which 0 = conv_*_1, 1 = conv_*_2).
+constexpr int CONV_PER_ENTRY = 96;
+__host__ __device__ __forceinline__ size_t conv_index(size_t entry, int k)
+{
+    return ((entry >> 5) * CONV_PER_ENTRY + (size_t)k) * 32 + (entry & 31);
+}
 
 constexpr int META_INTS = 16;           // per tile
 constexpr int META_RING = 8;
@@ -234,14 +251,19 @@ __device__ __forceinline__ int4 meta_group(const int *slot, int g)
     return v;
 }
 
-template <bool NEED_BETA>
+// MODE 0: slots + c1, c2; MODE 1, 2: + beta; MODE 3 (BKT): slots only, the coefficient record is
+// read where the round starts
+template <int MODE>
 __device__ __forceinline__ Entry load_entry(const StepArgs &A, int idx)
 {
     Entry e;
     e.s = ldg_u4_pinned(A.ent_slot + idx);
-    const double *c = A.ent_coef + 3 * (size_t)idx;
-    e.c1 = ldg_f64_pinned(c); e.c2 = ldg_f64_pinned(c + 1);
-    e.beta = NEED_BETA ? ldg_f64_pinned(c + 2) : 0.0;
+    e.c1 = e.c2 = e.beta = 0.0;
+    if (MODE != 3) {
+        const double *c = A.ent_coef + 3 * (size_t)idx;
+        e.c1 = ldg_f64_pinned(c); e.c2 = ldg_f64_pinned(c + 1);
+        if (MODE != 0) e.beta = ldg_f64_pinned(c + 2);
+    }
     return e;
 }
 
@@ -413,6 +435,84 @@ __device__ __forceinline__ void finish_record(const StepArgs &A, int n0, const i
     }
 }
 
+// firstVector_mu (stiffness.c:351-379): v += shear part of the scaled modes, b = -0.5625 c1
+__device__ __forceinline__ void scale_modes_mu_add(const double (&tx)[8], const double (&ty)[8],
+                                                   const double (&tz)[8], double b,
+                                                   double (&vx)[8], double (&vy)[8], double (&vz)[8])
+{
+    const double b3 = b * (1.0 / 3.0), b9 = b * (1.0 / 9.0), b27 = b * (10.0 / 27.0);
+    const double sxz = b * (tz[3] + tx[1]), sxy = b * (ty[3] + tx[2]), syz = b * (tz[2] + ty[1]);
+    const double m4 = b3 * (ty[5] + tz[6] + 2.0 * tx[4]);
+    const double m5 = b3 * (tx[4] + tz[6] + 2.0 * ty[5]);
+    const double m6 = b3 * (tx[4] + ty[5] + 2.0 * tz[6]);
+    vx[1] += sxz; vx[2] += sxy; vx[3] += b3 * (4.0 * tx[3] - 2.0 * (ty[2] + tz[1]));
+    vx[4] += m4;  vx[5] += b9 * (7.0 * tx[5] - 2.0 * ty[4]); vx[6] += b9 * (7.0 * tx[6] - 2.0 * tz[4]);
+    vx[7] += b27 * tx[7];
+    vy[1] += syz; vy[2] += b3 * (4.0 * ty[2] - 2.0 * (tx[3] + tz[1])); vy[3] += sxy;
+    vy[4] += b9 * (7.0 * ty[4] - 2.0 * tx[5]); vy[5] += m5; vy[6] += b9 * (7.0 * ty[6] - 2.0 * tz[5]);
+    vy[7] += b27 * ty[7];
+    vz[1] += b3 * (4.0 * tz[1] - 2.0 * (tx[3] + ty[2])); vz[2] += syz; vz[3] += sxz;
+    vz[4] += b9 * (7.0 * tz[4] - 2.0 * tx[6]); vz[5] += b9 * (7.0 * tz[5] - 2.0 * ty[6]); vz[6] += m6;
+    vz[7] += b27 * tz[7];
+}
+
+// firstVector_kappa (stiffness.c:321-349): v += volumetric part, kappa = -0.5625 (c2 + 2/3 c1)
+__device__ __forceinline__ void scale_modes_kappa_add(const double (&tx)[8], const double (&ty)[8],
+                                                      const double (&tz)[8], double kap,
+                                                      double (&vx)[8], double (&vy)[8], double (&vz)[8])
+{
+    const double k3 = kap * (1.0 / 3.0), k9 = kap * (1.0 / 9.0);
+    const double div = kap * (tx[3] + ty[2] + tz[1]);
+    const double exy = k3 * (tx[5] + ty[4]), exz = k3 * (tx[6] + tz[4]), eyz = k3 * (ty[6] + tz[5]);
+    vx[3] += div; vx[5] += exy; vx[6] += exz; vx[7] += k9 * tx[7];
+    vy[2] += div; vy[4] += exy; vy[6] += eyz; vy[7] += k9 * ty[7];
+    vz[1] += div; vz[4] += exz; vz[5] += eyz; vz[7] += k9 * tz[7];
+}
+
+// One family (shear or kappa) of calc_conv + the damping vector of constant_Q_addforce
+// (damping.c:126-169 / 173-216 and 256-311 / 315-371) for one element: the memory variables are
+// advanced in place (global memory, entry-chunked layout) and the 8 x 3 damping vector
+//   d = (b / rmax) (u1 - u2) - (a0 f0 + a1 f1) + u1     (or u1 when a0 + a1 + b = 0)
+// is taken straight to mode space, t[c][m] = sum_i S[m][i] d[i][c] (the sign matrix of aTransposeU,
+// stiffness.c:260-288; row 0 is dropped as the reference zeroes it), without ever being stored.
+__device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, float a0f, float a1f, float bf,
+                                           float g0f, float g1f, double rmax, const double *su1, const double *su2,
+                                           const uint32_t (&sl)[8], double (&tx)[8], double (&ty)[8], double (&tz)[8])
+{
+    const bool advance = g0f != 0.f && g1f != 0.f;           // damping.c:126, 173
+    const double a0 = a0f, a1 = a1f, b = bf;
+    const bool damped = (a0 + a1 + b) != 0.0;                 // damping.c:262, 321
+    const double g0 = (double)g0f * rmax, g1 = (double)g1f * rmax;
+    const double k1 = 0.5 * g0, k2 = k1 * (1.0 - g0), k3 = 0.5 * g1, k4 = k3 * (1.0 - g1);
+    const double e0 = exp(-g0), e1 = exp(-g1), cb = b / rmax;
+#pragma unroll
+    for (int m = 0; m < 8; m++) { tx[m] = 0.0; ty[m] = 0.0; tz[m] = 0.0; }
+    double *p0 = conv + conv_index(entry, fam * 48), *p1 = p0 + 24 * 32;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        double d[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const double x1 = su1[sl[i] + c], x2 = su2[sl[i] + c];
+            double f0 = p0[(3 * i + c) * 32], f1 = p1[(3 * i + c) * 32];
+            if (advance) {
+                f0 = fma(e0, f0, k2 * x1 + k1 * x2);
+                f1 = fma(e1, f1, k4 * x1 + k3 * x2);
+                p0[(3 * i + c) * 32] = f0; p1[(3 * i + c) * 32] = f1;
+            }
+            d[c] = damped ? (cb * (x1 - x2) - (a0 * f0 + a1 * f1)) + x1 : x1;
+        }
+        // node i = ix + 2 iy + 4 iz; mode signs (see wht_forward): 1 = z, 2 = y, 3 = x, 4 = yz, 5 = xz, 6 = xy, 7 = xyz
+        const bool px = i & 1, py = i & 2, pz = i & 4;
+#define HGPU_ACC(T, v)                                                                     \
+        T[1] += pz ? (v) : -(v); T[2] += py ? (v) : -(v); T[3] += px ? (v) : -(v);              \
+        T[4] += (py == pz) ? (v) : -(v); T[5] += (px == pz) ? (v) : -(v);                       \
+        T[6] += (px == py) ? (v) : -(v); T[7] += ((px != py) != pz) ? (v) : -(v);
+        HGPU_ACC(tx, d[0]) HGPU_ACC(ty, d[1]) HGPU_ACC(tz, d[2])
+#undef HGPU_ACC
+    }
+}
+
 template <int MODE, bool DENSE, int THREADS>
 __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 {
@@ -470,7 +570,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
     {
         const int4 mb = meta_group(smeta[0], 1);
-        if (tid < mb.y - mb.x) enext = load_entry<U2E>(A, mb.x + tid);
+        if (tid < mb.y - mb.x) enext = load_entry<MODE>(A, mb.x + tid);
     }
 
     for (int it = 0;; it++) {
@@ -523,9 +623,9 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             }
             // next round's entry (or the first round of the next tile) rides along with the math
             if (!last) {
-                if (base + nthr + tid < ne) enext = load_entry<U2E>(A, eb + base + nthr + tid);
+                if (base + nthr + tid < ne) enext = load_entry<MODE>(A, eb + base + nthr + tid);
             } else if (tid < nxt_ne) {
-                enext = load_entry<U2E>(A, nxt_eb + tid);
+                enext = load_entry<MODE>(A, nxt_eb + tid);
             }
             double fx[8], fy[8], fz[8];
             uint32_t sl[8];
@@ -533,6 +633,23 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 sl[0] = ecur.s.x & 0xffffu; sl[1] = ecur.s.x >> 16; sl[2] = ecur.s.y & 0xffffu; sl[3] = ecur.s.y >> 16;
                 sl[4] = ecur.s.z & 0xffffu; sl[5] = ecur.s.z >> 16; sl[6] = ecur.s.w & 0xffffu; sl[7] = ecur.s.w >> 16;
                 double wx[8], wy[8], wz[8];
+                if (MODE == 3) {
+                    // BKT: calc_conv + constant_Q_addforce (damping.c:110-416), elastic term included
+                    const size_t entry = (size_t)(eb + base + tid);
+                    const double *cr = A.ent_bkt + 8 * entry;
+                    const double c1 = __ldg(cr), c2 = __ldg(cr + 1);
+                    const float2 q0 = __ldg(reinterpret_cast<const float2 *>(cr + 2)), q1 = __ldg(reinterpret_cast<const float2 *>(cr + 3));
+                    const float2 q2 = __ldg(reinterpret_cast<const float2 *>(cr + 4)), q3 = __ldg(reinterpret_cast<const float2 *>(cr + 5));
+                    const float2 q4 = __ldg(reinterpret_cast<const float2 *>(cr + 6));
+                    double tx[8], ty[8], tz[8];
+#pragma unroll
+                    for (int m = 0; m < 8; m++) { wx[m] = 0.0; wy[m] = 0.0; wz[m] = 0.0; }
+                    bkt_family(A.conv, entry, 0, q0.x, q0.y, q1.x, q1.y, q2.x, A.rmax, su1, su2, sl, tx, ty, tz);
+                    scale_modes_mu_add(tx, ty, tz, -0.5625 * c1, wx, wy, wz);
+                    bkt_family(A.conv, entry, 1, q2.y, q3.x, q3.y, q4.x, q4.y, A.rmax, su1, su2, sl, tx, ty, tz);
+                    scale_modes_kappa_add(tx, ty, tz, -0.5625 * (c2 + (2.0 / 3.0) * c1), wx, wy, wz);
+                    wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
+                } else {
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
                     const int o = sl[j];
@@ -577,6 +694,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                             if (jj == i) { fx[jj] = r[0]; fy[jj] = r[1]; fz[jj] = r[2]; }
                     }
                 }
+                }
             }
             if (last) {
                 if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
@@ -599,7 +717,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             }
         }
         if (ne == 0) {                          // a tile of element-less nodes: keep the pipeline fed
-            if (tid < nxt_ne) enext = load_entry<U2E>(A, nxt_eb + tid);
+            if (tid < nxt_ne) enext = load_entry<MODE>(A, nxt_eb + tid);
             if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
             if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
             if (prv_pending) {
@@ -850,6 +968,18 @@ __global__ void p2p_pull_kernel(const PullSeg *__restrict__ segs, double *__rest
         const double x = __ldcg(sg.local + k);
         v[g] = add ? v[g] + x : x;
     }
+}
+
+// BKT memory variables between the reference's layout ([8 E][3] per array, psolve.h:308-311) and the
+// entry-chunked device layout.  which_k0 = family * 48 + which * 24; to_ref = 1: device -> ref.
+__global__ void conv_convert_kernel(int E, const int32_t *__restrict__ entry_of_elem, int which_k0,
+                                    double *conv, double *ref, int to_ref)
+{
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 24LL * E) return;
+    const int e = (int)(k / 24), ic = (int)(k % 24);
+    const size_t idx = conv_index((size_t)entry_of_elem[e], which_k0 + ic);
+    if (to_ref) ref[k] = conv[idx]; else conv[idx] = ref[k];
 }
 
 __global__ void gather_nodes_kernel(int n, const int32_t *__restrict__ lnid, const double *__restrict__ v,

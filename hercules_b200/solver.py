@@ -27,6 +27,7 @@ from . import _lib
 RAYLEIGH, MASS, NONE, BKT = 0, 1, 2, 3      # damping_type_t, damping.h:28
 CONVENTIONAL, EFFECTIVE = 0, 1              # stiffness_type_t, stiffness.h:24
 TM1, TM2, TM3, FORCE = 1, 2, 3, 4
+CONV_SHEAR_1, CONV_SHEAR_2, CONV_KAPPA_1, CONV_KAPPA_2 = 5, 6, 7, 8   # psolve.h:308-311, [8 E][3] each
 FLAG_NO_FUSE = 1
 FLAG_TIMERS = 2
 FLAG_NO_OVERLAP = 4
@@ -226,15 +227,18 @@ class Solver:
             _chk(self._L.hgpu_run(self._h, step0, nsteps, None))
 
     # -- taps ------------------------------------------------------------------------------------------
+    def _rows(self, which: int) -> int:
+        return 8 * self.E if CONV_SHEAR_1 <= which <= CONV_KAPPA_2 else self.N
+
     def fetch_all(self, which: int) -> np.ndarray:
-        out = np.empty((self.N, 3), np.float64)
+        out = np.empty((self._rows(which), 3), np.float64)
         _chk(self._L.hgpu_fetch_all(self._h, which, out.ctypes.data))
         return out
 
     def store_all(self, which: int, a) -> None:
         a = np.ascontiguousarray(a, np.float64)
-        if a.size != 3 * self.N:
-            raise ValueError("array must be [nharbored][3]")
+        if a.size != 3 * self._rows(which):
+            raise ValueError("array must be [nharbored][3] ([8 lenum][3] for a conv array)")
         _chk(self._L.hgpu_store_all(self._h, which, a.ctypes.data))
 
     def fetch_nodes(self, which: int, lnid) -> np.ndarray:
