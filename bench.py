@@ -51,8 +51,12 @@ sys.path.insert(0, str(ROOT))
 METRIC = "element-updates/sec"
 UNIT = "element-updates/s"
 LAYERS = ((0.0, 4000.0, 2000.0, 2600.0), (1000.0, 6000.0, 3464.0, 2700.0))   # ztop, Vp, Vs, rho
+# --damping bkt: a soft sedimentary column (Vs 500..1500) so that Qs AND Qk fall inside the BKT
+# table for every element (psolve.c:7255-7310): both memory-variable families are advanced everywhere
+LAYERS_BKT = ((0.0, 1500.0, 500.0, 2000.0), (500.0, 2200.0, 1000.0, 2200.0), (2000.0, 3000.0, 1500.0, 2400.0))
 H_M, DT, FREQ = 25.0, 0.002, 1.0
-BYTES_PER_ELEM = 64      # 32 B ids + 32 B coefficients
+BYTES_PER_ELEM = {"rayleigh": 64,       # 32 B ids + 32 B coefficients
+                  "bkt": 1624}          # 32 ids + 16 c1,c2 + 40 BKT coefs + 768 state read + 768 state write
 BYTES_PER_NODE = 248     # 72 B (tm1, tm2, force write) + 176 B update
 
 
@@ -203,10 +207,13 @@ def block_grid(world: int) -> tuple[int, int, int]:
     return bx, by, bz
 
 
-def workload_config(world: int, n: int, halo: str = "p2p") -> dict:
+def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh") -> dict:
     bx, by, bz = block_grid(world)
-    return {"workload": f"configs[1]: layered half-space (LOH.1 values), uniform octree mesh {n}^3 elements "
-                        f"per GPU (h={H_M:g} m), rayleigh damping, effective stiffness, point source, 5 stations",
+    what = ("rayleigh damping, effective stiffness" if damping == "rayleigh" else
+            "BKT damping (variant of configs[1] with configs[4]'s damping model on a soft sedimentary column, "
+            "Vs 500-1500 m/s; Qs, Qk from Vs as mesh_correct_properties derives them)")
+    return {"workload": f"configs[1]: layered half-space{' (LOH.1 values)' if damping == 'rayleigh' else ''}, uniform octree mesh {n}^3 elements "
+                        f"per GPU (h={H_M:g} m), {what}, point source, 5 stations",
             "elements_per_gpu": n ** 3, "global_elements": n ** 3 * world,
             "global_grid": [n * bx, n * by, n * bz], "dt": DT,
             "partition": f"{world} Morton-contiguous block(s) (octor_partitiontree rule), halo exchange over "
@@ -225,6 +232,8 @@ def main() -> None:
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after all tiles, one stream")
     ap.add_argument("--tile-nodes", type=int, default=0)
+    ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
+                    help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
     args = ap.parse_args()
@@ -261,11 +270,13 @@ def main() -> None:
     n = args.n
     bx, by, bz = block_grid(world)
     t0 = time.time()
+    damp = hb.BKT if args.damping == "bkt" else hb.RAYLEIGH
+    layers = LAYERS_BKT if args.damping == "bkt" else LAYERS
     if world == 1:
-        mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=LAYERS)
+        mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
     else:
         mesh, info = meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=H_M, dt=DT, freq=FREQ,
-                                               layers=LAYERS, part=(rank, world))
+                                               layers=layers, part=(rank, world), damping=damp)
     E, N = info["E"], info["N"]
     # point source: the 8 nodes of the element at the centre of this rank's block, 2000 m deep on
     # rank 0 (other ranks carry no source, as in a real run where one rank holds the hypocentre)
@@ -286,7 +297,7 @@ def main() -> None:
     t_mesh = time.time() - t0
 
     t0 = time.time()
-    s = hb.Solver(mesh, dt=DT, damping=hb.RAYLEIGH, stiffness=hb.EFFECTIVE, freq=FREQ,
+    s = hb.Solver(mesh, dt=DT, damping=damp, stiffness=hb.EFFECTIVE, freq=FREQ,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
                   tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0))
     if world > 1:
@@ -361,7 +372,7 @@ def main() -> None:
 
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.damping == "rayleigh":
         try:
             r = reference_sample(100)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -370,7 +381,7 @@ def main() -> None:
 
     if rank == 0:
         peak, peak_src = peaks()
-        alg_bytes = BYTES_PER_ELEM * E + BYTES_PER_NODE * N
+        alg_bytes = BYTES_PER_ELEM[args.damping] * E + BYTES_PER_NODE * N
         k_s = fused_s / max(tile_launches, 1)
         achieved = alg_bytes / k_s / 1e9 if k_s > 0 else None
         line = {
@@ -378,9 +389,12 @@ def main() -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv"),
+            "config": workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",
+                                      args.damping),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "tile_kernel<true,false> (element force + update, fused)",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("step_kernel<1,false,256> (stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"
+                                    else "step_kernel<3,false,256> (BKT memory variables + constant-Q force + update, fused)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,
@@ -397,7 +411,7 @@ def main() -> None:
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             try:
-                line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("tile_kernel_bytes_per_launch")
+                line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("step_kernel_bytes_per_launch" if args.damping == "rayleigh" else "step_kernel_bkt_bytes_per_launch")
             except Exception:
                 pass
         sys.stdout.flush()

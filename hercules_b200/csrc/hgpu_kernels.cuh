@@ -477,7 +477,7 @@ __device__ __forceinline__ void scale_modes_kappa_add(const double (&tx)[8], con
 // stiffness.c:260-288; row 0 is dropped as the reference zeroes it), without ever being stored.
 __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, float a0f, float a1f, float bf,
                                            float g0f, float g1f, double rmax, const double *su1, const double *su2,
-                                           const uint32_t (&sl)[8], double (&tx)[8], double (&ty)[8], double (&tz)[8])
+                                           const uint4 slots, double (&tx)[8], double (&ty)[8], double (&tz)[8])
 {
     const bool advance = g0f != 0.f && g1f != 0.f;           // damping.c:126, 173
     const double a0 = a0f, a1 = a1f, b = bf;
@@ -488,28 +488,44 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
 #pragma unroll
     for (int m = 0; m < 8; m++) { tx[m] = 0.0; ty[m] = 0.0; tz[m] = 0.0; }
     double *p0 = conv + conv_index(entry, fam * 48), *p1 = p0 + 24 * 32;
+    // two nodes (an x pair: ix = 0, 1) per trip, not unrolled further: 12 loads of state in flight
+    // per thread keep HBM busy without the whole element's 48 values sitting in registers
+#pragma unroll 1
+    for (int h = 0; h < 4; h++) {
+        const uint32_t w = h == 0 ? slots.x : h == 1 ? slots.y : h == 2 ? slots.z : slots.w;
+        const uint32_t o[2] = {w & 0xffffu, w >> 16};
+        double f0[2][3], f1[2][3];
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        double d[3];
+        for (int q = 0; q < 2; q++)
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const double x1 = su1[sl[i] + c], x2 = su2[sl[i] + c];
-            double f0 = p0[(3 * i + c) * 32], f1 = p1[(3 * i + c) * 32];
-            if (advance) {
-                f0 = fma(e0, f0, k2 * x1 + k1 * x2);
-                f1 = fma(e1, f1, k4 * x1 + k3 * x2);
-                p0[(3 * i + c) * 32] = f0; p1[(3 * i + c) * 32] = f1;
+            for (int c = 0; c < 3; c++) {
+                f0[q][c] = p0[(6 * h + 3 * q + c) * 32];
+                f1[q][c] = p1[(6 * h + 3 * q + c) * 32];
             }
-            d[c] = damped ? (cb * (x1 - x2) - (a0 * f0 + a1 * f1)) + x1 : x1;
-        }
-        // node i = ix + 2 iy + 4 iz; mode signs (see wht_forward): 1 = z, 2 = y, 3 = x, 4 = yz, 5 = xz, 6 = xy, 7 = xyz
-        const bool px = i & 1, py = i & 2, pz = i & 4;
+        const bool py = h & 1, pz = h & 2;                    // node = q + 2 h: iy = h & 1, iz = h >> 1
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            double d[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const double x1 = su1[o[q] + c], x2 = su2[o[q] + c];
+                double v0 = f0[q][c], v1 = f1[q][c];
+                if (advance) {
+                    v0 = fma(e0, v0, k2 * x1 + k1 * x2);
+                    v1 = fma(e1, v1, k4 * x1 + k3 * x2);
+                    p0[(6 * h + 3 * q + c) * 32] = v0; p1[(6 * h + 3 * q + c) * 32] = v1;
+                }
+                d[c] = damped ? (cb * (x1 - x2) - (a0 * v0 + a1 * v1)) + x1 : x1;
+            }
+            // mode signs (see wht_forward): 1 = z, 2 = y, 3 = x, 4 = yz, 5 = xz, 6 = xy, 7 = xyz
+            const bool px = q == 1;
 #define HGPU_ACC(T, v)                                                                     \
-        T[1] += pz ? (v) : -(v); T[2] += py ? (v) : -(v); T[3] += px ? (v) : -(v);              \
-        T[4] += (py == pz) ? (v) : -(v); T[5] += (px == pz) ? (v) : -(v);                       \
-        T[6] += (px == py) ? (v) : -(v); T[7] += ((px != py) != pz) ? (v) : -(v);
-        HGPU_ACC(tx, d[0]) HGPU_ACC(ty, d[1]) HGPU_ACC(tz, d[2])
+            T[1] += pz ? (v) : -(v); T[2] += py ? (v) : -(v); T[3] += px ? (v) : -(v);          \
+            T[4] += (py == pz) ? (v) : -(v); T[5] += (px == pz) ? (v) : -(v);                   \
+            T[6] += (px == py) ? (v) : -(v); T[7] += ((px != py) != pz) ? (v) : -(v);
+            HGPU_ACC(tx, d[0]) HGPU_ACC(ty, d[1]) HGPU_ACC(tz, d[2])
 #undef HGPU_ACC
+        }
     }
 }
 
@@ -644,9 +660,9 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                     double tx[8], ty[8], tz[8];
 #pragma unroll
                     for (int m = 0; m < 8; m++) { wx[m] = 0.0; wy[m] = 0.0; wz[m] = 0.0; }
-                    bkt_family(A.conv, entry, 0, q0.x, q0.y, q1.x, q1.y, q2.x, A.rmax, su1, su2, sl, tx, ty, tz);
+                    bkt_family(A.conv, entry, 0, q0.x, q0.y, q1.x, q1.y, q2.x, A.rmax, su1, su2, ecur.s, tx, ty, tz);
                     scale_modes_mu_add(tx, ty, tz, -0.5625 * c1, wx, wy, wz);
-                    bkt_family(A.conv, entry, 1, q2.y, q3.x, q3.y, q4.x, q4.y, A.rmax, su1, su2, sl, tx, ty, tz);
+                    bkt_family(A.conv, entry, 1, q2.y, q3.x, q3.y, q4.x, q4.y, A.rmax, su1, su2, ecur.s, tx, ty, tz);
                     scale_modes_kappa_add(tx, ty, tz, -0.5625 * (c2 + (2.0 / 3.0) * c1), wx, wy, wz);
                     wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
                 } else {

@@ -23,7 +23,7 @@ import math
 
 import numpy as np
 
-from .solver import HostMesh, MsgList, RAYLEIGH, MASS
+from .solver import HostMesh, MsgList, RAYLEIGH, MASS, BKT
 
 _XI = np.array([[-1, 1, -1, 1, -1, 1, -1, 1],
                 [-1, -1, 1, 1, -1, -1, 1, 1],
@@ -145,6 +145,73 @@ class _MortonIndex:
         n = self.n
         return (self.bx[b] * n + _compact1by2(w), self.by[b] * n + _compact1by2(w >> np.uint64(1)),
                 self.bz[b] * n + _compact1by2(w >> np.uint64(2)))
+
+
+# constract_Quality_Factor_Table (psolve.c:5575-5616): 26 rows are declared but only the first 18
+# are copied into Global.theQTABLE; the rest stay zero (SURVEY.md 8a notes): kept as is.
+_QTABLE = np.zeros((26, 6))
+_QTABLE[:18] = np.array([
+    [5., 0.211111102, 0.236842104, 0.032142857, 0.271428571, 0.14],
+    [6.25, 0.188888889, 0.184210526, 0.039893617, 0.336879433, 0.10152],
+    [8.33, 0.157777778, 0.139473684, 0.045, 0.38, 0.07],
+    [10., 0.137777765, 0.12105263, 0.032942899, 0.27818448, 0.0683],
+    [15., 0.097777765, 0.08105263, 0.032942899, 0.27818448, 0.045],
+    [20., 0.078139527, 0.060526314, 0.031409788, 0.277574872, 0.034225],
+    [25., 0.064285708, 0.049999999, 0.031578947, 0.285714286, 0.0266],
+    [30., 0.053658537, 0.044736842, 0.026640676, 0.24691358, 0.023085],
+    [35., 0.046341463, 0.038157895, 0.02709848, 0.251156642, 0.019669],
+    [40., 0.040487805, 0.034210526, 0.025949367, 0.240506329, 0.01738],
+    [45., 0.036585366, 0.028947368, 0.031393568, 0.290964778, 0.014366],
+    [50., 0.032926829, 0.026315789, 0.032488114, 0.30110935, 0.01262],
+    [60., 0.0279, 0.0223, 0.0275, 0.2545, 0.0114],
+    [70., 0.024, 0.019, 0.032488114, 0.30110935, 0.0083],
+    [80., 0.0207, 0.0174, 0.0251, 0.2326, 0.0088],
+    [90., 0.0187, 0.0154, 0.0244, 0.2256, 0.0079],
+    [100., 0.017, 0.014, 0.028021016, 0.288966725, 0.006281],
+    [120., 0.0142, 0.0115, 0.0280, 0.2700, 0.0052]])
+
+
+def _search_quality_table(Q: np.ndarray) -> np.ndarray:
+    """Search_Quality_Table (quake_util.c:128-163), vectorised: the first row whose distance to Q
+    stops decreasing ends the scan and the row before it is returned; -1 for Q > 500; -2 = none."""
+    Q = np.asarray(Q, np.float64)
+    out = np.full(Q.shape, -2, np.int64)
+    done = Q > 500
+    out[done] = -1
+    mn = np.full(Q.shape, 1000.0)
+    for i in range(_QTABLE.shape[0]):
+        diff = np.abs(Q - _QTABLE[i, 0])
+        stop = ~done & ~(diff < mn)
+        out[stop] = i - 1
+        done |= stop
+        mn = np.where(~done & (diff < mn), diff, mn)
+    return out
+
+
+def bkt_coefficients(Vp, Vs, use_inf_qk: bool = False) -> np.ndarray:
+    """The ten BKT floats of edata_t (a0, a1, b, g0, g1 for shear, then for kappa; psolve.h:95-97)
+    as mesh_correct_properties derives them from the element's float Vp, Vs (psolve.c:7239-7310,
+    simulation_velocity_profile_freq_hz = 0).  Returns float32 [E][10] in edata order
+    a0_shear a1_shear b_shear g0_shear g1_shear a0_kappa a1_kappa b_kappa g0_kappa g1_kappa."""
+    Vp = np.asarray(Vp, np.float32).astype(np.float64)
+    Vs = np.asarray(Vs, np.float32).astype(np.float64)
+    vs_vp = (np.asarray(Vs, np.float32) / np.asarray(Vp, np.float32)).astype(np.float64)   # float division
+    vs = Vs * 0.001
+    L = 4. / 3. * vs_vp * vs_vp
+    Qs = 10.5 + vs * (-16. + vs * (153. + vs * (-103. + vs * (34.7 + vs * (-5.29 + vs * 0.31)))))
+    Qp = 2. * Qs
+    Qk = np.full(Qs.shape, 1000.0) if use_inf_qk else (1. - L) / (1. / Qp - L / Qs)
+    out = np.zeros((Vs.size, 10), np.float32)
+    for col, Q in ((0, Qs), (5, Qk)):
+        idx = _search_quality_table(Q)
+        if (idx == -2).any() or (idx >= _QTABLE.shape[0]).any():
+            raise ValueError("Problem with the Quality Factor Table (psolve.c:7266)")
+        ok = idx >= 0
+        row = _QTABLE[np.where(ok, idx, 0)]
+        # table columns 1..5 = a0, a1, g0, g1, b  ->  edata order a0, a1, b, g0, g1
+        vals = np.stack([row[:, 1], row[:, 2], row[:, 5], row[:, 3], row[:, 4]], axis=1)
+        out[:, col:col + 5] = np.where(ok[:, None], vals, 0.0).astype(np.float32)
+    return out
 
 
 def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs):
@@ -391,6 +458,8 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
             nT[rows] += partial[rows]
     edata = np.zeros((E, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
+    if damping == BKT:
+        edata[:, 4:14] = bkt_coefficients(pr["Vp"], pr["Vs"])
     K1, K2 = compute_K()
     mesh = HostMesh(lnid, pr["eT"], nT, np.zeros((0, 6), np.int32), edata, K1, K2,
                     msg["dn_c"], msg["dn_s"], msg["an_c"], msg["an_s"])

@@ -112,17 +112,29 @@ def test_whole_run_matches_reference(hb, name, flags):
     s.close()
 
 
+@pytest.mark.parametrize("edata", ["golden", "random"])
 @pytest.mark.parametrize("flags", [0, 1])
-def test_bkt_memory_variables_match_oracle(hb, oracle, flags):
+def test_bkt_memory_variables_match_oracle(hb, oracle, flags, edata):
     """calc_conv + constant_Q_addforce (damping.c:110-416): after a number of steps the four
     memory-variable arrays (psolve.h:308-311) and the displacements agree with the oracle, starting
     from a random state so that every term is exercised; conv arrays round-trip through
     hgpu_store_all / hgpu_fetch_all bit for bit."""
-    g = load_golden("graded2_bkt")
+    g = dict(load_golden("graded2_bkt"))
+    rng = np.random.default_rng(3)
+    if edata == "random":
+        # the reference's run has Qk = infinity (kappa coefficients all zero) and one material:
+        # random coefficients exercise the kappa family and both branches of every test
+        # (damping.c:126, 173, 262, 321); the oracle is pinned on such input against the
+        # reference's own damping.c (tests/test_oracle_pinned.py)
+        ed = np.array(g["elem_edata"], np.float32)
+        ed[:, 4:] = (np.abs(rng.standard_normal((ed.shape[0], 10))) * 0.1).astype(np.float32)
+        ed[::3, 4:9] = 0
+        ed[1::4, 9:] = 0
+        ed[5::7, 7] = 0                  # g0_shear = 0 alone: not advanced, but still damped
+        g["elem_edata"] = ed
     s, P = make_solver(hb, g, flags=flags)
     m = oracle.Mesh.from_dump(g)
     st = oracle.State(m, bkt=True)
-    rng = np.random.default_rng(3)
     st.tm1[:] = 1e-3 * rng.standard_normal(st.tm1.shape)
     st.tm2[:] = 1e-3 * rng.standard_normal(st.tm2.shape)
     st.conv[:] = 1e-4 * rng.standard_normal(st.conv.shape)

@@ -58,3 +58,18 @@ def test_partition_matches_octor(name, world):
             assert np.array_equal(ml.mapping, v[side + "_map"]), (r, side)
         assert np.array_equal(mesh.eTable, v["eTable"])
         assert np.array_equal(mesh.nTable, v["nTable"]), r
+
+
+def test_bkt_coefficients_match_reference_edata():
+    """meshgen.bkt_coefficients restates mesh_correct_properties' BKT block (psolve.c:7239-7310,
+    Search_Quality_Table quake_util.c:128-163, the 18-of-26-row table psolve.c:5575-5616): bit-exact
+    with the edata the unmodified reference produced for its BKT run (use_infinite_qk = yes there)."""
+    import numpy as np
+    from conftest import load_golden
+    from hercules_b200 import meshgen
+    ed = load_golden("graded2_bkt")["elem_edata"]
+    c = meshgen.bkt_coefficients(ed[:, 1], ed[:, 2], use_inf_qk=True)
+    assert np.array_equal(c, ed[:, 4:14])
+    # finite Qk: every element of a stiff layer still finds a table row, soft ones differ
+    c2 = meshgen.bkt_coefficients(np.float32([4000, 6000, 1500]), np.float32([2000, 3464, 500]))
+    assert c2.shape == (3, 10) and (c2[:, :5] > 0).all()
