@@ -77,6 +77,8 @@ SYMBOLS = {
     "hgpu_fetch_nodes": (C.c_int, [_H, i32, C.c_void_p, i32, C.c_void_p]),
     "hgpu_fetch_all": (C.c_int, [_H, i32, C.c_void_p]),
     "hgpu_store_all": (C.c_int, [_H, i32, C.c_void_p]),
+    "hgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "hgpu_host_free": (None, [C.c_void_p]),
     "hgpu_sync": (C.c_int, [_H]),
     "hgpu_get_timers": (C.c_int, [_H, C.POINTER(Timers)]),
     "hgpu_stream": (C.c_void_p, [_H]),

@@ -181,6 +181,7 @@ struct hgpu_solver {
     double phase_s[PH_COUNT] = {0};
     // scratch for fetch
     int32_t *d_fetch_ids = nullptr; double *d_fetch_out = nullptr; int32_t fetch_cap = 0;
+    std::vector<int32_t> fetch_ids_host;     // the list d_fetch_ids holds
 };
 
 template <typename T>
@@ -1110,8 +1111,14 @@ extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *
         if ((rc = dalloc(s, &s->d_fetch_ids, (size_t)n))) return rc;
         if ((rc = dalloc(s, &s->d_fetch_out, 3 * (size_t)n))) return rc;
         s->fetch_cap = n;
+        s->fetch_ids_host.clear();
     }
-    CK(cudaMemcpyAsync(s->d_fetch_ids, lnid, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    // stations and planes ask for the same nodes at every output step (psolve.c:6680, io_planes.c:151):
+    // the list travels only when it changes
+    if ((size_t)n != s->fetch_ids_host.size() || memcmp(s->fetch_ids_host.data(), lnid, (size_t)n * sizeof(int32_t)) != 0) {
+        s->fetch_ids_host.assign(lnid, lnid + n);
+        CK(cudaMemcpyAsync(s->d_fetch_ids, s->fetch_ids_host.data(), (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream));
+    }
     gather_nodes_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(n, s->d_fetch_ids, p, s->d_fetch_out);
     CK(cudaGetLastError());
     s->tm.launches++;
@@ -1119,6 +1126,16 @@ extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *
     CK(cudaStreamSynchronize(s->stream));
     return HGPU_OK;
 }
+
+extern "C" void *hgpu_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { fail(HGPU_ENOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); return nullptr; }
+    return p;
+}
+
+extern "C" void hgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 extern "C" int hgpu_sync(hgpu_solver_t *s)
 {

@@ -652,6 +652,17 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 if (MODE == 3) {
                     // BKT: calc_conv + constant_Q_addforce (damping.c:110-416), elastic term included
                     const size_t entry = (size_t)(eb + base + tid);
+                    {
+                        // the warp's 24 KB of memory variables: start all of it towards L2 now (192
+                        // lines, 6 per lane), the per-pair loads below then find it there or in flight
+                        const int lane = tid & 31;
+#pragma unroll
+                        for (int q = 0; q < 3; q++) {
+                            const double *row = A.conv + conv_index(entry & ~(size_t)31, lane + 32 * q);
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                            asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 16));
+                        }
+                    }
                     const double *cr = A.ent_bkt + 8 * entry;
                     const double c1 = __ldg(cr), c2 = __ldg(cr + 1);
                     const float2 q0 = __ldg(reinterpret_cast<const float2 *>(cr + 2)), q1 = __ldg(reinterpret_cast<const float2 *>(cr + 3));

@@ -230,8 +230,11 @@ class Solver:
     def _rows(self, which: int) -> int:
         return 8 * self.E if CONV_SHEAR_1 <= which <= CONV_KAPPA_2 else self.N
 
-    def fetch_all(self, which: int) -> np.ndarray:
-        out = np.empty((self._rows(which), 3), np.float64)
+    def fetch_all(self, which: int, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self._rows(which), 3), np.float64)
+        elif out.dtype != np.float64 or out.size != 3 * self._rows(which) or not out.flags.c_contiguous:
+            raise ValueError("out must be a contiguous float64 array of the selected array's size")
         _chk(self._L.hgpu_fetch_all(self._h, which, out.ctypes.data))
         return out
 
@@ -241,9 +244,10 @@ class Solver:
             raise ValueError("array must be [nharbored][3] ([8 lenum][3] for a conv array)")
         _chk(self._L.hgpu_store_all(self._h, which, a.ctypes.data))
 
-    def fetch_nodes(self, which: int, lnid) -> np.ndarray:
+    def fetch_nodes(self, which: int, lnid, out: np.ndarray | None = None) -> np.ndarray:
         lnid = np.ascontiguousarray(lnid, np.int32)
-        out = np.empty((lnid.size, 3), np.float64)
+        if out is None:
+            out = np.empty((lnid.size, 3), np.float64)
         _chk(self._L.hgpu_fetch_nodes(self._h, which, lnid.ctypes.data, lnid.size, out.ctypes.data))
         return out
 
@@ -263,6 +267,32 @@ class Solver:
         t = _lib.Layout()
         _chk(self._L.hgpu_get_layout(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in t._fields_}
+
+
+class PinnedArray:
+    """A float64 numpy array over page-locked host memory from hgpu_host_alloc (freed with the
+    object): hand ``.a`` to fetch_all / fetch_nodes / step for full-speed, bounce-free copies."""
+
+    def __init__(self, shape):
+        self._L = _lib.lib()
+        n = int(np.prod(shape))
+        self._p = self._L.hgpu_host_alloc(max(1, 8 * n))
+        if not self._p:
+            raise HerculesGpuError("hgpu_host_alloc failed: " + (self._L.hgpu_last_error() or b"?").decode())
+        buf = (C.c_double * n).from_address(self._p)
+        self.a = np.frombuffer(buf, np.float64, n).reshape(shape)
+
+    def close(self) -> None:
+        if self._p:
+            self.a = None
+            self._L.hgpu_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def plan_build(elem_lnid, nharbored: int, tile_nodes: int = 0, mesh: "HostMesh | None" = None) -> dict:

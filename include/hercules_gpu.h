@@ -193,6 +193,13 @@ int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out);
 /* Restart after checkpoint_read (psolve.c:4249), and test set-up: overwrite a device array. */
 int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in);
 
+/* Page-locked host memory for the buffers handed to hgpu_fetch_all / hgpu_store_all / hgpu_fetch_nodes /
+ * hgpu_force_source (the calloc'ed tm1/tm2 of solver_init, psolve.c:3317-3325, on the host side):
+ * copies to and from it run at full PCIe/C2C speed and without a bounce buffer.  Any host pointer
+ * is accepted by those calls; memory from here is just faster.  NULL on failure. */
+void *hgpu_host_alloc(size_t bytes);
+void hgpu_host_free(void *p);
+
 int hgpu_sync(hgpu_solver_t *s);
 int hgpu_get_timers(hgpu_solver_t *s, hgpu_timers_t *out);
 /* Raw CUDA stream the kernels are launched on (cudaStream_t), for event timing by the caller. */
