@@ -1,0 +1,268 @@
+/*
+ * psolve_gpu.c -- the reference's own psolve with its time loop executed by libhercules_gpu.so.
+ *
+ * This is the binding INTEGRATION.md describes, as a working program.  psolve.c keeps the state
+ * the hot path needs in file-static structs (`Param`, `Global`, quake/forward/psolve.c:193-337),
+ * so the binding has to live in psolve.c's translation unit: this file compiles psolve.c WHERE
+ * IT LIES (#include REF_PSOLVE_C, set by integration/Makefile; no reference text is copied) and
+ * interposes on two external functions psolve.c calls, exactly as oracle/ref_dump.c does:
+ *
+ *   Timer_Start("Solver")   psolve.c:7514, immediately before solver_run(): parameters, octor
+ *                           mesh and partition, solver_init, source_init, stiffness_init and
+ *                           the station/plane set-up are done.  The hook runs the whole time
+ *                           loop on the GPU (gpu_solver_run below, a transcription of the loop
+ *                           body of solver_run, psolve.c:4265-4319, with every hot-path wrapper
+ *                           replaced by its hgpu_* call) and then sets Param.theTotalSteps to
+ *                           the starting step so that the reference's own loop has nothing left
+ *                           to do.
+ *   Timer_Stop("Solver")    psolve.c:7516: restores Param.theTotalSteps for print_timing_stat.
+ *
+ * Everything the reference does outside the loop -- and, inside it, the checkpoint, status,
+ * 4D-output, plane and station writers and read_myForces -- runs unchanged and is CALLED from
+ * here (they are static functions of the same translation unit): the station files of a
+ * psolve_gpu run are produced by the reference's interpolate_station_displacements from
+ * displacements fetched off the GPU.
+ *
+ * Multi-rank: one process per GPU; the four schedule_senddata calls per step become the
+ * library's peer-memory exchange; the mailbox descriptors are all-gathered over comm_solver.
+ */
+#include <stdio.h>
+#include <stdint.h>
+
+#define Timer_Start(name) hgpu_hook_Timer_Start(name)
+#define Timer_Stop(name)  hgpu_hook_Timer_Stop(name)
+
+#include REF_PSOLVE_C
+
+#undef Timer_Start
+#undef Timer_Stop
+
+void Timer_Start(char *name);
+void Timer_Stop(char *name);
+
+#include "hercules_gpu.h"
+
+static hgpu_solver_t *theGpu;
+static int32_t        theSavedTotalSteps = -1;
+
+#define GPU(call)                                                                          \
+    do {                                                                                   \
+        if ((call) != 0) {                                                                 \
+            fprintf(stderr, "psolve_gpu: %s failed: %s\n", #call, hgpu_last_error());      \
+            MPI_Abort(MPI_COMM_WORLD, ERROR);                                              \
+            exit(1);                                                                       \
+        }                                                                                  \
+    } while (0)
+
+/* messenger_t list (psolve.h:235-272) -> flat arrays; list order = the reference's unpack order */
+static void flatten_messengers(messenger_t *first, hgpu_msglist_t *out)
+{
+    int32_t k = 0, t = 0, count = 0, total = 0;
+    for (messenger_t *m = first; m; m = m->next) { count++; total += m->nodecount; }
+    int32_t *peer = malloc(sizeof(int32_t) * (count + 1)), *nodes = malloc(sizeof(int32_t) * (count + 1));
+    int32_t *map = malloc(sizeof(int32_t) * (total + 1));
+    for (messenger_t *m = first; m; m = m->next) {
+        peer[k] = m->procid; nodes[k++] = m->nodecount;
+        for (int32_t i = 0; i < m->nodecount; i++) map[t++] = m->mapping[i];
+    }
+    out->count = count; out->peer = peer; out->nodes = nodes; out->mapping = map;
+}
+
+static void gpu_attach(void)
+{
+    mesh_t *mesh = Global.myMesh;
+    mysolver_t *sv = Global.mySolver;
+    hgpu_mesh_t m;
+    hgpu_params_t p;
+    memset(&m, 0, sizeof m);
+    memset(&p, 0, sizeof p);
+    int32_t *lnid = malloc(sizeof(int32_t) * 8 * (mesh->lenum + 1));
+    float *edata = malloc(sizeof(float) * 14 * (mesh->lenum + 1));
+    int32_t *dn = malloc(sizeof(int32_t) * 6 * (mesh->ldnnum + 1));
+    for (int32_t e = 0; e < mesh->lenum; e++) {                 /* elem_t, octor.h:110-115 */
+        memcpy(lnid + 8 * e, mesh->elemTable[e].lnid, 8 * sizeof(int32_t));
+        memcpy(edata + 14 * e, mesh->elemTable[e].data, 14 * sizeof(float));   /* edata_t, psolve.h:95-97 */
+    }
+    for (int32_t d = 0; d < mesh->ldnnum; d++) {                /* dnode_t, octor.h:153-158 */
+        dnode_t *q = &mesh->dnodeTable[d];
+        int a = 0;
+        dn[6 * d] = q->ldnid; dn[6 * d + 1] = (int32_t)q->deps;
+        for (int32link_t *l = q->lanid; l && a < 4; l = l->next) dn[6 * d + 2 + a++] = l->id;
+        for (; a < 4; a++) dn[6 * d + 2 + a] = -1;
+    }
+    m.lenum = mesh->lenum; m.nharbored = mesh->nharbored; m.ldnnum = mesh->ldnnum;
+    m.elem_lnid = lnid; m.edata = edata; m.dnode = dn;
+    m.eTable = (const double *)sv->eTable;                      /* e_t = 4 doubles, psolve.h:196-198 */
+    m.nTable = (const double *)sv->nTable;                      /* n_t = 7 doubles, psolve.h:210-214 */
+    m.K1 = (const double *)Global.theK1; m.K2 = (const double *)Global.theK2;
+    flatten_messengers(sv->dn_sched->first_c, &m.dn_c); flatten_messengers(sv->dn_sched->first_s, &m.dn_s);
+    flatten_messengers(sv->an_sched->first_c, &m.an_c); flatten_messengers(sv->an_sched->first_s, &m.an_s);
+    p.dt = Param.theDeltaT; p.dt2 = Param.theDeltaTSquared; p.freq = Param.theFreq;
+    p.damping = (int32_t)Param.theTypeOfDamping;                /* same enum values, damping.h:28 */
+    p.stiffness = (int32_t)Param.theStiffness;                  /* stiffness.h:24 */
+    p.print_accel = Param.printStationAccelerations == YES;
+    p.rank = Global.myID; p.nranks = Global.theGroupSize;
+    p.nloaded = Global.theNodesLoaded; p.loaded_lnid = Global.theNodesLoadedList;
+    p.device = -1;
+    p.flags = HGPU_FLAG_TIMERS;
+    GPU(hgpu_init(&theGpu, &m, &p));
+    if (Global.theGroupSize > 1) {
+        /* every rank's mailbox descriptor to every rank (fixed-size slots: MPI_Allgather) */
+        int32_t n = 0, nmax = 0;
+        GPU(hgpu_comm_p2p_export(theGpu, NULL, 0, &n));
+        MPI_Allreduce(&n, &nmax, 1, MPI_INT, MPI_MAX, comm_solver);
+        char *mine = calloc(1, nmax), *all = calloc((size_t)Global.theGroupSize, nmax);
+        int32_t *sizes = malloc(sizeof(int32_t) * Global.theGroupSize);
+        const void **blobs = malloc(sizeof(void *) * Global.theGroupSize);
+        GPU(hgpu_comm_p2p_export(theGpu, mine, nmax, &n));
+        MPI_Allgather(&n, 1, MPI_INT, sizes, 1, MPI_INT, comm_solver);
+        MPI_Allgather(mine, nmax, MPI_CHAR, all, nmax, MPI_CHAR, comm_solver);
+        for (int r = 0; r < Global.theGroupSize; r++) blobs[r] = all + (size_t)r * nmax;
+        GPU(hgpu_comm_p2p_connect(theGpu, blobs, sizes));
+        free(mine); free(all); free(sizes); free(blobs);
+    }
+    free(lnid); free(edata); free(dn);
+}
+
+/* rows of a device array at the stations' nodes -> the same rows of the host array the
+ * reference's writers read (psolve.c:6680-6795) */
+static void fetch_station_rows(int32_t which, fvector_t *host, const int32_t *ids, int32_t n, double *tmp)
+{
+    if (n == 0 || host == NULL) return;
+    GPU(hgpu_fetch_nodes(theGpu, which, ids, n, tmp));
+    for (int32_t i = 0; i < n; i++)
+        for (int c = 0; c < 3; c++) host[ids[i]].f[c] = tmp[3 * i + c];
+}
+
+static void gpu_solver_run(void)
+{
+    int32_t step, startingStep;
+    mysolver_t *sv = Global.mySolver;
+
+    gpu_attach();
+    if (Param.theUseCheckPoint == 1) {                          /* psolve.c:4248-4253 */
+        startingStep = checkpoint_read(Global.myID, Global.myMesh, Param.theCheckPointingDirOut,
+                                       Global.theGroupSize, Global.mySolver, comm_solver);
+        GPU(hgpu_store_all(theGpu, HGPU_TM1, (const double *)sv->tm1));
+        GPU(hgpu_store_all(theGpu, HGPU_TM2, (const double *)sv->tm2));
+        Param.theUseCheckPoint = 0;                             /* solver_run must not read it again */
+    } else {
+        startingStep = 0;
+    }
+    if (Global.myID == 0)
+        monitor_print("gpu_solver_run() start (libhercules_gpu.so)\nStarting time step = %d\n\n", startingStep);
+
+    /* the 8 interpolation nodes of every station of this rank (psolve.c:6697-6701) */
+    int32_t nst = 8 * Param.myNumberOfStations;
+    int32_t *st_ids = malloc(sizeof(int32_t) * (nst + 1));
+    double *st_tmp = malloc(sizeof(double) * 3 * (nst + 1));
+    for (int32_t s = 0; s < Param.myNumberOfStations; s++)
+        for (int k = 0; k < 8; k++) st_ids[8 * s + k] = Param.myStations[s].nodestointerpolate[k];
+    const int vel = (Param.printStationVelocities == YES) || (Param.printStationAccelerations == YES);
+    const int acc = Param.printStationAccelerations == YES;
+
+    MPI_Barrier(comm_solver);
+    for (step = startingStep; step < Param.theTotalSteps; step++) {
+        fvector_t *tmpvector = sv->tm2;                         /* psolve.c:4271-4273 */
+        sv->tm2 = sv->tm1;
+        sv->tm1 = tmpvector;
+        GPU(hgpu_step_begin(theGpu, step));
+
+        /* Solver I/O (psolve.c:4275-4284): the reference's writers read host tm1 (tm2, tm3);
+         * fetch whole fields only on the steps a writer needs them, station rows otherwise */
+        const int ckpt = (Param.theCheckPointingRate != 0) && (step != startingStep) &&
+                         ((step % Param.theCheckPointingRate) == 0);
+        const int wave = DO_OUTPUT && (step % Param.theRate == 0);
+        const int plane = (Param.theNumberOfPlanes != 0) && (step % Param.thePlanePrintRate == 0);
+        const int stat = (Param.theNumberOfStations != 0) && (step % Param.theStationsPrintRate == 0);
+        if (ckpt || wave || plane) {
+            GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
+            if (ckpt || wave) GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
+        } else if (stat) {
+            fetch_station_rows(HGPU_TM1, sv->tm1, st_ids, nst, st_tmp);
+        }
+        if (stat && vel) fetch_station_rows(HGPU_TM2, sv->tm2, st_ids, nst, st_tmp);
+        if (stat && acc) fetch_station_rows(HGPU_TM3, sv->tm3, st_ids, nst, st_tmp);
+        Timer_Start("Solver I/O");
+        solver_write_checkpoint(step, startingStep);
+        solver_update_status(step, startingStep);
+        solver_output_wavefield(step);
+        solver_output_planes(Global.mySolver, Global.myID, step);
+        solver_output_stations(step);
+        solver_read_source_forces(step);                        /* read_myForces, psolve.c:3651 */
+        Timer_Stop("Solver I/O");
+
+        /* Compute Physics / Communication (psolve.c:4286-4316), under the reference's timer names
+         * (solver_run_collect_timers reduces them, psolve.c:4186-4235).  The calls only enqueue
+         * device work, so these host timers hold launch time; the device times are reported from
+         * hgpu_get_timers below. */
+        Timer_Start("Compute Physics");
+        Timer_Start("Compute addforces s");
+        if (Global.theNodesLoaded > 0) GPU(hgpu_force_source(theGpu, (const double *)Global.myForces));
+        Timer_Stop("Compute addforces s");
+        Timer_Start("Compute addforces e");
+        GPU(hgpu_force_stiffness(theGpu));
+        Timer_Stop("Compute addforces e");
+        Timer_Start("Damping addforce");
+        GPU(hgpu_force_damping(theGpu));
+        Timer_Stop("Damping addforce");
+        Timer_Stop("Compute Physics");
+        Timer_Start("Communication");
+        Timer_Start("1st schedule send data (contribution)");
+        GPU(hgpu_force_exchange(theGpu));                       /* phases 8-10 in one call */
+        Timer_Stop("1st schedule send data (contribution)");
+        Timer_Start("1st compute adjust (distribution)"); Timer_Stop("1st compute adjust (distribution)");
+        Timer_Start("2nd schedule send data (contribution)"); Timer_Stop("2nd schedule send data (contribution)");
+        Timer_Stop("Communication");
+        Timer_Start("Compute Physics");
+        Timer_Start("Compute new displacement");
+        GPU(hgpu_update(theGpu));
+        Timer_Stop("Compute new displacement");
+        Timer_Stop("Compute Physics");
+        Timer_Start("Communication");
+        Timer_Start("3rd schedule send data (sharing)");
+        GPU(hgpu_disp_exchange(theGpu));                        /* phases 13-15 in one call */
+        Timer_Stop("3rd schedule send data (sharing)");
+        Timer_Start("2nd compute adjust (assignment)"); Timer_Stop("2nd compute adjust (assignment)");
+        Timer_Start("4th schadule send data (sharing)"); Timer_Stop("4th schadule send data (sharing)");
+        Timer_Stop("Communication");
+    }
+    Timer_Start("Compute Physics");
+    GPU(hgpu_sync(theGpu));                                     /* the device finishes the last steps */
+    Timer_Stop("Compute Physics");
+    /* leave the host arrays as the reference's loop would: tm1 = u(t_last), tm2 = u(t_last + dt) */
+    GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
+    GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
+    {
+        hgpu_timers_t tm;
+        GPU(hgpu_get_timers(theGpu, &tm));
+        if (Global.myID == 0)
+            monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, fused step kernels %.3f s, "
+                          "new displacement %.3f s, exchanges %.3f s (device time)\n",
+                          (long long)tm.steps, (long long)tm.launches, tm.fused_step + tm.addforce_e + tm.damping,
+                          tm.new_disp, tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp);
+    }
+    GPU(hgpu_finalize(theGpu));
+    theGpu = NULL;
+    free(st_ids); free(st_tmp);
+}
+
+void hgpu_hook_Timer_Start(char *name)
+{
+    Timer_Start(name);
+    if (strcmp(name, "Solver") == 0 && theSavedTotalSteps < 0) {
+        gpu_solver_run();
+        /* nothing left for the reference's loop (psolve.c:4265): it starts at step 0 */
+        theSavedTotalSteps = Param.theTotalSteps;
+        Param.theTotalSteps = 0;
+    }
+}
+
+void hgpu_hook_Timer_Stop(char *name)
+{
+    if (strcmp(name, "Solver") == 0 && theSavedTotalSteps >= 0) {
+        Param.theTotalSteps = theSavedTotalSteps;
+        theSavedTotalSteps = -2;
+    }
+    Timer_Stop(name);
+}

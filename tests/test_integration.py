@@ -1,0 +1,99 @@
+"""Drop-in test at the reference's own boundary: integration/_bin/psolve_gpu is the UNMODIFIED
+reference psolve.c (compiled where it lies) whose time loop is executed by libhercules_gpu.so
+(integration/psolve_gpu.c).  The same case is run by the reference's CPU binary
+(oracle/_ref/psolve_ref_O2) and by psolve_gpu; the station files -- written in both runs by the
+reference's own interpolate_station_displacements (psolve.c:6680-6795) -- must agree to the
+precision they are printed with (`% 8e`: 7 significant digits), the way the reference's shipped
+goldens pin examples/simple.
+
+Both binaries are built in the development container (they need /root/reference) and travel to
+the GPU box with the repository snapshot; the tests skip when they are absent.
+"""
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT / "oracle"))
+import refcase  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+GPU_BIN = ROOT / "integration" / "_bin" / "psolve_gpu"
+
+TWO_LAYER = dict(cvm_level=3, cvm_n=(8, 8, 4), vs_min=800, freq_hz=2.5,
+                 layers=[(0, 3000, 1732, 2000), (125, 6000, 3464, 2700)])
+THREE_LAYER = dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5,
+                   layers=[(0, 1800, 866, 1800), (62.5, 3000, 1732, 2000), (250, 6000, 3464, 2700)])
+SRC = dict(src_xyz=(437.5, 562.5, 140.0), src_strike_dip_rake=(30.0, 70.0, 20.0),
+           stations=[(500.0, 500.0, 0.0), (700.0, 300.0, 50.0), (120.0, 880.0, 300.0)])
+
+
+def read_station(path: Path) -> np.ndarray:
+    rows = [list(map(float, ln.split())) for ln in path.read_text().splitlines()
+            if ln.strip() and not ln.lstrip().startswith("#")]
+    return np.array(rows)
+
+
+def run_both(case: refcase.Case, nranks: int):
+    import subprocess, os
+    if not (refcase.have_ref("psolve_ref_O2") and refcase.have_ref("mkcvm") and GPU_BIN.exists()):
+        pytest.skip("reference binaries / integration/_bin/psolve_gpu not built (need /root/reference at build time)")
+    out = {}
+    for which in ("ref", "gpu"):
+        with tempfile.TemporaryDirectory() as td:
+            d = refcase.write_case(case, td)
+            if which == "ref":
+                log = refcase.run("psolve_ref_O2", d, nranks=nranks, timeout=900)
+            else:
+                env = dict(os.environ, HMPI_NP=str(nranks))
+                p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=env, stdout=subprocess.PIPE,
+                                   stderr=subprocess.STDOUT, text=True, timeout=900)
+                assert p.returncode == 0, p.stdout[-4000:]
+                log = p.stdout
+                mon = (d / "out" / "monitor.txt").read_text()
+                assert "gpu_solver_run() done" in mon, mon[-2000:]
+            out[which] = ([read_station(d / "out" / "stations" / f"station.{i}") for i in range(len(case.stations))],
+                          refcase.parse_timing(log))
+    return out
+
+
+def check(out, steps):
+    (ref, tref), (gpu, tgpu) = out["ref"], out["gpu"]
+    assert tref.get("elements") == tgpu.get("elements") and tref.get("steps") == tgpu.get("steps") == steps
+    moved = False
+    for a, b in zip(ref, gpu):
+        assert a.shape == b.shape and a.shape[0] == steps
+        assert np.array_equal(a[:, 0], b[:, 0])                    # time column
+        scale = np.abs(a[:, 1:4]).max()
+        moved |= scale > 0
+        # 7 printed digits: one unit in the last place of either print, plus values that round to ~0
+        assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2.5e-6 * np.abs(a[:, 1:]) + 1e-9 * scale)
+    assert moved
+
+
+@pytest.mark.parametrize("damping,stiffness", [("rayleigh", "effective"), ("rayleigh", "conventional"),
+                                               ("bkt", "effective"), ("none", "effective")])
+def test_reference_main_with_gpu_time_loop(damping, stiffness):
+    """Two-layer model: octor produces two refinement levels with hanging nodes on the interface."""
+    c = refcase.Case(**TWO_LAYER, **SRC, damping=damping, stiffness=stiffness, end_t=0.06)
+    check(run_both(c, 1), c.steps)
+
+
+def test_reference_main_with_gpu_time_loop_accelerations():
+    """print_station_accelerations = yes: the station writer also reads tm2 and tm3 (psolve.c:6738-6775)."""
+    c = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.03, print_accel="yes")
+    check(run_both(c, 1), c.steps)
+
+
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_reference_main_with_gpu_time_loop_multirank(nranks):
+    """octor's partition across mini-MPI ranks, one GPU per rank, halo exchange over peer memory."""
+    import hercules_b200 as hb
+    if hb.lib().hgpu_device_count() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    c = refcase.Case(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1)
+    check(run_both(c, nranks), c.steps)
