@@ -344,6 +344,9 @@ def main() -> None:
     tm1 = s.timers()
     launches = int(tm1["launches"] - tm0["launches"])
     fused_s = tm1["fused_step"] - tm0["fused_step"]
+    # device time of every phase per step (CUDA events, rank 0), under the reference's timer names
+    phases_ms = {k: round(1e3 * (tm1[k] - tm0[k]) / args.steps, 4) for k in tm1
+                 if k not in ("launches", "steps") and tm1[k] != tm0[k]}
     tile_launches = args.steps
     probe = s.fetch_nodes(hb.TM2, st_nodes)
     if not np.isfinite(probe).all():
@@ -417,6 +420,7 @@ def main() -> None:
                                               "tile_halo_total", "n_regular", "n_special", "device_bytes",
                                               "smem_bytes", "block_threads", "grid_ctas", "ctas_per_sm",
                                               "early_tiles")},
+            "phases_ms_per_step": phases_ms,
             "setup_s": {"mesh": round(t_mesh, 1), "hgpu_init": round(t_init, 1)},
         }
         traffic_file = ROOT / "profiles" / "traffic.json"

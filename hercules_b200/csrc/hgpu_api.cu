@@ -581,7 +581,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // CTAs of the same launch
         s->grid = std::max(1, std::min(pl.ntiles, nsm * occ));
         {
-            int reserve = 2;
+            int reserve = 1;
             const char *renv = getenv("HGPU_COMM_SMS");
             if (renv && atoi(renv) >= 0) reserve = atoi(renv);
             s->grid_late = std::max(1, (nsm - reserve) * occ);
@@ -784,6 +784,9 @@ extern "C" int hgpu_force_damping(hgpu_solver_t *s)
 //   sharing     : s-list packs v -> sharers; c-list unpacks with =
 static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool contribution, cudaStream_t st)
 {
+    // blocks per messenger: the force exchange runs beside the late tiles on the one or two SMs
+    // left free for it; the displacement exchange has the whole GPU to itself
+    const int max_gx = (st == s->stream) ? 64 : 8;
     if (s->P.nranks == 1 || (c.total == 0 && sl.total == 0)) return HGPU_OK;
     MsgList &snd = contribution ? c : sl;
     MsgList &rcv = contribution ? sl : c;
@@ -793,14 +796,14 @@ static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool con
         if (nsnd) {
             int maxn = 1;
             for (int32_t n : snd.nodes) maxn = std::max(maxn, n);
-            const int gx = std::max(1, std::min(8, (3 * maxn + 255) / 256));
+            const int gx = std::max(1, std::min(max_gx, (3 * maxn + 255) / 256));
             p2p_push_kernel<<<dim3(gx, nsnd), 256, 0, st>>>(snd.d_push + (so & 1) * nsnd, v, so);
             CK(cudaGetLastError());
             s->tm.launches++;
         }
         if (nrcv && contribution) {
             for (int i = 0; i < nrcv; i++) {
-                const int gx = std::max(1, std::min(8, (3 * rcv.nodes[i] + 255) / 256));
+                const int gx = std::max(1, std::min(max_gx, (3 * rcv.nodes[i] + 255) / 256));
                 p2p_pull_kernel<<<dim3(gx, 1), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv + i, v, si, 1, s->d_p2p_err);
                 CK(cudaGetLastError());
                 s->tm.launches++;
@@ -808,7 +811,7 @@ static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool con
         } else if (nrcv) {
             int maxn = 1;
             for (int32_t n : rcv.nodes) maxn = std::max(maxn, n);
-            const int gx = std::max(1, std::min(8, (3 * maxn + 255) / 256));
+            const int gx = std::max(1, std::min(max_gx, (3 * maxn + 255) / 256));
             p2p_pull_kernel<<<dim3(gx, nrcv), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv, v, si, 0, s->d_p2p_err);
             CK(cudaGetLastError());
             s->tm.launches++;
