@@ -221,6 +221,75 @@ def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayle
             "l2": "inputs larger than L2 (node arrays >= 400 MB each step); no explicit flush"}
 
 
+def run_graded(args) -> None:
+    """--workload graded: configs[2] at reduced size.  The unmodified reference (integration/_bin/
+    psolve_gpu: its own main, octor mesher, solver_init, source and station writers) meshes a
+    three-layer model whose Vs bands give three consecutive octree levels with hanging nodes on
+    both interfaces, and libhercules_gpu.so executes its time loop.  The size is bounded by the
+    reference's single-rank host mesher (~20 us per element), not by the GPU."""
+    import re
+    import subprocess
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import refcase
+    gpu_bin = ROOT / "integration" / "_bin" / "psolve_gpu"
+    if not (gpu_bin.exists() and refcase.have_ref("mkcvm")):
+        raise SystemExit("--workload graded needs integration/_bin/psolve_gpu and oracle/_ref/mkcvm "
+                         "(built where /root/reference exists)")
+    steps = args.steps + args.warmup
+    f = args.graded_freq
+    dt = 0.0025 / f                      # h_min / Vp_max with margin: h = 1000 / 2^ceil(log2(f 8 1000 / 866))
+    c = refcase.Case(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=f,
+                     layers=[(0, 1800, 866, 1800), (62.5, 3000, 1732, 2000), (250, 6000, 3464, 2700)],
+                     src_xyz=(437.5, 562.5, 140.0), src_strike_dip_rake=(30.0, 70.0, 20.0), src_risetime=20 * dt,
+                     stations=[(500.0, 500.0, 0.0), (700.0, 300.0, 50.0), (120.0, 880.0, 300.0)], station_rate=10,
+                     damping="rayleigh", stiffness="effective", dt=dt, end_t=dt * (steps + 0.5))
+    t0 = time.time()
+    with tempfile.TemporaryDirectory() as td:
+        d = refcase.write_case(c, td)
+        p = subprocess.run([str(gpu_bin), "parameters.in"], cwd=d, env=dict(os.environ, HMPI_NP="1"),
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
+        if p.returncode != 0:
+            raise SystemExit("psolve_gpu failed:\n" + p.stdout[-3000:])
+        mon = (d / "out" / "monitor.txt").read_text()
+        st0 = (d / "out" / "stations" / "station.0").read_text().splitlines()
+    wall = time.time() - t0
+    t = refcase.parse_timing(p.stdout)
+    m = re.search(r"gpu_solver_run\(\) done: (\d+) steps, (\d+) kernel launches, loop wall ([0-9.eE+-]+) s; device time: "
+                  r"step kernels ([0-9.eE+-]+) s, new displacement ([0-9.eE+-]+) s, adjust ([0-9.eE+-]+) s, "
+                  r"exchanges ([0-9.eE+-]+) s", mon)
+    if not m or "elements" not in t:
+        raise SystemExit("could not parse psolve_gpu's report:\n" + mon[-2000:])
+    nst, launches = int(m.group(1)), int(m.group(2))
+    loop_s, k_s, nd_s, adj_s = float(m.group(3)), float(m.group(4)), float(m.group(5)), float(m.group(6))
+    E, N = int(t["elements"]), int(t["nodes"])
+    dangling = int(re.search(r"Total dangling nodes:\s*(\d+)", p.stdout).group(1))
+    last = [float(x) for x in st0[-1].split()]
+    if not all(np.isfinite(last)):
+        raise SystemExit("non-finite station values")
+    peak, peak_src = peaks()
+    alg = BYTES_PER_ELEM["rayleigh"] * E + BYTES_PER_NODE * N
+    line = {"metric": METRIC, "value": E * nst / loop_s, "unit": UNIT, "n_gpus": 1, "steps": nst, "warmup": 0,
+            "ms_per_step": 1e3 * loop_s / nst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2] at reduced size: adaptive octree mesh, 3 refinement levels, {E} elements, "
+                                   f"{N} nodes, {dangling} hanging nodes (three-layer model meshed for {f:g} Hz by the "
+                                   "reference's own octor on the host), rayleigh damping, effective stiffness, point "
+                                   "source, 3 stations every 10 steps; the reference's main() with its time loop on "
+                                   "libhercules_gpu.so (integration/psolve_gpu.c)",
+                       "elements_per_gpu": E, "dt": dt,
+                       "l2": "node arrays smaller than L2 at this size: not an HBM-roofline run" if N * 24 < 60e6 else
+                             "inputs larger than L2"},
+            "e2e": {"value": E * nst / loop_s, "unit": UNIT, "h2d_bytes_per_step": 192, "d2h_bytes_per_step": 58,
+                    "what": "value IS end to end here: host source rows in every step, station rows out every 10 steps"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": "step_kernel<1,false,256>", "achieved": alg * nst / k_s / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": alg * nst / k_s / 1e9 / peak, "peak_source": peak_src,
+                         "kernel_ms": 1e3 * k_s / nst, "kernel_share_of_step": k_s / loop_s, "traffic": None},
+            "phases_ms_per_step": {"step_kernels": 1e3 * k_s / nst, "new_disp": 1e3 * nd_s / nst, "adjust": 1e3 * adj_s / nst},
+            "cpu_baseline": None, "setup_s": {"reference_host_code_and_meshing": round(wall - loop_s, 1)}}
+    print(json.dumps(line), flush=True)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -234,6 +303,10 @@ def main() -> None:
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "graded"],
+                    help="uniform = configs[1] (the headline); graded = configs[2] at reduced size through the "
+                         "reference's own main (integration/psolve_gpu)")
+    ap.add_argument("--graded-freq", type=float, default=20.0, help="--workload graded: meshing frequency (Hz)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
     args = ap.parse_args()
@@ -241,6 +314,9 @@ def main() -> None:
         args.warmup = 3
     if args.impl == "reference":
         run_reference_arm(args)
+        return
+    if args.workload == "graded":
+        run_graded(args)
         return
 
     import torch

@@ -162,6 +162,7 @@ static void gpu_solver_run(void)
     const int acc = Param.printStationAccelerations == YES;
 
     MPI_Barrier(comm_solver);
+    const double loop_t0 = MPI_Wtime();
     for (step = startingStep; step < Param.theTotalSteps; step++) {
         fvector_t *tmpvector = sv->tm2;                         /* psolve.c:4271-4273 */
         sv->tm2 = sv->tm1;
@@ -230,6 +231,7 @@ static void gpu_solver_run(void)
     Timer_Start("Compute Physics");
     GPU(hgpu_sync(theGpu));                                     /* the device finishes the last steps */
     Timer_Stop("Compute Physics");
+    const double loop_wall = MPI_Wtime() - loop_t0;
     /* leave the host arrays as the reference's loop would: tm1 = u(t_last), tm2 = u(t_last + dt) */
     GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
     GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
@@ -237,10 +239,11 @@ static void gpu_solver_run(void)
         hgpu_timers_t tm;
         GPU(hgpu_get_timers(theGpu, &tm));
         if (Global.myID == 0)
-            monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, fused step kernels %.3f s, "
-                          "new displacement %.3f s, exchanges %.3f s (device time)\n",
-                          (long long)tm.steps, (long long)tm.launches, tm.fused_step + tm.addforce_e + tm.damping,
-                          tm.new_disp, tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp);
+            monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, loop wall %.6f s; device time: "
+                          "step kernels %.6f s, new displacement %.6f s, adjust %.6f s, exchanges %.6f s\n",
+                          (long long)tm.steps, (long long)tm.launches, loop_wall,
+                          tm.fused_step + tm.addforce_e + tm.damping, tm.new_disp, tm.adjust_force + tm.adjust_disp,
+                          tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp);
     }
     GPU(hgpu_finalize(theGpu));
     theGpu = NULL;

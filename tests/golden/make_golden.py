@@ -49,6 +49,7 @@ CASES = {
     "graded2_none_eff": (dict(**TWO_LAYER, **SRC, damping="none", stiffness="effective", end_t=0.06), 1, 20),
     "graded2_mass_eff": (dict(**TWO_LAYER, **SRC, damping="mass", stiffness="effective", end_t=0.06), 1, 20),
     "graded2_bkt": (dict(**TWO_LAYER, **SRC, damping="bkt", stiffness="effective", end_t=0.06), 1, 20),
+    "graded2_bkt_np2": (dict(**TWO_LAYER, **SRC, damping="bkt", stiffness="effective", end_t=0.06), 2, 20),
     "graded2_accel": (dict(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.03,
                            print_accel="yes"), 1, 10),
     "graded3_rayleigh_eff": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 1, 25),

@@ -55,7 +55,7 @@ def _ngpu():
 
 @pytest.mark.parametrize("flags", [0, 4])          # 4 = HGPU_FLAG_NO_OVERLAP
 @pytest.mark.parametrize("name,world", [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4),
-                                        ("uniform_rayleigh_eff_np3", 3)])
+                                        ("uniform_rayleigh_eff_np3", 3), ("graded2_bkt_np2", 2)])
 def test_nccl_halo_matches_reference_ranks(name, world, flags):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs for NCCL (one rank per device)")
@@ -64,7 +64,7 @@ def test_nccl_halo_matches_reference_ranks(name, world, flags):
 
 @pytest.mark.parametrize("flags", [0, 4])
 @pytest.mark.parametrize("name,world", [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4),
-                                        ("uniform_rayleigh_eff_np3", 3)])
+                                        ("uniform_rayleigh_eff_np3", 3), ("graded2_bkt_np2", 2)])
 def test_p2p_halo_matches_reference_ranks(name, world, flags):
     """Peer-memory transport; ranks are spread over the GPUs present (all on one device on a
     single-GPU box: the mailboxes are then IPC mappings of the same device's memory)."""

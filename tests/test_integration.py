@@ -97,3 +97,33 @@ def test_reference_main_with_gpu_time_loop_multirank(nranks):
         pytest.skip(f"needs {nranks} GPUs")
     c = refcase.Case(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1)
     check(run_both(c, nranks), c.steps)
+
+
+def test_reference_main_with_gpu_time_loop_1p5M_elements():
+    """The same three-layer model meshed for 20 Hz: 1.5 M elements on three octree levels, 62 k
+    hanging nodes.  CPU reference on up to 8 mini-MPI ranks, GPU run on one rank: the station
+    series are partition-independent and must agree to their printed precision."""
+    import os
+    c = refcase.Case(**{**THREE_LAYER, "freq_hz": 20.0}, **SRC, damping="rayleigh", stiffness="effective",
+                     dt=0.000125, end_t=0.000125 * 60.5)
+    if not (refcase.have_ref("psolve_ref_O2") and refcase.have_ref("mkcvm") and GPU_BIN.exists()):
+        pytest.skip("reference binaries / integration/_bin/psolve_gpu not built")
+    import subprocess
+    nref = 1
+    while nref * 2 <= min(8, os.cpu_count() or 1):
+        nref *= 2
+    out = {}
+    for which in ("ref", "gpu"):
+        with tempfile.TemporaryDirectory() as td:
+            d = refcase.write_case(c, td)
+            if which == "ref":
+                log = refcase.run("psolve_ref_O2", d, nranks=nref, timeout=1500)
+            else:
+                p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=dict(os.environ, HMPI_NP="1"),
+                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+                assert p.returncode == 0, p.stdout[-4000:]
+                log = p.stdout
+            out[which] = ([read_station(d / "out" / "stations" / f"station.{i}") for i in range(len(c.stations))],
+                          refcase.parse_timing(log))
+    assert out["gpu"][1]["elements"] == 1507328
+    check(out, c.steps)
