@@ -259,6 +259,7 @@ def run_graded(args) -> None:
                   r"exchanges ([0-9.eE+-]+) s", mon)
     if not m or "elements" not in t:
         raise SystemExit("could not parse psolve_gpu's report:\n" + mon[-2000:])
+    hm = re.search(r"host time: taps ([0-9.eE+-]+) s, reference I/O block ([0-9.eE+-]+) s, hgpu calls ([0-9.eE+-]+) s", mon)
     nst, launches = int(m.group(1)), int(m.group(2))
     loop_s, k_s, nd_s, adj_s = float(m.group(3)), float(m.group(4)), float(m.group(5)), float(m.group(6))
     E, N = int(t["elements"]), int(t["nodes"])
@@ -286,6 +287,8 @@ def run_graded(args) -> None:
                          "unit": "GB/s", "frac": alg * nst / k_s / 1e9 / peak, "peak_source": peak_src,
                          "kernel_ms": 1e3 * k_s / nst, "kernel_share_of_step": k_s / loop_s, "traffic": None},
             "phases_ms_per_step": {"step_kernels": 1e3 * k_s / nst, "new_disp": 1e3 * nd_s / nst, "adjust": 1e3 * adj_s / nst},
+            "host_ms_per_step": ({"station_taps": 1e3 * float(hm.group(1)) / nst, "reference_io_block": 1e3 * float(hm.group(2)) / nst,
+                                  "hgpu_calls": 1e3 * float(hm.group(3)) / nst} if hm else None),
             "cpu_baseline": None, "setup_s": {"reference_host_code_and_meshing": round(wall - loop_s, 1)}}
     print(json.dumps(line), flush=True)
 

@@ -50,6 +50,8 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
     }
 
     // cut points
+    int32_t min_tile = std::min(256, max_owned / 2);
+    { const char *e = getenv("HGPU_MIN_TILE"); if (e && atoi(e) > 0) min_tile = std::min(atoi(e), max_owned); }
     std::vector<int32_t> cuts;
     cuts.push_back(0);
     {
@@ -61,7 +63,12 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
                                     ? nelem[(size_t)noff[(size_t)n + 1] - 1] / caps.elem_block : last_blk;
             last_blk = blk;
             if (n == start) { cur_blk = blk; continue; }
-            if (!(n & 1) && (blk != cur_blk || n - start >= max_owned)) {
+            // At the interface of two octree levels the Z-ordered node list alternates between
+            // nodes whose highest element lies in a block of fine elements and nodes whose highest
+            // element lies in a block of coarse ones: cutting at every change would shred the
+            // interface into tiles of one to three nodes.  A change of block therefore only ends a
+            // tile that has reached a useful size; shorter runs are absorbed into it.
+            if (!(n & 1) && ((blk != cur_blk && n - start >= min_tile) || n - start >= max_owned)) {
                 cuts.push_back(n);
                 start = n;
                 cur_blk = blk;

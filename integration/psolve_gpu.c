@@ -163,11 +163,13 @@ static void gpu_solver_run(void)
 
     MPI_Barrier(comm_solver);
     const double loop_t0 = MPI_Wtime();
+    double host_io = 0, host_tap = 0, host_gpu = 0, tmark;      /* where the host spends the loop */
     for (step = startingStep; step < Param.theTotalSteps; step++) {
         fvector_t *tmpvector = sv->tm2;                         /* psolve.c:4271-4273 */
         sv->tm2 = sv->tm1;
         sv->tm1 = tmpvector;
         GPU(hgpu_step_begin(theGpu, step));
+        tmark = MPI_Wtime();
 
         /* Solver I/O (psolve.c:4275-4284): the reference's writers read host tm1 (tm2, tm3);
          * fetch whole fields only on the steps a writer needs them, station rows otherwise */
@@ -184,6 +186,7 @@ static void gpu_solver_run(void)
         }
         if (stat && vel) fetch_station_rows(HGPU_TM2, sv->tm2, st_ids, nst, st_tmp);
         if (stat && acc) fetch_station_rows(HGPU_TM3, sv->tm3, st_ids, nst, st_tmp);
+        host_tap += MPI_Wtime() - tmark; tmark = MPI_Wtime();
         Timer_Start("Solver I/O");
         solver_write_checkpoint(step, startingStep);
         solver_update_status(step, startingStep);
@@ -192,6 +195,7 @@ static void gpu_solver_run(void)
         solver_output_stations(step);
         solver_read_source_forces(step);                        /* read_myForces, psolve.c:3651 */
         Timer_Stop("Solver I/O");
+        host_io += MPI_Wtime() - tmark; tmark = MPI_Wtime();
 
         /* Compute Physics / Communication (psolve.c:4286-4316), under the reference's timer names
          * (solver_run_collect_timers reduces them, psolve.c:4186-4235).  The calls only enqueue
@@ -227,6 +231,7 @@ static void gpu_solver_run(void)
         Timer_Start("2nd compute adjust (assignment)"); Timer_Stop("2nd compute adjust (assignment)");
         Timer_Start("4th schadule send data (sharing)"); Timer_Stop("4th schadule send data (sharing)");
         Timer_Stop("Communication");
+        host_gpu += MPI_Wtime() - tmark;
     }
     Timer_Start("Compute Physics");
     GPU(hgpu_sync(theGpu));                                     /* the device finishes the last steps */
@@ -239,6 +244,8 @@ static void gpu_solver_run(void)
         hgpu_timers_t tm;
         GPU(hgpu_get_timers(theGpu, &tm));
         if (Global.myID == 0)
+            monitor_print("gpu_solver_run() host time: taps %.6f s, reference I/O block %.6f s, hgpu calls %.6f s\n",
+                          host_tap, host_io, host_gpu);
             monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, loop wall %.6f s; device time: "
                           "step kernels %.6f s, new displacement %.6f s, adjust %.6f s, exchanges %.6f s\n",
                           (long long)tm.steps, (long long)tm.launches, loop_wall,

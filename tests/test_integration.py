@@ -71,7 +71,9 @@ def check(out, steps):
         scale = np.abs(a[:, 1:4]).max()
         moved |= scale > 0
         # 7 printed digits: one unit in the last place of either print, plus values that round to ~0
-        assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2.5e-6 * np.abs(a[:, 1:]) + 1e-9 * scale)
+        # (a station the wave has not reached holds exact zeros in one run and 1e-45-size noise of
+        # flushed products in the other: absolute floor far below anything physical)
+        assert np.all(np.abs(a[:, 1:] - b[:, 1:]) <= 2.5e-6 * np.abs(a[:, 1:]) + 1e-9 * scale + 1e-30)
     assert moved
 
 
@@ -104,8 +106,10 @@ def test_reference_main_with_gpu_time_loop_1p5M_elements():
     hanging nodes.  CPU reference on up to 8 mini-MPI ranks, GPU run on one rank: the station
     series are partition-independent and must agree to their printed precision."""
     import os
-    c = refcase.Case(**{**THREE_LAYER, "freq_hz": 20.0}, **SRC, damping="rayleigh", stiffness="effective",
-                     dt=0.000125, end_t=0.000125 * 60.5)
+    # stations next to the hypocentre: 60 steps of 0.125 ms do not carry the wave far
+    src = dict(SRC, stations=[(437.5, 562.5, 140.0), (441.0, 560.0, 137.0), (430.0, 570.0, 150.0)])
+    c = refcase.Case(**{**THREE_LAYER, "freq_hz": 20.0}, **src, damping="rayleigh", stiffness="effective",
+                     dt=0.000125, end_t=0.000125 * 60.5, src_risetime=0.004)
     if not (refcase.have_ref("psolve_ref_O2") and refcase.have_ref("mkcvm") and GPU_BIN.exists()):
         pytest.skip("reference binaries / integration/_bin/psolve_gpu not built")
     import subprocess
