@@ -246,7 +246,8 @@ def run_graded(args) -> None:
     t0 = time.time()
     with tempfile.TemporaryDirectory() as td:
         d = refcase.write_case(c, td)
-        p = subprocess.run([str(gpu_bin), "parameters.in"], cwd=d, env=dict(os.environ, HMPI_NP="1"),
+        p = subprocess.run([str(gpu_bin), "parameters.in"], cwd=d,
+                           env=dict(os.environ, HMPI_NP="1", PSOLVE_GPU_WARMUP=str(args.warmup)),
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=3000)
         if p.returncode != 0:
             raise SystemExit("psolve_gpu failed:\n" + p.stdout[-3000:])
@@ -269,7 +270,7 @@ def run_graded(args) -> None:
         raise SystemExit("non-finite station values")
     peak, peak_src = peaks()
     alg = BYTES_PER_ELEM["rayleigh"] * E + BYTES_PER_NODE * N
-    line = {"metric": METRIC, "value": E * nst / loop_s, "unit": UNIT, "n_gpus": 1, "steps": nst, "warmup": 0,
+    line = {"metric": METRIC, "value": E * nst / loop_s, "unit": UNIT, "n_gpus": 1, "steps": nst, "warmup": args.warmup,
             "ms_per_step": 1e3 * loop_s / nst, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"configs[2] at reduced size: adaptive octree mesh, 3 refinement levels, {E} elements, "

@@ -162,9 +162,22 @@ static void gpu_solver_run(void)
     const int acc = Param.printStationAccelerations == YES;
 
     MPI_Barrier(comm_solver);
-    const double loop_t0 = MPI_Wtime();
+    double loop_t0 = MPI_Wtime();
     double host_io = 0, host_tap = 0, host_gpu = 0, tmark;      /* where the host spends the loop */
+    /* PSOLVE_GPU_WARMUP=w: the loop clock (and the device timers) restart after w steps, so that the
+     * reported rate excludes one-time costs (CUDA module load, first allocations, file opens) */
+    const int warm = getenv("PSOLVE_GPU_WARMUP") ? atoi(getenv("PSOLVE_GPU_WARMUP")) : 0;
+    hgpu_timers_t tm_warm;
+    memset(&tm_warm, 0, sizeof tm_warm);
+    int32_t timed_from = startingStep;
     for (step = startingStep; step < Param.theTotalSteps; step++) {
+        if (warm > 0 && step == startingStep + warm) {
+            GPU(hgpu_sync(theGpu));
+            GPU(hgpu_get_timers(theGpu, &tm_warm));
+            host_io = host_tap = host_gpu = 0;
+            timed_from = step;
+            loop_t0 = MPI_Wtime();
+        }
         fvector_t *tmpvector = sv->tm2;                         /* psolve.c:4271-4273 */
         sv->tm2 = sv->tm1;
         sv->tm1 = tmpvector;
@@ -248,9 +261,12 @@ static void gpu_solver_run(void)
                           host_tap, host_io, host_gpu);
             monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, loop wall %.6f s; device time: "
                           "step kernels %.6f s, new displacement %.6f s, adjust %.6f s, exchanges %.6f s\n",
-                          (long long)tm.steps, (long long)tm.launches, loop_wall,
-                          tm.fused_step + tm.addforce_e + tm.damping, tm.new_disp, tm.adjust_force + tm.adjust_disp,
-                          tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp);
+                          (long long)(Param.theTotalSteps - timed_from), (long long)(tm.launches - tm_warm.launches), loop_wall,
+                          (tm.fused_step + tm.addforce_e + tm.damping) - (tm_warm.fused_step + tm_warm.addforce_e + tm_warm.damping),
+                          tm.new_disp - tm_warm.new_disp,
+                          (tm.adjust_force + tm.adjust_disp) - (tm_warm.adjust_force + tm_warm.adjust_disp),
+                          (tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp) -
+                          (tm_warm.send_dn_force + tm_warm.send_an_force + tm_warm.send_an_disp + tm_warm.send_dn_disp));
     }
     GPU(hgpu_finalize(theGpu));
     theGpu = NULL;
