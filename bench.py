@@ -76,25 +76,40 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.stop_flag = index, threading.Event()
         self.sm, self.reasons, self.sm_max = [], set(), None
-
-    def run(self):
-        try:
+        self.nv = self.h = None
+        self.lock = threading.Lock()
+        try:                                        # NVML is brought up before the timed region starts
             import pynvml as nv
             nv.nvmlInit()
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
-            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[0].isdigit() else self.index
-            h = nv.nvmlDeviceGetHandleByIndex(idx)
-            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            while not self.stop_flag.is_set():
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
-                    nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            idx = int(vis.split(",")[index]) if vis and vis.split(",")[0].isdigit() else index
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.nv = nv
+        except Exception as e:                      # clocks are evidence, not a reason to fail
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def sample_now(self):
+        """One sample from the calling thread (the bench calls it while the timed steps are in flight)."""
+        nv = self.nv
+        if nv is None:
+            return
+        try:
+            sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(
+                nv, "nvmlDeviceGetCurrentClocksEventReasons") else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            with self.lock:
+                self.sm.append(sm)
                 for bit, name in self.REASONS.items():
                     if r & bit:
                         self.reasons.add(name)
-                time.sleep(0.05)
-        except Exception as e:                      # clocks are evidence, not a reason to fail
+        except Exception as e:
             self.reasons.add(f"nvml_error:{type(e).__name__}")
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            self.sample_now()
+            time.sleep(0.01)
 
     def result(self) -> dict:
         self.stop_flag.set()
@@ -207,7 +222,28 @@ def block_grid(world: int) -> tuple[int, int, int]:
     return bx, by, bz
 
 
-def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh") -> dict:
+def adaptive_bands(n: int):
+    """configs[2]: three octree levels by depth on an n x n h-grid, n h deep: 11/16 of the depth in
+    elements of edge h, 4/16 in 2h, 1/16 in 4h (n = 512: 92.3 M + 4.2 M + 0.13 M = 96.6 M elements)."""
+    return ((n * 11 // 16, 1), (n // 8, 2), (n // 64, 4))
+
+
+def adaptive_layers(n: int):
+    """Vs doubles from band to band, which is what makes octor refine by one level per band."""
+    z1, z2 = (n * 11 // 16) * H_M, (n * 11 // 16 + n // 4) * H_M
+    return ((0.0, 1800.0, 1000.0, 2200.0), (z1, 3600.0, 2000.0, 2500.0), (z2, 6000.0, 3464.0, 2700.0))
+
+
+def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh", info: dict | None = None) -> dict:
+    if info is not None and "bands" in info:
+        return {"workload": f"configs[2]: adaptive octree mesh, 3 refinement levels (element edge {H_M:g}/{2*H_M:g}/{4*H_M:g} m by "
+                            f"depth band, Vs 1000/2000/3464 m/s), {info['E']} elements, {info['N']} nodes, {info['D']} hanging "
+                            f"(dangling) nodes on the two 2:1 interfaces, {damping} damping, effective stiffness, point source, "
+                            "5 stations; mesh tables in octor's layout from meshgen.graded_halfspace (bit-exact with the "
+                            "reference's mesher on tests/golden/graded{2,3}_*.npz)",
+                "elements_per_gpu": info["E"], "global_elements": info["E"], "hanging_nodes": info["D"],
+                "global_grid": [n, n, n], "bands": [list(b) for b in info["bands"]], "dt": DT, "partition": "single rank",
+                "l2": "inputs larger than L2; no explicit flush"}
     bx, by, bz = block_grid(world)
     what = ("rayleigh damping, effective stiffness" if damping == "rayleigh" else
             "BKT damping (variant of configs[1] with configs[4]'s damping model on a soft sedimentary column, "
@@ -297,8 +333,8 @@ def run_graded(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--edge", dest="n", type=int, default=256, help="elements per edge per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -307,9 +343,10 @@ def main() -> None:
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
-    ap.add_argument("--workload", default="uniform", choices=["uniform", "graded"],
-                    help="uniform = configs[1] (the headline); graded = configs[2] at reduced size through the "
-                         "reference's own main (integration/psolve_gpu)")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "adaptive", "graded"],
+                    help="uniform = configs[1] (the headline); adaptive = configs[2]: 3-level octree mesh with hanging "
+                         "nodes, ~100 M elements at --edge 512 (meshgen.graded_halfspace, single GPU); graded = configs[2] "
+                         "at reduced size through the reference's own main and mesher (integration/psolve_gpu)")
     ap.add_argument("--graded-freq", type=float, default=20.0, help="--workload graded: meshing frequency (Hz)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
@@ -352,7 +389,23 @@ def main() -> None:
     t0 = time.time()
     damp = hb.BKT if args.damping == "bkt" else hb.RAYLEIGH
     layers = LAYERS_BKT if args.damping == "bkt" else LAYERS
-    if world == 1:
+    adaptive = args.workload == "adaptive"
+    if adaptive:
+        if world != 1:
+            raise SystemExit("--workload adaptive is a single-GPU workload (configs[2])")
+        if n % 64:
+            raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
+        bands = adaptive_bands(n)
+        try:                                        # the host-side mesh tables peak at ~400 B per element
+            import psutil
+            need = 400 * sum(nl * (n // sz) ** 2 for nl, sz in bands)
+            if psutil.virtual_memory().available < need:
+                raise SystemExit(f"--workload adaptive --edge {n}: needs ~{need >> 30} GiB of host memory for the mesh tables")
+        except ImportError:
+            pass
+        layers = adaptive_layers(n) if args.damping == "rayleigh" else LAYERS_BKT
+        mesh, info = meshgen.graded_halfspace(n, n, bands, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
+    elif world == 1:
         mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
     else:
         mesh, info = meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=H_M, dt=DT, freq=FREQ,
@@ -412,12 +465,13 @@ def main() -> None:
     barrier()
     tm0 = s.timers()
     clk = ClockSampler(local)
-    clk.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clk.start()
     ev0.record(stream)
     s.run(0, args.steps)
     ev1.record(stream)
+    clk.sample_now()                       # the steps are still in flight here
     barrier()
     dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     clocks = clk.result()
@@ -466,7 +520,7 @@ def main() -> None:
 
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.damping == "rayleigh":
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.damping == "rayleigh" and not adaptive:
         try:
             r = reference_sample(100)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -484,7 +538,7 @@ def main() -> None:
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",
-                                      args.damping),
+                                      args.damping, info if adaptive else None),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm",
                          "kernel": ("step_kernel<1,false,256> (stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"

@@ -214,18 +214,21 @@ def bkt_coefficients(Vp, Vs, use_inf_qk: bool = False) -> np.ndarray:
     return out
 
 
-def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs):
-    """Per-element quantities of solver_init (psolve.c:3360-3473) for uniform elements of edge h at
-    global grid coordinates (ex, ey, ez): eTable rows, lumped mass, a, dashpot terms."""
+def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=None):
+    """Per-element quantities of solver_init (psolve.c:3360-3473) for elements whose lowest corner
+    is grid point (ex, ey, ez) of the h-grid and whose edge is size * h (size = 1 when None):
+    eTable rows, lumped mass, a, dashpot terms."""
     f32 = np.float32
     nx, ny, nz = dims
     E = ex.size
-    zc = (ez + 0.5) * h
+    sz = 1 if size is None else np.asarray(size, np.int64)
+    dt, h = np.float64(dt), np.float64(h)      # a Python float would leave dt2 * edge in float32
+    zc = (ez + 0.5 * sz) * h
     Vp, Vs, rho = np.empty(E, f32), np.empty(E, f32), np.empty(E, f32)
     for (zt, vp, vs, r) in layers:
         sel = zc >= zt
         Vp[sel], Vs[sel], rho[sel] = vp, vs, r
-    edge = np.full(E, h, f32)
+    edge = np.full(E, h, f32) if size is None else (sz * h).astype(f32)
     # mu_and_lambda (psolve.c:3236-3272): float products, then double
     mu = (rho * Vs * Vs).astype(np.float64)
     big = Vp > (Vs.astype(np.float64) * thr_vpvs)
@@ -250,7 +253,7 @@ def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_
     M = (rho * edge * edge * edge).astype(np.float64) / 8
     scale = (rho * (edge / f32(2)) * (edge / f32(2))).astype(np.float64)
     # absorbing faces: x near/far, y near/far, z far; the top (z near) is free under HALFSPACE
-    touch = ((ex == 0, ex == nx - 1), (ey == 0, ey == ny - 1), (np.zeros(E, bool), ez == nz - 1))
+    touch = ((ex == 0, ex + sz == nx), (ey == 0, ey + sz == ny), (np.zeros(E, bool), ez + sz == nz))
     boundary = touch[0][0] | touch[0][1] | touch[1][0] | touch[1][1] | touch[2][1]   # flag != 13
     # dashpots only on boundary elements: keep them sparse
     bi = np.nonzero(boundary)[0]
@@ -468,6 +471,120 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
                 elem_xyz=(ex, ey, ez), elem_geid=np.arange(lo, hi, dtype=np.int64), origin=(x0, y0, z0),
                 dims=(nx, ny, nz), h=h, owner=owner, share=share, rank=rank, nranks=world,
                 etotal=Etot)
+    return mesh, info
+
+
+def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float = 1.0,
+                     damping: int = RAYLEIGH, layers=((0.0, 6000.0, 3464.0, 2700.0),),
+                     thr_damping: float = 0.05, thr_vpvs: float = 3.0, exact: bool = False):
+    """Single-rank adaptive (2:1 balanced) octree mesh of a depth-banded half-space, in the layout
+    octor + solver_init produce for it (bit-exact on tests/golden/graded3_rayleigh_eff.npz,
+    tests/test_meshgen.py).  The h-grid has nx x ny points per horizontal plane; bands = ((nlayers,
+    size), ...) from the surface down: nlayers layers of cubic elements of edge size * h, size
+    doubling from one band to the next (what octor's refinement + balancing yield when Vs grows
+    with depth by band).  layers = (ztop, Vp, Vs, rho) by the depth of the element centre.
+
+    * leaves in preorder = Morton order of their lowest corner (octor.c:5362-5374, 5505);
+    * nodes = the distinct leaf corners in Z-order with the far faces pulled in by one tick
+      (octor.c:3034, 5466-5475, 6166);
+    * a node on the plane between two bands that is not a corner of the coarse side is dangling:
+      on a coarse edge it hangs on that edge's 2 end nodes, inside a coarse face on its 4 corners;
+      the anchor list is in descending Z-order (octor pushes at the head, octor.c:5863-5991);
+      dnodeTable is in ascending ldnid;
+    * nTable: element loop of solver_init, then compute_adjust(DISTRIBUTION) over all 7 columns
+      in dnodeTable order (psolve.c:3503-3504, 5936-5978).
+    Returns (HostMesh, info)."""
+    bands = [(int(a), int(b)) for a, b in bands]
+    for (_, s0), (_, s1) in zip(bands[:-1], bands[1:]):
+        if s1 != 2 * s0:
+            raise ValueError("element size must double from one band to the next")
+    smax = bands[-1][1]
+    if nx % smax or ny % smax:
+        raise ValueError("nx, ny must be multiples of the coarsest element size")
+    ztop = [0]
+    for nl, sz in bands:
+        if ztop[-1] % sz:
+            raise ValueError("a band must start on a multiple of its element size")
+        ztop.append(ztop[-1] + nl * sz)
+    nz = ztop[-1]
+    # ---- leaves -----------------------------------------------------------------------------------
+    ex, ey, ez, es = [], [], [], []
+    for (nl, sz), z0 in zip(bands, ztop):
+        gx, gy, gz = np.meshgrid(np.arange(0, nx, sz, dtype=np.int32), np.arange(0, ny, sz, dtype=np.int32),
+                                 np.arange(z0, z0 + nl * sz, sz, dtype=np.int32), indexing="ij")
+        ex.append(gx.ravel()); ey.append(gy.ravel()); ez.append(gz.ravel())
+        es.append(np.full(gx.size, sz, np.int32))
+    ex, ey, ez, es = (np.concatenate(v) for v in (ex, ey, ez, es))
+    o = np.argsort(morton3(ex, ey, ez), kind="stable")
+    ex, ey, ez, es = ex[o].astype(np.int64), ey[o].astype(np.int64), ez[o].astype(np.int64), es[o].astype(np.int64)
+    del o
+    E = ex.size
+    # ---- nodes ------------------------------------------------------------------------------------
+    px, py, pz = [], [], []
+    for k, ((nl, sz), z0) in enumerate(zip(bands, ztop)):
+        first = z0 if k == 0 else z0 + sz                       # a band's top plane belongs to the finer band above
+        gx, gy, gz = np.meshgrid(np.arange(0, nx + 1, sz, dtype=np.int32), np.arange(0, ny + 1, sz, dtype=np.int32),
+                                 np.arange(first, z0 + nl * sz + 1, sz, dtype=np.int32), indexing="ij")
+        px.append(gx.ravel()); py.append(gy.ravel()); pz.append(gz.ravel())
+    px, py, pz = (np.concatenate(v) for v in (px, py, pz))
+
+    def key(g, n):
+        return np.where(g == n, 2 * n - 1, 2 * g)
+    o = np.argsort(morton3(key(px, nx), key(py, ny), key(pz, nz)), kind="stable")
+    px, py, pz = px[o].astype(np.int64), py[o].astype(np.int64), pz[o].astype(np.int64)
+    del o
+    N = px.size
+    nrank = np.full((nx + 1, ny + 1, nz + 1), -1, np.int32)
+    nrank[px, py, pz] = np.arange(N, dtype=np.int32)
+    lnid = np.empty((E, 8), np.int32)
+    for j in range(8):
+        lnid[:, j] = nrank[ex + es * (j & 1), ey + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)]
+    assert lnid.min() >= 0
+    # ---- dangling nodes ---------------------------------------------------------------------------
+    rows = []
+    for (_, sf), (_, sc), zp in zip(bands[:-1], bands[1:], ztop[1:]):
+        gx, gy = np.meshgrid(np.arange(0, nx + 1, sf, dtype=np.int64), np.arange(0, ny + 1, sf, dtype=np.int64),
+                             indexing="ij")
+        gx, gy = gx.ravel(), gy.ravel()
+        ox, oy = (gx % sc) != 0, (gy % sc) != 0
+        sel = ox | oy
+        gx, gy, ox, oy = gx[sel], gy[sel], ox[sel], oy[sel]
+        r = np.full((gx.size, 6), -1, np.int32)
+        r[:, 0] = nrank[gx, gy, zp]
+        r[:, 1] = np.where(ox & oy, 4, 2)
+        xh, xl = np.where(ox, gx + sf, gx), np.where(ox, gx - sf, gx)
+        yh, yl = np.where(oy, gy + sf, gy), np.where(oy, gy - sf, gy)
+        both = ox & oy
+        # 2 anchors: (high, low) along the hanging axis; 4 anchors: (xh,yh) (xl,yh) (xh,yl) (xl,yl)
+        r[:, 2] = nrank[xh, yh, zp]
+        r[:, 3] = np.where(both, nrank[xl, yh, zp], nrank[xl, yl, zp])
+        r[both, 4] = nrank[xh[both], yl[both], zp]
+        r[both, 5] = nrank[xl[both], yl[both], zp]
+        rows.append(r)
+    dnode = np.concatenate(rows) if rows else np.zeros((0, 6), np.int32)
+    dnode = np.ascontiguousarray(dnode[np.argsort(dnode[:, 0], kind="stable")])
+    del nrank
+    # ---- solver tables ----------------------------------------------------------------------------
+    abase, bbase = compute_setab(damping, freq)
+    pr = _elem_props(ex, ey, ez, (nx, ny, nz), h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=es)
+    nT = np.zeros((N, 7))
+    _accumulate(nT, lnid, pr, dt, exact)
+    if dnode.shape[0]:
+        deps = dnode[:, 1].astype(np.int64)
+        d = nT[dnode[:, 0]] / deps[:, None].astype(np.float64)          # darray = myvalue / deps
+        slot = np.arange(4)[None, :] < deps[:, None]
+        tgt = dnode[:, 2:6][slot]                                        # dnodeTable order, list order
+        np.add.at(nT, tgt, np.repeat(d, deps, axis=0))
+    edata = np.zeros((E, 14), np.float32)
+    edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
+    if damping == BKT:
+        edata[:, 4:14] = bkt_coefficients(pr["Vp"], pr["Vs"])
+    K1, K2 = compute_K()
+    empty = MsgList()
+    mesh = HostMesh(lnid, pr["eT"], nT, dnode, edata, K1, K2, empty, MsgList(), MsgList(), MsgList())
+    info = dict(E=E, N=N, D=int(dnode.shape[0]), abase=abase, bbase=bbase, node_xyz=(px, py, pz),
+                node_order=(px * (ny + 1) + py) * (nz + 1) + pz, elem_xyz=(ex, ey, ez), elem_size=es,
+                origin=(0, 0, 0), dims=(nx, ny, nz), h=h, rank=0, nranks=1, etotal=E, bands=bands)
     return mesh, info
 
 

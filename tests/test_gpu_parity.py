@@ -241,3 +241,41 @@ def test_properties_at_scale(hb):
         sol.run(0, 5)
     assert rel_l2(s.fetch_all(hb.TM2), s2.fetch_all(hb.TM2)) < 1e-13
     s.close(); s2.close()
+
+
+def test_adaptive_workload_matches_oracle(hb, oracle):
+    """bench.py --workload adaptive (configs[2]) at 1/512 of its size: a 3-level mesh with 3 936
+    hanging nodes from meshgen.graded_halfspace (itself bit-exact with octor on the goldens,
+    tests/test_meshgen.py), stepped through hgpu_run, against the oracle stepping the same tables;
+    plus the size-independent property the constraint gives: after every step each dangling node
+    holds exactly sum(anchor / deps) in list order (compute_adjust ASSIGNMENT, psolve.c:6006-6024)."""
+    import bench
+    from hercules_b200 import meshgen
+    n = 64
+    mesh, info = meshgen.graded_halfspace(n, n, bench.adaptive_bands(n), h=bench.H_M, dt=bench.DT, freq=bench.FREQ,
+                                          layers=bench.adaptive_layers(n))
+    assert info["D"] == 3 * (n // 2) ** 2 + n + 3 * (n // 4) ** 2 + n // 2   # fine-only points of both planes
+    ce = meshgen.element_index(info, n // 2, n // 2, 20)
+    loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
+    steps = 12
+    rng = np.random.default_rng(4)
+    F = 1e9 * rng.standard_normal((steps, 8, 3))
+    m = oracle.Mesh(mesh.elem_lnid, mesh.eTable, mesh.nTable, mesh.dnode, mesh.edata, mesh.K1, mesh.K2)
+    st = oracle.State(m)
+    u0 = 1e-3 * rng.standard_normal((m.N, 3)); v0 = 1e-3 * rng.standard_normal((m.N, 3))
+    st.tm1[:], st.tm2[:] = u0, v0
+    s = hb.Solver(mesh, dt=bench.DT, damping=hb.RAYLEIGH, stiffness=hb.EFFECTIVE, freq=bench.FREQ, loaded_lnid=loaded)
+    s.store_all(hb.TM1, u0); s.store_all(hb.TM2, v0)
+    s.run(0, steps, F)
+    for k in range(steps):
+        oracle.step(m, st, oracle.RAYLEIGH, oracle.EFFECTIVE, bench.FREQ, bench.DT, loaded, F[k])
+    got = s.fetch_all(hb.TM2)
+    assert rel_l2(got, st.tm2) < REL_TOL_RUN
+    d = mesh.dnode
+    deps = d[:, 1].astype(np.float64)
+    want = np.zeros((d.shape[0], 3))
+    for j in range(4):
+        sel = d[:, 1] > j
+        want[sel] += got[d[sel, 2 + j]] / deps[sel, None]
+    assert np.array_equal(got[d[:, 0]], want)
+    s.close()

@@ -73,3 +73,31 @@ def test_bkt_coefficients_match_reference_edata():
     # finite Qk: every element of a stiff layer still finds a table row, soft ones differ
     c2 = meshgen.bkt_coefficients(np.float32([4000, 6000, 1500]), np.float32([2000, 3464, 500]))
     assert c2.shape == (3, 10) and (c2[:, :5] > 0).all()
+
+
+@pytest.mark.parametrize("name,grid,bands,h,layers", [
+    ("graded3_rayleigh_eff", (32, 32), ((2, 1), (3, 2), (2, 4)), 31.25,
+     [(0, 1800, 866, 1800), (62.5, 3000, 1732, 2000), (250, 6000, 3464, 2700)]),
+    ("graded2_rayleigh_eff", (16, 16), ((2, 1), (3, 2)), 62.5,
+     [(0, 3000, 1732, 2000), (125, 6000, 3464, 2700)]),
+])
+def test_graded_mesh_matches_octor_and_solver_init(name, grid, bands, h, layers):
+    """The adaptive (hanging-node) generator reproduces octor's refined + balanced mesh of a banded
+    half-space bit for bit: leaf order, node numbering, elem_t.lnid, dnodeTable (ids, deps, anchor
+    list order), and solver_init's eTable / nTable after compute_adjust(DISTRIBUTION)."""
+    from hercules_b200 import meshgen
+    g = load_golden(name); P = params_of(g)
+    mesh, info = meshgen.graded_halfspace(*grid, bands, h=h, dt=P["dt"], freq=P["freq"],
+                                          damping=P["damping"], layers=layers, exact=True)
+    assert np.array_equal(mesh.elem_lnid, g["elem_lnid"])
+    assert np.array_equal(mesh.dnode, g["dnode"]) and info["D"] == g["dnode"].shape[0] > 0
+    tick = int(g["node_ticks"][g["node_ticks"] > 0].min())
+    assert np.array_equal(np.stack(info["node_xyz"], 1) * tick, g["node_ticks"])
+    lvl = g["elem_level"].astype(np.int64)
+    assert np.array_equal(info["elem_size"], 2 ** (lvl.max() - lvl))
+    assert np.array_equal(mesh.edata[:, :4], g["elem_edata"][:, :4])
+    assert np.array_equal(mesh.eTable, g["eTable"])
+    assert np.array_equal(mesh.nTable, g["nTable"])
+    fast, _ = meshgen.graded_halfspace(*grid, bands, h=h, dt=P["dt"], freq=P["freq"],
+                                       damping=P["damping"], layers=layers)
+    assert np.allclose(fast.nTable, g["nTable"], rtol=1e-13, atol=0)
