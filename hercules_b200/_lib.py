@@ -77,6 +77,10 @@ SYMBOLS = {
     "hgpu_fetch_nodes": (C.c_int, [_H, i32, C.c_void_p, i32, C.c_void_p]),
     "hgpu_fetch_all": (C.c_int, [_H, i32, C.c_void_p]),
     "hgpu_store_all": (C.c_int, [_H, i32, C.c_void_p]),
+    "hgpu_stations_attach": (C.c_int, [_H, i32, C.c_void_p, C.c_void_p, i32, i32, i32, i32]),
+    "hgpu_stations_record": (C.c_int, [_H, i32]),
+    "hgpu_stations_pending": (C.c_int, [_H]),
+    "hgpu_stations_drain": (C.c_int, [_H, C.c_void_p, C.c_void_p, i32, C.POINTER(i32)]),
     "hgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "hgpu_host_free": (None, [C.c_void_p]),
     "hgpu_sync": (C.c_int, [_H]),

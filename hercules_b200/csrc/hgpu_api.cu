@@ -182,6 +182,10 @@ struct hgpu_solver {
     // scratch for fetch
     int32_t *d_fetch_ids = nullptr; double *d_fetch_out = nullptr; int32_t fetch_cap = 0;
     std::vector<int32_t> fetch_ids_host;     // the list d_fetch_ids holds
+    // stations interpolated on the device (hgpu_stations_*): ring of rows [capacity][nst][9]
+    int32_t st_n = 0, st_vel = 0, st_acc = 0, st_rate = 0, st_cap = 0, st_count = 0;
+    int32_t *d_st_nodes = nullptr; double *d_st_local = nullptr, *d_st_rows = nullptr;
+    std::vector<int32_t> st_steps;           // step of each recorded row
 };
 
 template <typename T>
@@ -618,6 +622,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
     dfree(s->d_anchor_id); dfree(s->d_anchor_off); dfree(s->d_anchor_dn); dfree(s->d_anchor_deps);
     dfree(s->d_fetch_ids); dfree(s->d_fetch_out);
+    dfree(s->d_st_nodes); dfree(s->d_st_local); dfree(s->d_st_rows);
     free_msglist(s->dn_c); free_msglist(s->dn_s); free_msglist(s->an_c); free_msglist(s->an_s);
     for (int i = 0; i < hgpu_solver::SRC_RING; i++) if (s->src_done[i]) cudaEventDestroy(s->src_done[i]);
     for (EvPair &e : s->evpool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
@@ -1015,6 +1020,8 @@ extern "C" int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const d
     for (int32_t k = 0; k < nsteps; k++) {
         int rc;
         if ((rc = hgpu_step_begin(s, step0 + k))) return rc;
+        if (s->st_n > 0 && s->st_rate > 0 && (step0 + k) % s->st_rate == 0)
+            if ((rc = hgpu_stations_record(s, step0 + k))) return rc;       // solver_output_stations, psolve.c:4281
         if (n > 0) {
             PhaseTimer pt(s, PH_ADDFORCE_S);
             source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(
@@ -1127,6 +1134,70 @@ extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *
     s->tm.launches++;
     CK(cudaMemcpyAsync(out, s->d_fetch_out, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
+    return HGPU_OK;
+}
+
+// ---- stations on the device ---------------------------------------------------------
+
+extern "C" int hgpu_stations_attach(hgpu_solver_t *s, int32_t nstations, const int32_t *nodes, const double *localcoords,
+                                    int32_t print_vel, int32_t print_acc, int32_t rate, int32_t capacity)
+{
+    if (!s || nstations < 0 || (nstations > 0 && (!nodes || !localcoords)) || rate < 0 || capacity < 1)
+        return fail(HGPU_EINVAL, "hgpu_stations_attach: bad argument");
+    if (print_acc && !s->P.print_accel)
+        return fail(HGPU_EINVAL, "hgpu_stations_attach: accelerations need hgpu_params_t.print_accel (tm3, psolve.c:4094-4101)");
+    for (int64_t i = 0; i < 8LL * nstations; i++)
+        if (nodes[i] < 0 || nodes[i] >= s->N) return fail(HGPU_EINVAL, "hgpu_stations_attach: node id out of range");
+    CK(cudaSetDevice(s->dev));
+    CK(cudaStreamSynchronize(s->stream));
+    dfree(s->d_st_nodes); dfree(s->d_st_local); dfree(s->d_st_rows);
+    s->d_st_nodes = nullptr; s->d_st_local = nullptr; s->d_st_rows = nullptr;
+    s->st_n = nstations; s->st_vel = print_vel != 0; s->st_acc = print_acc != 0; s->st_rate = rate;
+    s->st_cap = capacity; s->st_count = 0; s->st_steps.clear();
+    if (nstations == 0) return HGPU_OK;
+    int rc;
+    if ((rc = upload(s, &s->d_st_nodes, nodes, 8 * (size_t)nstations))) return rc;
+    if ((rc = upload(s, &s->d_st_local, localcoords, 3 * (size_t)nstations))) return rc;
+    if ((rc = dalloc(s, &s->d_st_rows, 9 * (size_t)nstations * (size_t)capacity))) return rc;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_stations_record(hgpu_solver_t *s, int32_t step)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (s->st_n == 0) return HGPU_OK;
+    if (s->st_count >= s->st_cap)
+        return fail(HGPU_ESTATE, "hgpu_stations_record: the device ring holds %d rows already; call hgpu_stations_drain", s->st_cap);
+    CK(cudaSetDevice(s->dev));
+    station_kernel<<<grid_for(s->st_n, 64), 64, 0, s->stream>>>(
+        s->st_n, s->d_st_nodes, s->d_st_local, s->u[s->i1], s->u[s->i2], s->u[s->i3], s->st_vel, s->st_acc,
+        s->P.dt, s->P.dt2, s->d_st_rows + 9 * (size_t)s->st_n * (size_t)s->st_count);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    s->st_steps.push_back(step);
+    s->st_count++;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_stations_pending(hgpu_solver_t *s)
+{
+    return s ? s->st_count : fail(HGPU_EINVAL, "null solver");
+}
+
+extern "C" int hgpu_stations_drain(hgpu_solver_t *s, double *rows, int32_t *steps, int32_t max_rows, int32_t *nrows)
+{
+    if (!s || !nrows) return fail(HGPU_EINVAL, "hgpu_stations_drain: bad argument");
+    *nrows = 0;
+    if (s->st_count == 0 || s->st_n == 0) { s->st_count = 0; s->st_steps.clear(); return HGPU_OK; }
+    if (!rows || max_rows < s->st_count)
+        return fail(HGPU_EINVAL, "hgpu_stations_drain: %d rows are pending, room for %d", s->st_count, max_rows);
+    CK(cudaSetDevice(s->dev));
+    CK(cudaMemcpyAsync(rows, s->d_st_rows, 9 * (size_t)s->st_n * (size_t)s->st_count * sizeof(double),
+                       cudaMemcpyDeviceToHost, s->stream));
+    CK(cudaStreamSynchronize(s->stream));
+    if (steps) memcpy(steps, s->st_steps.data(), (size_t)s->st_count * sizeof(int32_t));
+    *nrows = s->st_count;
+    s->st_count = 0; s->st_steps.clear();
     return HGPU_OK;
 }
 

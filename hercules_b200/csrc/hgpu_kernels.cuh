@@ -1016,4 +1016,54 @@ __global__ void gather_nodes_kernel(int n, const int32_t *__restrict__ lnid, con
     if (k < 3 * n) out[k] = v[3 * (size_t)lnid[k / 3] + (k % 3)];
 }
 
+// interpolate_station_displacements (psolve.c:6680-6795) for every station of this rank, one thread
+// per station: trilinear shape functions phi_i = (1 + xi_i lx)(1 + eta_i ly)(1 + zeta_i lz) / 8 of the
+// station's local coordinates, applied to tm1 (displacement), then -tm2 (velocity = (u1 - u2) / dt),
+// then -tm2 + tm3 (acceleration = (u1 - 2 u2 + u3) / dt2).  Explicit round-to-nearest multiplies and
+// adds in the reference's order (no FMA contraction), so that a row equals the reference's doubles
+// bit for bit when the displacement field does.  row = [nst][9]: dis, vel, acc (unused = 0).
+__global__ void station_kernel(int nst, const int32_t *__restrict__ nodes, const double *__restrict__ local,
+                               const double *__restrict__ tm1, const double *__restrict__ tm2,
+                               const double *__restrict__ tm3, int vel, int acc, double dt, double dt2,
+                               double *__restrict__ row)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nst) return;
+    const double lx = local[3 * s], ly = local[3 * s + 1], lz = local[3 * s + 2];
+    double phi[8];
+    size_t nd[8];
+    double d[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double sx = (i & 1) ? 1.0 : -1.0, sy = (i & 2) ? 1.0 : -1.0, sz = (i & 4) ? 1.0 : -1.0;
+        phi[i] = __dmul_rn(__dmul_rn(__dadd_rn(1.0, __dmul_rn(sx, lx)), __dadd_rn(1.0, __dmul_rn(sy, ly))),
+                           __dadd_rn(1.0, __dmul_rn(sz, lz))) * 0.125;      // / 8 is exact
+        nd[i] = 3 * (size_t)nodes[8 * s + i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) d[c] = __dadd_rn(d[c], __dmul_rn(phi[i], tm1[nd[i] + c]));
+    }
+    double *o = row + 9 * (size_t)s;
+#pragma unroll
+    for (int c = 0; c < 9; c++) o[c] = c < 3 ? d[c] : 0.0;
+    if (vel || acc) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) d[c] = __dsub_rn(d[c], __dmul_rn(phi[i], tm2[nd[i] + c]));
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[3 + c] = __ddiv_rn(d[c], dt);
+    }
+    if (acc) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                d[c] = __dsub_rn(d[c], __dmul_rn(phi[i], tm2[nd[i] + c]));
+                d[c] = __dadd_rn(d[c], __dmul_rn(phi[i], tm3[nd[i] + c]));
+            }
+#pragma unroll
+        for (int c = 0; c < 3; c++) o[6 + c] = __ddiv_rn(d[c], dt2);
+    }
+}
+
 }  // namespace hgpu

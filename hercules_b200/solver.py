@@ -251,6 +251,36 @@ class Solver:
         _chk(self._L.hgpu_fetch_nodes(self._h, which, lnid.ctypes.data, lnid.size, out.ctypes.data))
         return out
 
+    # -- stations on the device (interpolate_station_displacements, psolve.c:6680-6795) ---------------
+    def stations_attach(self, nodes, localcoords, vel: bool = False, acc: bool = False, rate: int = 0,
+                        capacity: int = 1024) -> None:
+        nodes = np.ascontiguousarray(nodes, np.int32).reshape(-1, 8)
+        loc = np.ascontiguousarray(localcoords, np.float64).reshape(-1, 3)
+        if nodes.shape[0] != loc.shape[0]:
+            raise ValueError("nodes [n][8] and localcoords [n][3] disagree on the station count")
+        self._nst, self._st_cap = nodes.shape[0], capacity
+        _chk(self._L.hgpu_stations_attach(self._h, self._nst, nodes.ctypes.data, loc.ctypes.data, int(vel), int(acc),
+                                          rate, capacity))
+
+    def stations_record(self, step: int) -> None:
+        _chk(self._L.hgpu_stations_record(self._h, step))
+
+    def stations_pending(self) -> int:
+        n = self._L.hgpu_stations_pending(self._h)
+        if n < 0:
+            _chk(n)
+        return n
+
+    def stations_drain(self, out: np.ndarray | None = None):
+        """(steps [r], rows [r][nstations][9] = dis, vel, acc) recorded since the last drain."""
+        cap = self._st_cap
+        if out is None:
+            out = np.empty((cap, self._nst, 9), np.float64)
+        steps = np.empty(cap, np.int32)
+        n = C.c_int32()
+        _chk(self._L.hgpu_stations_drain(self._h, out.ctypes.data, steps.ctypes.data, cap, C.byref(n)))
+        return steps[:n.value].copy(), out[:n.value]
+
     def sync(self) -> None:
         _chk(self._L.hgpu_sync(self._h))
 

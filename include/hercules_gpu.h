@@ -193,6 +193,29 @@ int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out);
 /* Restart after checkpoint_read (psolve.c:4249), and test set-up: overwrite a device array. */
 int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in);
 
+/* ---- stations on the device ------------------------------------------------
+ * interpolate_station_displacements (psolve.c:6680-6795) evaluated by a kernel, so that a station
+ * step neither drains the device pipeline nor moves 8 nodes per station to the host: the rows
+ * are collected in a device ring and read back many steps at a time.  The reference's writer keeps
+ * the "station.N" text format (psolve.c:6733-6776); INTEGRATION.md shows the loop.
+ *
+ * attach: nodes = station_t.nodestointerpolate [nstations][8], localcoords = station_t.localcoords
+ *   [nstations][3] (psolve.c:6597-6660); print_vel / print_acc = Param.printStationVelocities /
+ *   Accelerations (acc needs hgpu_params_t.print_accel); rate = Param.theStationsPrintRate: hgpu_run
+ *   then records by itself on every step with step % rate == 0 (0 = explicit hgpu_stations_record
+ *   calls only); capacity = rows the ring holds between two drains.
+ * record: at the point of the step where solver_output_stations runs (psolve.c:4281, after the
+ *   swap): row = for every station dis[3], vel[3] = (u1-u2)/dt, acc[3] = (u1-2 u2+u3)/dt2, computed
+ *   with the reference's operation order, unfused -- bit-equal to the reference's doubles for equal
+ *   fields.  Asynchronous.  HGPU_ESTATE when the ring is full.
+ * drain: waits for the recorded rows and copies them out: rows[r][station][9], steps[r] (may be
+ *   NULL); max_rows must cover hgpu_stations_pending(). */
+int hgpu_stations_attach(hgpu_solver_t *s, int32_t nstations, const int32_t *nodes, const double *localcoords,
+                         int32_t print_vel, int32_t print_acc, int32_t rate, int32_t capacity);
+int hgpu_stations_record(hgpu_solver_t *s, int32_t step);
+int hgpu_stations_pending(hgpu_solver_t *s);
+int hgpu_stations_drain(hgpu_solver_t *s, double *rows, int32_t *steps, int32_t max_rows, int32_t *nrows);
+
 /* Page-locked host memory for the buffers handed to hgpu_fetch_all / hgpu_store_all / hgpu_fetch_nodes /
  * hgpu_force_source (the calloc'ed tm1/tm2 of solver_init, psolve.c:3317-3325, on the host side):
  * copies to and from it run at full PCIe/C2C speed and without a bounce buffer.  Any host pointer

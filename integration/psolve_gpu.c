@@ -134,6 +134,22 @@ static void fetch_station_rows(int32_t which, fvector_t *host, const int32_t *id
         for (int c = 0; c < 3; c++) host[ids[i]].f[c] = tmp[3 * i + c];
 }
 
+/* Station rows interpolated on the device (hgpu_stations_*) -> the reference's "station.N" text:
+ * the row layout of interpolate_station_displacements (psolve.c:6729-6786): time, displacement,
+ * then velocity and acceleration when asked for. */
+static void write_station_rows(const double *rows, const int32_t *steps, int32_t nrows, int vel, int acc)
+{
+    const int32_t nst = Param.myNumberOfStations;
+    for (int32_t r = 0; r < nrows; r++)
+        for (int32_t i = 0; i < nst; i++) {
+            const double *q = rows + 9 * ((size_t)r * nst + i);
+            FILE *fp = Param.myStations[i].fpoutputfile;
+            fprintf(fp, "\n%10.6f % 8e % 8e % 8e", Param.theDeltaT * steps[r], q[0], q[1], q[2]);
+            if (vel) fprintf(fp, " % 8e % 8e % 8e", q[3], q[4], q[5]);
+            if (acc) fprintf(fp, " % 8e % 8e % 8e", q[6], q[7], q[8]);
+        }
+}
+
 static void gpu_solver_run(void)
 {
     int32_t step, startingStep;
@@ -160,6 +176,25 @@ static void gpu_solver_run(void)
         for (int k = 0; k < 8; k++) st_ids[8 * s + k] = Param.myStations[s].nodestointerpolate[k];
     const int vel = (Param.printStationVelocities == YES) || (Param.printStationAccelerations == YES);
     const int acc = Param.printStationAccelerations == YES;
+    /* Stations on the device (default): the interpolation runs as a kernel at the station steps and
+     * the rows come back ST_RING steps at a time, so a station step no longer drains the device
+     * pipeline.  PSOLVE_GPU_HOST_STATIONS=1 keeps the reference's interpolate_station_displacements
+     * on displacements fetched off the GPU (the two produce identical files, tests/test_integration.py). */
+    enum { ST_RING = 256 };
+    const int dev_stations = Param.myNumberOfStations > 0 && !(getenv("PSOLVE_GPU_HOST_STATIONS") &&
+                                                              atoi(getenv("PSOLVE_GPU_HOST_STATIONS")));
+    double *st_rows = NULL;
+    int32_t *st_steps = NULL;
+    if (dev_stations) {
+        double *loc = malloc(sizeof(double) * 3 * Param.myNumberOfStations);
+        for (int32_t s = 0; s < Param.myNumberOfStations; s++)
+            for (int c = 0; c < 3; c++) loc[3 * s + c] = Param.myStations[s].localcoords.x[c];
+        GPU(hgpu_stations_attach(theGpu, Param.myNumberOfStations, st_ids, loc, vel, acc, 0, ST_RING));
+        free(loc);
+        st_rows = hgpu_host_alloc(sizeof(double) * 9 * (size_t)Param.myNumberOfStations * ST_RING);
+        st_steps = malloc(sizeof(int32_t) * ST_RING);
+    }
+    const int32_t saved_nstations = Param.theNumberOfStations;
 
     MPI_Barrier(comm_solver);
     double loop_t0 = MPI_Wtime();
@@ -194,18 +229,29 @@ static void gpu_solver_run(void)
         if (ckpt || wave || plane) {
             GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
             if (ckpt || wave) GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
-        } else if (stat) {
+        } else if (stat && !dev_stations) {
             fetch_station_rows(HGPU_TM1, sv->tm1, st_ids, nst, st_tmp);
         }
-        if (stat && vel) fetch_station_rows(HGPU_TM2, sv->tm2, st_ids, nst, st_tmp);
-        if (stat && acc) fetch_station_rows(HGPU_TM3, sv->tm3, st_ids, nst, st_tmp);
+        if (stat && dev_stations) {
+            if (hgpu_stations_pending(theGpu) == ST_RING) {
+                int32_t nr = 0;
+                GPU(hgpu_stations_drain(theGpu, st_rows, st_steps, ST_RING, &nr));
+                write_station_rows(st_rows, st_steps, nr, vel, acc);
+            }
+            GPU(hgpu_stations_record(theGpu, step));
+        } else {
+            if (stat && vel) fetch_station_rows(HGPU_TM2, sv->tm2, st_ids, nst, st_tmp);
+            if (stat && acc) fetch_station_rows(HGPU_TM3, sv->tm3, st_ids, nst, st_tmp);
+        }
         host_tap += MPI_Wtime() - tmark; tmark = MPI_Wtime();
         Timer_Start("Solver I/O");
         solver_write_checkpoint(step, startingStep);
         solver_update_status(step, startingStep);
         solver_output_wavefield(step);
         solver_output_planes(Global.mySolver, Global.myID, step);
+        if (dev_stations) Param.theNumberOfStations = 0;       /* rows are written by write_station_rows */
         solver_output_stations(step);
+        Param.theNumberOfStations = saved_nstations;
         solver_read_source_forces(step);                        /* read_myForces, psolve.c:3651 */
         Timer_Stop("Solver I/O");
         host_io += MPI_Wtime() - tmark; tmark = MPI_Wtime();
@@ -249,6 +295,11 @@ static void gpu_solver_run(void)
     Timer_Start("Compute Physics");
     GPU(hgpu_sync(theGpu));                                     /* the device finishes the last steps */
     Timer_Stop("Compute Physics");
+    if (dev_stations) {
+        int32_t nr = 0;
+        GPU(hgpu_stations_drain(theGpu, st_rows, st_steps, ST_RING, &nr));
+        write_station_rows(st_rows, st_steps, nr, vel, acc);
+    }
     const double loop_wall = MPI_Wtime() - loop_t0;
     /* leave the host arrays as the reference's loop would: tm1 = u(t_last), tm2 = u(t_last + dt) */
     GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
@@ -270,7 +321,8 @@ static void gpu_solver_run(void)
     }
     GPU(hgpu_finalize(theGpu));
     theGpu = NULL;
-    free(st_ids); free(st_tmp);
+    free(st_ids); free(st_tmp); free(st_steps);
+    hgpu_host_free(st_rows);
 }
 
 void hgpu_hook_Timer_Start(char *name)

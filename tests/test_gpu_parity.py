@@ -279,3 +279,79 @@ def test_adaptive_workload_matches_oracle(hb, oracle):
         want[sel] += got[d[sel, 2 + j]] / deps[sel, None]
     assert np.array_equal(got[d[:, 0]], want)
     s.close()
+
+
+def _station_rows_numpy(loc, nodes, t1, t2, t3, dt, dt2, vel, acc):
+    """interpolate_station_displacements (psolve.c:6680-6795) in numpy, operation for operation
+    (numpy never contracts a*b+c), as the checker of the device rows."""
+    nst = nodes.shape[0]
+    xi = np.array([[-1, 1, -1, 1, -1, 1, -1, 1], [-1, -1, 1, 1, -1, -1, 1, 1], [-1, -1, -1, -1, 1, 1, 1, 1]], float)
+    rows = np.zeros((nst, 9))
+    phi = np.empty((nst, 8))
+    d = np.zeros((nst, 3))
+    for i in range(8):
+        phi[:, i] = (1 + xi[0, i] * loc[:, 0]) * (1 + xi[1, i] * loc[:, 1]) * (1 + xi[2, i] * loc[:, 2]) / 8
+        d = d + phi[:, i:i + 1] * t1[nodes[:, i]]
+    rows[:, 0:3] = d
+    if vel or acc:
+        for i in range(8):
+            d = d - phi[:, i:i + 1] * t2[nodes[:, i]]
+        rows[:, 3:6] = d / dt
+    if acc:
+        for i in range(8):
+            d = d - phi[:, i:i + 1] * t2[nodes[:, i]]
+            d = d + phi[:, i:i + 1] * t3[nodes[:, i]]
+        rows[:, 6:9] = d / dt2
+    return rows
+
+
+@pytest.mark.parametrize("acc", [False, True])
+def test_device_stations_bit_exact(hb, acc):
+    """hgpu_stations_record == the reference's interpolation arithmetic on the same fields, bit for
+    bit (displacement, velocity, acceleration columns); hgpu_run records at the station cadence; the
+    ring reports overflow instead of dropping rows; drained displacement rows reproduce the
+    reference's printed station files."""
+    g = load_golden("graded2_accel" if acc else "graded2_rayleigh_eff")
+    P = params_of(g)
+    s = hb.Solver(hb.HostMesh.from_dump(g), dt=P["dt"], dt2=P["dt2"], damping=P["damping"], stiffness=P["stiffness"],
+                  freq=P["freq"], loaded_lnid=g["loaded_lnid"], print_accel=acc)
+    nodes, loc = g["station_nodes"][:, 1:], g["station_local"]
+    ids = list(g["station_nodes"][:, 0])
+    rng = np.random.default_rng(9)
+    # random stations on top of the case's own: arbitrary elements, arbitrary local coordinates
+    extra = rng.integers(0, g["elem_lnid"].shape[0], 200)
+    nodes = np.concatenate([nodes, g["elem_lnid"][extra]]).astype(np.int32)
+    loc = np.concatenate([loc, rng.uniform(-1, 1, (200, 3))])
+    rate, n = 3, P["steps"]
+    s.stations_attach(nodes, loc, vel=True, acc=acc, rate=rate, capacity=n)
+    s.run(0, n, g["forces"])
+    steps, rows = s.stations_drain()
+    assert list(steps) == list(range(0, n, rate)) and rows.shape == (len(steps), nodes.shape[0], 9)
+    # replay step by step and check every recorded row against the numpy restatement on fetched fields
+    b = hb.Solver(hb.HostMesh.from_dump(g), dt=P["dt"], dt2=P["dt2"], damping=P["damping"], stiffness=P["stiffness"],
+                  freq=P["freq"], loaded_lnid=g["loaded_lnid"], print_accel=acc)
+    b.stations_attach(nodes, loc, vel=True, acc=acc, rate=0, capacity=2)
+    r = 0
+    for k in range(n):
+        b.step_begin(k)
+        if k % rate == 0:
+            t1, t2, t3 = b.fetch_all(hb.TM1), b.fetch_all(hb.TM2), b.fetch_all(hb.TM3)
+            want = _station_rows_numpy(loc, nodes, t1, t2, t3, P["dt"], P["dt2"], True, acc)
+            assert np.array_equal(rows[r], want), k
+            b.stations_record(k)
+            _, one = b.stations_drain()
+            assert np.array_equal(one[0], want)
+            # the reference's own printed rows (7 digits) for the case's stations
+            for i in range(3):
+                ref = g[f"station{i}"][k, 1:4]
+                assert np.all(np.abs(want[ids.index(i), :3] - ref) <= 6e-7 * np.abs(ref) + 1e-30)
+            r += 1
+        b.compute_force_source(g["forces"][k]); b.compute_force_stiffness(); b.compute_force_damping()
+        b.send_force_and_adjust(); b.compute_displacement(); b.send_displacement_and_adjust()
+    assert np.abs(rows[:, :, :3]).max() > 0
+    # overflow is an error, not a silent drop
+    b.stations_record(0); b.stations_record(1)
+    with pytest.raises(hb.HerculesGpuError, match="drain"):
+        b.stations_record(2)
+    assert b.stations_pending() == 2
+    s.close(); b.close()

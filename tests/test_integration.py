@@ -131,3 +131,24 @@ def test_reference_main_with_gpu_time_loop_1p5M_elements():
                           refcase.parse_timing(log))
     assert out["gpu"][1]["elements"] == 1507328
     check(out, c.steps)
+
+
+def test_device_stations_write_the_same_files():
+    """psolve_gpu with the station interpolation on the device (default) and with the reference's
+    interpolate_station_displacements on fetched displacements (PSOLVE_GPU_HOST_STATIONS=1) write
+    byte-identical station files, velocities and accelerations included."""
+    import os, subprocess
+    if not (refcase.have_ref("mkcvm") and GPU_BIN.exists()):
+        pytest.skip("integration/_bin/psolve_gpu not built")
+    c = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.05, print_accel="yes",
+                     station_rate=3)
+    files = {}
+    for host in ("0", "1"):
+        with tempfile.TemporaryDirectory() as td:
+            d = refcase.write_case(c, td)
+            p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                               text=True, timeout=900, env=dict(os.environ, HMPI_NP="1", PSOLVE_GPU_HOST_STATIONS=host))
+            assert p.returncode == 0, p.stdout[-4000:]
+            files[host] = [(d / "out" / "stations" / f"station.{i}").read_bytes() for i in range(len(c.stations))]
+    assert files["0"] == files["1"]
+    assert all(len(f.splitlines()) > 10 for f in files["0"])
