@@ -340,6 +340,9 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after all tiles, one stream")
+    ap.add_argument("--tail-overlap", action="store_true",
+                    help="multi-GPU, opt-in: shared-node update + displacement exchange beside the late tiles "
+                         "(HGPU_FLAG_TAIL_OVERLAP)")
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
@@ -432,7 +435,8 @@ def main() -> None:
     t0 = time.time()
     s = hb.Solver(mesh, dt=DT, damping=damp, stiffness=hb.EFFECTIVE, freq=FREQ,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
-                  tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0))
+                  tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0) |
+                  (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0))
     if world > 1:
         if args.halo == "nccl":
             uid = [hb.Solver.comm_unique_id() if rank == 0 else None]

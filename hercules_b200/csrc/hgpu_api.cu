@@ -153,6 +153,10 @@ struct hgpu_solver {
         cap_recs = 0, cap_srcs = 0, ctas_per_sm = 0;
     // special-node path
     int32_t nS = 0; int32_t *d_slist = nullptr;
+    // the first nS_early entries of d_slist are owned by self tiles: their forces are final once the
+    // early tiles and the force exchange are done, so their update and the displacement exchange can
+    // run on the communication stream while the late tiles are evaluated (tail_done: they did)
+    int32_t nS_early = 0; bool tail_done = false;
     int32_t *d_loaded = nullptr; double *d_F = nullptr; double *h_F = nullptr;
     // per-step source staging: SRC_RING pinned + device slots so hgpu_force_source never has to
     // wait for the previous step (slot k is reusable once its own copy has completed)
@@ -426,6 +430,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRYCU(cudaEventCreateWithFlags(&s->src_done[i], cudaEventDisableTiming));
 
     std::vector<uint8_t> early_node((size_t)N, 0);   // nodes the exchange / hanging-node phases touch
+    std::vector<int32_t> slist;                      // SPECIAL nodes
     // ---- node classes -----------------------------------------------------------------------------
     // A node is advanced inside the fused step kernel unless something else must see or change its
     // force first (source assignment, hanging-node transfer, halo exchange), or unless its
@@ -458,12 +463,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             nt3[3 * (size_t)n + 1] = np[1];
             nt3[3 * (size_t)n + 2] = np[4];
         }
-        std::vector<int32_t> slist;
         for (int32_t n = 0; n < N; n++) if (cls[n] == NODE_SPECIAL) slist.push_back(n);
         s->nS = (int32_t)slist.size();
         s->n_special = s->nS; s->n_regular = (int64_t)N - s->nS;
         TRY(upload(s, &s->nt3, nt3.data(), n3));
-        if (!(params->flags & HGPU_FLAG_NO_FUSE)) TRY(upload(s, &s->d_slist, slist.data(), slist.size()));
     }
 
     // ---- tiles ------------------------------------------------------------------------------------
@@ -503,6 +506,18 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             for (int32_t t = 0; t < pl.ntiles; t++) if (pl.tile_self[t]) order.push_back(t);
             s->n_early = s->n_self = (int32_t)order.size();
             for (int32_t t = 0; t < pl.ntiles; t++) if (!pl.tile_self[t]) order.push_back(t);
+            // SPECIAL nodes owned by self tiles first (ascending within each part)
+            if (fused) {
+                std::vector<int32_t> early_part, late_part;
+                int32_t t = 0;
+                for (int32_t n : slist) {
+                    while (t + 1 < pl.ntiles && pl.node_off[(size_t)t + 1] <= n) t++;
+                    (pl.ntiles > 0 && pl.tile_self[t] ? early_part : late_part).push_back(n);
+                }
+                s->nS_early = (int32_t)early_part.size();
+                early_part.insert(early_part.end(), late_part.begin(), late_part.end());
+                TRY(upload(s, &s->d_slist, early_part.data(), early_part.size()));
+            }
             std::vector<int32_t> meta((size_t)META_INTS * (size_t)pl.ntiles, 0);
             for (int32_t i = 0; i < pl.ntiles; i++) {
                 const int32_t t = order[i];
@@ -725,6 +740,7 @@ extern "C" int hgpu_step_begin(hgpu_solver_t *s, int32_t step)
     if (s->fstate == F_PENDING || s->fstate == F_FUSED_DONE)
         return fail(HGPU_ESTATE, "hgpu_step_begin: previous step's forces were never consumed by hgpu_update");
     std::swap(s->i1, s->i2);   // psolve.c:4271-4273
+    s->tail_done = false;
     return HGPU_OK;
 }
 
@@ -876,6 +892,28 @@ static int force_phases(hgpu_solver *s, cudaStream_t st)
     return HGPU_OK;
 }
 
+// phases 13-15 on stream st; tm2 = the array holding the new displacements
+static int disp_phases(hgpu_solver *s, double *tm2, cudaStream_t st)
+{
+    int rc;
+    // phase 13: owners publish anchored-node displacements
+    {
+        PhaseTimer pt(s, PH_SEND_AN_DISP, st);
+        if ((rc = exchange(s, s->an_c, s->an_s, tm2, false, st))) return rc;
+    }
+    // phase 14: dangling nodes interpolate from their anchors
+    if (s->D > 0) {
+        PhaseTimer pt(s, PH_ADJUST_DISP, st);
+        adjust_asgn_kernel<<<grid_for(3LL * s->D, 128), 128, 0, st>>>(s->D, s->d_dnode, tm2);
+        CK(cudaGetLastError());
+        s->tm.launches++;
+    }
+    // phase 15: owners publish dangling-node displacements
+    PhaseTimer pt(s, PH_SEND_DN_DISP, st);
+    if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false, st))) return rc;
+    return HGPU_OK;
+}
+
 extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
 {
     if (!s) return fail(HGPU_EINVAL, "null solver");
@@ -894,6 +932,22 @@ extern "C" int hgpu_force_exchange(hgpu_solver_t *s)
             CK(cudaEventRecord(s->ev_early, s->stream));
             CK(cudaStreamWaitEvent(s->comm_stream, s->ev_early, 0));
             if ((rc = force_phases(s, s->comm_stream))) return rc;
+            if (fuse && (s->P.flags & HGPU_FLAG_TAIL_OVERLAP)) {
+                // Every node the displacement phases read or write is owned by a self tile, whose
+                // forces are final here: advance those nodes and run phases 13-15 on this stream too.
+                // They write only the array of the NEW displacements (u[i3]) at nodes no late tile
+                // owns, while the late tiles read u[i1], u[i2].
+                double *un = s->u[s->i3];
+                if (s->nS_early > 0) {
+                    PhaseTimer pt(s, PH_NEW_DISP, s->comm_stream);
+                    update_list_kernel<<<grid_for(3LL * s->nS_early, 256), 256, 0, s->comm_stream>>>(
+                        s->nS_early, s->d_slist, s->u[s->i1], s->u[s->i2], un, s->force, s->mass, s->m2, s->m1);
+                    CK(cudaGetLastError());
+                    s->tm.launches++;
+                }
+                if ((rc = disp_phases(s, un, s->comm_stream))) return rc;
+                s->tail_done = true;
+            }
             CK(cudaEventRecord(s->ev_comm, s->comm_stream));
             // the step kernel fills every SM's registers: leave a few SMs to the exchange kernels
             if ((rc = launch_range(s, tm, fuse, Te, T, s->grid_late))) return rc;
@@ -920,9 +974,10 @@ extern "C" int hgpu_update(hgpu_solver_t *s)
     double *u1 = s->u[s->i1], *u2 = s->u[s->i2], *un = s->u[s->i3];
     PhaseTimer pt(s, PH_NEW_DISP);
     if (s->fstate == F_FUSED_DONE) {
-        if (s->nS > 0) {
-            update_list_kernel<<<grid_for(3LL * s->nS, 256), 256, 0, s->stream>>>(
-                s->nS, s->d_slist, u1, u2, un, s->force, s->mass, s->m2, s->m1);
+        const int32_t first = s->tail_done ? s->nS_early : 0;     // the self tiles' nodes are done already
+        if (s->nS > first) {
+            update_list_kernel<<<grid_for(3LL * (s->nS - first), 256), 256, 0, s->stream>>>(
+                s->nS - first, s->d_slist + first, u1, u2, un, s->force, s->mass, s->m2, s->m1);
             CK(cudaGetLastError());
             s->tm.launches++;
         }
@@ -947,24 +1002,8 @@ extern "C" int hgpu_disp_exchange(hgpu_solver_t *s)
 {
     if (!s) return fail(HGPU_EINVAL, "null solver");
     CK(cudaSetDevice(s->dev));
-    int rc;
-    double *tm2 = s->u[s->i2];
-    // phase 13: owners publish anchored-node displacements
-    {
-        PhaseTimer pt(s, PH_SEND_AN_DISP);
-        if ((rc = exchange(s, s->an_c, s->an_s, tm2, false, s->stream))) return rc;
-    }
-    // phase 14: dangling nodes interpolate from their anchors
-    if (s->D > 0) {
-        PhaseTimer pt(s, PH_ADJUST_DISP);
-        adjust_asgn_kernel<<<grid_for(3LL * s->D, 128), 128, 0, s->stream>>>(s->D, s->d_dnode, tm2);
-        CK(cudaGetLastError());
-        s->tm.launches++;
-    }
-    // phase 15: owners publish dangling-node displacements
-    PhaseTimer pt(s, PH_SEND_DN_DISP);
-    if ((rc = exchange(s, s->dn_c, s->dn_s, tm2, false, s->stream))) return rc;
-    return HGPU_OK;
+    if (s->tail_done) { s->tail_done = false; return HGPU_OK; }   // ran beside the late tiles of this step
+    return disp_phases(s, s->u[s->i2], s->stream);
 }
 
 extern "C" int hgpu_step(hgpu_solver_t *s, int32_t step, const double *F)

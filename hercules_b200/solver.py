@@ -31,6 +31,7 @@ CONV_SHEAR_1, CONV_SHEAR_2, CONV_KAPPA_1, CONV_KAPPA_2 = 5, 6, 7, 8   # psolve.h
 FLAG_NO_FUSE = 1
 FLAG_TIMERS = 2
 FLAG_NO_OVERLAP = 4
+FLAG_TAIL_OVERLAP = 8
 
 
 class HerculesGpuError(RuntimeError):

@@ -103,6 +103,8 @@ typedef struct hgpu_params {
 #define HGPU_FLAG_NO_FUSE 1     /* keep force evaluation and update as separate kernels */
 #define HGPU_FLAG_TIMERS  2     /* bracket every phase with CUDA events (hgpu_get_timers)   */
 #define HGPU_FLAG_NO_OVERLAP 4  /* multi-GPU: run the force exchange after all tiles, on one stream */
+#define HGPU_FLAG_TAIL_OVERLAP 8 /* multi-GPU, opt-in: also run the update of the shared nodes and the displacement
+                                   exchange on the communication stream, beside the late tiles */
 
 typedef struct hgpu_solver hgpu_solver_t;
 

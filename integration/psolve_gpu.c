@@ -178,11 +178,13 @@ static void gpu_solver_run(void)
     const int acc = Param.printStationAccelerations == YES;
     /* Stations on the device (default): the interpolation runs as a kernel at the station steps and
      * the rows come back ST_RING steps at a time, so a station step no longer drains the device
-     * pipeline.  PSOLVE_GPU_HOST_STATIONS=1 keeps the reference's interpolate_station_displacements
+     * pipeline (single-rank runs; PSOLVE_GPU_HOST_STATIONS=0 turns it on for multi-rank runs too).
+     * PSOLVE_GPU_HOST_STATIONS=1 keeps the reference's interpolate_station_displacements
      * on displacements fetched off the GPU (the two produce identical files, tests/test_integration.py). */
     enum { ST_RING = 256 };
-    const int dev_stations = Param.myNumberOfStations > 0 && !(getenv("PSOLVE_GPU_HOST_STATIONS") &&
-                                                              atoi(getenv("PSOLVE_GPU_HOST_STATIONS")));
+    const int host_stations = getenv("PSOLVE_GPU_HOST_STATIONS") ? atoi(getenv("PSOLVE_GPU_HOST_STATIONS"))
+                                                                 : Global.theGroupSize > 1;   /* multi-rank: not yet validated */
+    const int dev_stations = Param.myNumberOfStations > 0 && !host_stations;
     double *st_rows = NULL;
     int32_t *st_steps = NULL;
     if (dev_stations) {
