@@ -228,6 +228,19 @@ def adaptive_bands(n: int):
     return ((n * 11 // 16, 1), (n // 8, 2), (n // 64, 4))
 
 
+def column_grid(world: int) -> tuple[int, int]:
+    """Columns per axis (x, y) of the adaptive weak-scaling domain: Morton order fills x, then y."""
+    cx = cy = 1
+    while cx * cy < world:
+        if cx == cy:
+            cx *= 2
+        else:
+            cy *= 2
+    if cx * cy != world:
+        raise SystemExit("--workload adaptive needs a power-of-two number of GPUs")
+    return cx, cy
+
+
 def adaptive_layers(n: int):
     """Vs doubles from band to band, which is what makes octor refine by one level per band."""
     z1, z2 = (n * 11 // 16) * H_M, (n * 11 // 16 + n // 4) * H_M
@@ -236,13 +249,17 @@ def adaptive_layers(n: int):
 
 def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh", info: dict | None = None) -> dict:
     if info is not None and "bands" in info:
-        return {"workload": f"configs[2]: adaptive octree mesh, 3 refinement levels (element edge {H_M:g}/{2*H_M:g}/{4*H_M:g} m by "
-                            f"depth band, Vs 1000/2000/3464 m/s), {info['E']} elements, {info['N']} nodes, {info['D']} hanging "
-                            f"(dangling) nodes on the two 2:1 interfaces, {damping} damping, effective stiffness, point source, "
-                            "5 stations; mesh tables in octor's layout from meshgen.graded_halfspace (bit-exact with the "
-                            "reference's mesher on tests/golden/graded{2,3}_*.npz)",
-                "elements_per_gpu": info["E"], "global_elements": info["E"], "hanging_nodes": info["D"],
-                "global_grid": [n, n, n], "bands": [list(b) for b in info["bands"]], "dt": DT, "partition": "single rank",
+        cx, cy = column_grid(world)
+        return {"workload": f"configs[{2 if world == 1 else 3}]: adaptive octree mesh, 3 refinement levels (element edge "
+                            f"{H_M:g}/{2*H_M:g}/{4*H_M:g} m by depth band, Vs 1000/2000/3464 m/s), {info['E']} elements, {info['N']} "
+                            f"nodes, {info['D']} owned hanging (dangling) nodes per GPU on the two 2:1 interfaces, {damping} damping, "
+                            "effective stiffness, point source, 5 stations per GPU; mesh tables in octor's layout from "
+                            "meshgen.graded_halfspace (bit-exact with the reference's mesher and partition on "
+                            "tests/golden/graded{2,3}_*.npz)",
+                "elements_per_gpu": info["E"], "global_elements": info["etotal"], "hanging_nodes": info["D"],
+                "global_grid": [n * cx, n * cy, n], "bands": [list(b) for b in info["bands"]], "dt": DT,
+                "partition": (f"{world} columns of {n}^3 h-cells = octor's equal blocks of the Morton-ordered leaf list, halo "
+                              f"exchange over {halo} overlapped with interior tiles" if world > 1 else "single rank"),
                 "l2": "inputs larger than L2; no explicit flush"}
     bx, by, bz = block_grid(world)
     what = ("rayleigh damping, effective stiffness" if damping == "rayleigh" else
@@ -394,11 +411,10 @@ def main() -> None:
     layers = LAYERS_BKT if args.damping == "bkt" else LAYERS
     adaptive = args.workload == "adaptive"
     if adaptive:
-        if world != 1:
-            raise SystemExit("--workload adaptive is a single-GPU workload (configs[2])")
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
         bands = adaptive_bands(n)
+        cols = column_grid(world)
         try:                                        # the host-side mesh tables peak at ~400 B per element
             import psutil
             need = 400 * sum(nl * (n // sz) ** 2 for nl, sz in bands)
@@ -407,7 +423,10 @@ def main() -> None:
         except ImportError:
             pass
         layers = adaptive_layers(n) if args.damping == "rayleigh" else LAYERS_BKT
-        mesh, info = meshgen.graded_halfspace(n, n, bands, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
+        # configs[3] (N > 1): the same column repeated side by side, one per GPU -- octor's equal-count blocks
+        # of the Morton-ordered leaf list are then exactly the columns (meshgen.column_regions)
+        mesh, info = meshgen.graded_halfspace(n * cols[0], n * cols[1], bands, h=H_M, dt=DT, freq=FREQ, layers=layers,
+                                              damping=damp, part=(rank, world) if world > 1 else None)
     elif world == 1:
         mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
     else:

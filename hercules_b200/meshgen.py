@@ -474,15 +474,100 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
     return mesh, info
 
 
+def column_regions(nx: int, ny: int, nz: int, world: int):
+    """octor's partition of a laterally uniform (banded) mesh over `world` ranks, as rectangles of
+    the h-grid: the leaves in Morton order are cut into equal blocks (octor.c:685-746); with every
+    vertical column of aligned c x c cells (c a power of two >= nz) holding the same number of leaves
+    and being contiguous in Morton order, rank r gets `per` consecutive cells.  Returns
+    [(x0, x1, y0, y1)] by rank; raises when the blocks would not be whole rectangles."""
+    S = 1
+    while S < max(nx, ny, nz):
+        S *= 2
+    c = S
+    while c >= max(nz, 1):
+        if nx % c == 0 and ny % c == 0:
+            ncell = (nx // c) * (ny // c)
+            if ncell >= world and ncell % world == 0:
+                break
+        c //= 2
+    else:
+        raise ValueError(f"no column partition of {nx}x{ny}x{nz} over {world} ranks (cells must be >= nz wide)")
+    cx, cy = np.meshgrid(np.arange(nx // c), np.arange(ny // c), indexing="ij")
+    cx, cy = cx.ravel(), cy.ravel()
+    o = np.argsort(morton3(cx, cy, np.zeros_like(cx)), kind="stable")
+    cx, cy = cx[o], cy[o]
+    per = cx.size // world
+    out = []
+    for r in range(world):
+        gx, gy = cx[r * per:(r + 1) * per], cy[r * per:(r + 1) * per]
+        x0, x1, y0, y1 = int(gx.min()) * c, (int(gx.max()) + 1) * c, int(gy.min()) * c, (int(gy.max()) + 1) * c
+        if (x1 - x0) * (y1 - y0) != per * c * c:
+            raise ValueError("a rank's block of columns is not a rectangle")
+        out.append((x0, x1, y0, y1))
+    return out
+
+
+def _graded_leaves(bands, ztop, x0, x1, y0, y1):
+    """Leaves of the banded mesh inside [x0,x1) x [y0,y1), Morton order of the lowest corner."""
+    ex, ey, ez, es = [], [], [], []
+    for (nl, sz), z0 in zip(bands, ztop):
+        gx, gy, gz = np.meshgrid(np.arange(x0, x1, sz, dtype=np.int32), np.arange(y0, y1, sz, dtype=np.int32),
+                                 np.arange(z0, z0 + nl * sz, sz, dtype=np.int32), indexing="ij")
+        ex.append(gx.ravel()); ey.append(gy.ravel()); ez.append(gz.ravel())
+        es.append(np.full(gx.size, sz, np.int32))
+    ex, ey, ez, es = (np.concatenate(v) for v in (ex, ey, ez, es))
+    o = np.argsort(morton3(ex, ey, ez), kind="stable")
+    return ex[o].astype(np.int64), ey[o].astype(np.int64), ez[o].astype(np.int64), es[o].astype(np.int64)
+
+
+def _graded_nodes(bands, ztop, x0, x1, y0, y1, dims):
+    """Mesh nodes inside the closed box [x0,x1] x [y0,y1], in octor's node order."""
+    nx, ny, nz = dims
+    px, py, pz = [], [], []
+    for k, ((nl, sz), z0) in enumerate(zip(bands, ztop)):
+        first = z0 if k == 0 else z0 + sz                       # a band's top plane belongs to the finer band above
+        gx, gy, gz = np.meshgrid(np.arange(x0, x1 + 1, sz, dtype=np.int32), np.arange(y0, y1 + 1, sz, dtype=np.int32),
+                                 np.arange(first, z0 + nl * sz + 1, sz, dtype=np.int32), indexing="ij")
+        px.append(gx.ravel()); py.append(gy.ravel()); pz.append(gz.ravel())
+    px, py, pz = (np.concatenate(v) for v in (px, py, pz))
+
+    def key(g, n):
+        return np.where(g == n, 2 * n - 1, 2 * g)
+    o = np.argsort(morton3(key(px, nx), key(py, ny), key(pz, nz)), kind="stable")
+    return px[o].astype(np.int64), py[o].astype(np.int64), pz[o].astype(np.int64)
+
+
+def _graded_dangling(px, py, pz, bands, ztop):
+    """For nodes of the banded mesh: deps (0 = anchored, 2 = hangs on an edge, 4 = in a face) and the
+    coordinates of the anchors in the reference's list order (descending Z-order)."""
+    deps = np.zeros(px.size, np.int32)
+    ax, ay = np.zeros((px.size, 4), np.int64), np.zeros((px.size, 4), np.int64)
+    for (_, sf), (_, sc), zp in zip(bands[:-1], bands[1:], ztop[1:]):
+        on = pz == zp
+        ox, oy = on & ((px % sc) != 0), on & ((py % sc) != 0)
+        sel = ox | oy
+        both = ox & oy
+        deps[sel] = np.where(both[sel], 4, 2)
+        xh, xl = np.where(ox, px + sf, px), np.where(ox, px - sf, px)
+        yh, yl = np.where(oy, py + sf, py), np.where(oy, py - sf, py)
+        # 2 anchors: (high, low) along the hanging axis; 4 anchors: (xh,yh) (xl,yh) (xh,yl) (xl,yl)
+        ax[sel, 0], ay[sel, 0] = xh[sel], yh[sel]
+        ax[sel, 1], ay[sel, 1] = xl[sel], np.where(both, yh, yl)[sel]
+        ax[both, 2], ay[both, 2] = xh[both], yl[both]
+        ax[both, 3], ay[both, 3] = xl[both], yl[both]
+    return deps, ax, ay
+
+
 def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float = 1.0,
                      damping: int = RAYLEIGH, layers=((0.0, 6000.0, 3464.0, 2700.0),),
-                     thr_damping: float = 0.05, thr_vpvs: float = 3.0, exact: bool = False):
-    """Single-rank adaptive (2:1 balanced) octree mesh of a depth-banded half-space, in the layout
-    octor + solver_init produce for it (bit-exact on tests/golden/graded3_rayleigh_eff.npz,
-    tests/test_meshgen.py).  The h-grid has nx x ny points per horizontal plane; bands = ((nlayers,
-    size), ...) from the surface down: nlayers layers of cubic elements of edge size * h, size
-    doubling from one band to the next (what octor's refinement + balancing yield when Vs grows
-    with depth by band).  layers = (ztop, Vp, Vs, rho) by the depth of the element centre.
+                     thr_damping: float = 0.05, thr_vpvs: float = 3.0, exact: bool = False,
+                     part: tuple | None = None):
+    """Adaptive (2:1 balanced) octree mesh of a depth-banded half-space, in the layout octor +
+    solver_init produce for it (bit-exact on tests/golden/graded{2,3}_*.npz, tests/test_meshgen.py).
+    The h-grid has nx x ny points per horizontal plane; bands = ((nlayers, size), ...) from the
+    surface down: nlayers layers of cubic elements of edge size * h, size doubling from one band to
+    the next (what octor's refinement + balancing yield when Vs grows with depth by band).  layers =
+    (ztop, Vp, Vs, rho) by the depth of the element centre.
 
     * leaves in preorder = Morton order of their lowest corner (octor.c:5362-5374, 5505);
     * nodes = the distinct leaf corners in Z-order with the far faces pulled in by one tick
@@ -490,9 +575,20 @@ def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float =
     * a node on the plane between two bands that is not a corner of the coarse side is dangling:
       on a coarse edge it hangs on that edge's 2 end nodes, inside a coarse face on its 4 corners;
       the anchor list is in descending Z-order (octor pushes at the head, octor.c:5863-5991);
-      dnodeTable is in ascending ldnid;
+      dnodeTable holds the OWNED dangling nodes in ascending ldnid;
     * nTable: element loop of solver_init, then compute_adjust(DISTRIBUTION) over all 7 columns
       in dnodeTable order (psolve.c:3503-3504, 5936-5978).
+
+    part = (rank, nranks): that rank's share under octor's block partition of the Morton-ordered
+    leaf list, for domains whose blocks are whole columns of cells (column_regions): local
+    elements and geid, harbored nodes (the corners of the local elements), ownership (the rank whose
+    region holds the node's pixel, far faces pulled in, octor.c:5466-5475), share lists in the
+    order this rank discovers its neighbours (com_allocpctl, octor.c:2639-2742), dangling / anchored
+    schedules (schedule_build, psolve.c:4705-4863).  On a partitioned mesh nTable holds, for every
+    harbored node, the COMPLETE sums (all ranks' elements, all hanging-node transfers) evaluated in
+    single-rank order: owned rows equal the reference's up to the order of additions (1e-15), rows of
+    non-owned nodes are whole instead of partial (the reference overwrites those nodes after every
+    update, psolve.c:4130-4154, so their mass never reaches a result).
     Returns (HostMesh, info)."""
     bands = [(int(a), int(b)) for a, b in bands]
     for (_, s0), (_, s1) in zip(bands[:-1], bands[1:]):
@@ -507,85 +603,160 @@ def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float =
             raise ValueError("a band must start on a multiple of its element size")
         ztop.append(ztop[-1] + nl * sz)
     nz = ztop[-1]
+    dims = (nx, ny, nz)
+    rank, world = part if part is not None else (0, 1)
+    regions = column_regions(nx, ny, nz, world) if world > 1 else [(0, nx, 0, ny)]
+    x0, x1, y0, y1 = regions[rank]
+    if (x0 % smax) or (x1 % smax) or (y0 % smax) or (y1 % smax):
+        raise ValueError("partition columns must be aligned to the coarsest element size")
     # ---- leaves -----------------------------------------------------------------------------------
-    ex, ey, ez, es = [], [], [], []
-    for (nl, sz), z0 in zip(bands, ztop):
-        gx, gy, gz = np.meshgrid(np.arange(0, nx, sz, dtype=np.int32), np.arange(0, ny, sz, dtype=np.int32),
-                                 np.arange(z0, z0 + nl * sz, sz, dtype=np.int32), indexing="ij")
-        ex.append(gx.ravel()); ey.append(gy.ravel()); ez.append(gz.ravel())
-        es.append(np.full(gx.size, sz, np.int32))
-    ex, ey, ez, es = (np.concatenate(v) for v in (ex, ey, ez, es))
-    o = np.argsort(morton3(ex, ey, ez), kind="stable")
-    ex, ey, ez, es = ex[o].astype(np.int64), ey[o].astype(np.int64), ez[o].astype(np.int64), es[o].astype(np.int64)
-    del o
+    ex, ey, ez, es = _graded_leaves(bands, ztop, x0, x1, y0, y1)
     E = ex.size
     # ---- nodes ------------------------------------------------------------------------------------
-    px, py, pz = [], [], []
-    for k, ((nl, sz), z0) in enumerate(zip(bands, ztop)):
-        first = z0 if k == 0 else z0 + sz                       # a band's top plane belongs to the finer band above
-        gx, gy, gz = np.meshgrid(np.arange(0, nx + 1, sz, dtype=np.int32), np.arange(0, ny + 1, sz, dtype=np.int32),
-                                 np.arange(first, z0 + nl * sz + 1, sz, dtype=np.int32), indexing="ij")
-        px.append(gx.ravel()); py.append(gy.ravel()); pz.append(gz.ravel())
-    px, py, pz = (np.concatenate(v) for v in (px, py, pz))
-
-    def key(g, n):
-        return np.where(g == n, 2 * n - 1, 2 * g)
-    o = np.argsort(morton3(key(px, nx), key(py, ny), key(pz, nz)), kind="stable")
-    px, py, pz = px[o].astype(np.int64), py[o].astype(np.int64), pz[o].astype(np.int64)
-    del o
+    px, py, pz = _graded_nodes(bands, ztop, x0, x1, y0, y1, dims)
     N = px.size
-    nrank = np.full((nx + 1, ny + 1, nz + 1), -1, np.int32)
-    nrank[px, py, pz] = np.arange(N, dtype=np.int32)
+    nrank = np.full((x1 - x0 + 1, y1 - y0 + 1, nz + 1), -1, np.int32)
+    nrank[px - x0, py - y0, pz] = np.arange(N, dtype=np.int32)
     lnid = np.empty((E, 8), np.int32)
     for j in range(8):
-        lnid[:, j] = nrank[ex + es * (j & 1), ey + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)]
+        lnid[:, j] = nrank[ex - x0 + es * (j & 1), ey - y0 + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)]
     assert lnid.min() >= 0
+    # ---- ownership --------------------------------------------------------------------------------
+    owner = np.full(N, rank, np.int32)
+    if world > 1:
+        qx, qy = np.minimum(px, nx - 1), np.minimum(py, ny - 1)
+        for r, (a0, a1, b0, b1) in enumerate(regions):
+            owner[(qx >= a0) & (qx < a1) & (qy >= b0) & (qy < b1)] = r
+    mine = owner == rank
     # ---- dangling nodes ---------------------------------------------------------------------------
-    rows = []
-    for (_, sf), (_, sc), zp in zip(bands[:-1], bands[1:], ztop[1:]):
-        gx, gy = np.meshgrid(np.arange(0, nx + 1, sf, dtype=np.int64), np.arange(0, ny + 1, sf, dtype=np.int64),
-                             indexing="ij")
-        gx, gy = gx.ravel(), gy.ravel()
-        ox, oy = (gx % sc) != 0, (gy % sc) != 0
-        sel = ox | oy
-        gx, gy, ox, oy = gx[sel], gy[sel], ox[sel], oy[sel]
-        r = np.full((gx.size, 6), -1, np.int32)
-        r[:, 0] = nrank[gx, gy, zp]
-        r[:, 1] = np.where(ox & oy, 4, 2)
-        xh, xl = np.where(ox, gx + sf, gx), np.where(ox, gx - sf, gx)
-        yh, yl = np.where(oy, gy + sf, gy), np.where(oy, gy - sf, gy)
-        both = ox & oy
-        # 2 anchors: (high, low) along the hanging axis; 4 anchors: (xh,yh) (xl,yh) (xh,yl) (xl,yl)
-        r[:, 2] = nrank[xh, yh, zp]
-        r[:, 3] = np.where(both, nrank[xl, yh, zp], nrank[xl, yl, zp])
-        r[both, 4] = nrank[xh[both], yl[both], zp]
-        r[both, 5] = nrank[xl[both], yl[both], zp]
-        rows.append(r)
-    dnode = np.concatenate(rows) if rows else np.zeros((0, 6), np.int32)
-    dnode = np.ascontiguousarray(dnode[np.argsort(dnode[:, 0], kind="stable")])
-    del nrank
+    deps, ax, ay = _graded_dangling(px, py, pz, bands, ztop)
+    dsel = np.nonzero((deps > 0) & mine)[0]                      # ascending lnid
+    dnode = np.full((dsel.size, 6), -1, np.int32)
+    dnode[:, 0], dnode[:, 1] = dsel, deps[dsel]
+    for a in range(4):
+        has = deps[dsel] > a
+        dnode[has, 2 + a] = nrank[ax[dsel[has], a] - x0, ay[dsel[has], a] - y0, pz[dsel[has]]]
+    assert (dnode[:, 2:][dnode[:, 2:] != -1] >= 0).all()
+    # ---- share lists and schedules ----------------------------------------------------------------
+    msg = {k: MsgList() for k in ("dn_c", "dn_s", "an_c", "an_s")}
+    share = np.zeros((0, 2), np.int32)
+    if world > 1:
+        def make_list(nodes, peers):
+            # messengers are pushed at the head of the list as they first appear (psolve.c:4733-4746)
+            if nodes.size == 0:
+                return MsgList()
+            order = list(dict.fromkeys(peers.tolist()))[::-1]
+            maps = [nodes[peers == p_] for p_ in order]
+            return MsgList(np.array(order, np.int32), np.array([m.size for m in maps], np.int32),
+                           np.concatenate(maps).astype(np.int32))
+        anch = deps == 0
+        nm = np.nonzero(~mine)[0]
+        msg["an_c"] = make_list(nm[anch[nm]], owner[nm[anch[nm]]].astype(np.int64))
+        msg["dn_c"] = make_list(nm[~anch[nm]], owner[nm[~anch[nm]]].astype(np.int64))
+        disc = _column_discovery_order(ex, ey, es, regions, rank, dims)
+        pos = {p_: i for i, p_ in enumerate(disc)}
+        sh_nodes, sh_peers, sh_pos = [], [], []
+        own = np.nonzero(mine)[0]
+        for r, (a0, a1, b0, b1) in enumerate(regions):
+            if r == rank:
+                continue
+            hit = own[(px[own] >= a0) & (px[own] <= a1) & (py[own] >= b0) & (py[own] <= b1)]
+            if hit.size:
+                sh_nodes.append(hit); sh_peers.append(np.full(hit.size, r, np.int64))
+                sh_pos.append(np.full(hit.size, pos[r], np.int64))
+        if sh_nodes:
+            sh_nodes, sh_peers, sh_pos = np.concatenate(sh_nodes), np.concatenate(sh_peers), np.concatenate(sh_pos)
+            o = np.lexsort((sh_pos, sh_nodes))                   # by node, then by discovery order
+            sh_nodes, sh_peers = sh_nodes[o], sh_peers[o]
+            share = np.stack([sh_nodes, sh_peers], 1).astype(np.int32)
+            msg["an_s"] = make_list(sh_nodes[anch[sh_nodes]], sh_peers[anch[sh_nodes]])
+            msg["dn_s"] = make_list(sh_nodes[~anch[sh_nodes]], sh_peers[~anch[sh_nodes]])
     # ---- solver tables ----------------------------------------------------------------------------
     abase, bbase = compute_setab(damping, freq)
-    pr = _elem_props(ex, ey, ez, (nx, ny, nz), h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=es)
-    nT = np.zeros((N, 7))
-    _accumulate(nT, lnid, pr, dt, exact)
-    if dnode.shape[0]:
-        deps = dnode[:, 1].astype(np.int64)
-        d = nT[dnode[:, 0]] / deps[:, None].astype(np.float64)          # darray = myvalue / deps
-        slot = np.arange(4)[None, :] < deps[:, None]
-        tgt = dnode[:, 2:6][slot]                                        # dnodeTable order, list order
-        np.add.at(nT, tgt, np.repeat(d, deps, axis=0))
+    args = (dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs)
+    pr = _elem_props(ex, ey, ez, *args, size=es)
+    if world == 1:
+        nT = np.zeros((N, 7))
+        _accumulate(nT, lnid, pr, dt, exact)
+        _distribute(nT, dnode)
+    else:
+        # complete sums on the region widened by two coarse elements: every element and every
+        # dangling node that feeds a harbored node lies inside
+        m = 2 * smax
+        X0, X1, Y0, Y1 = max(0, x0 - m), min(nx, x1 + m), max(0, y0 - m), min(ny, y1 + m)
+        gx, gy, gz, gs = _graded_leaves(bands, ztop, X0, X1, Y0, Y1)
+        qx, qy, qz = _graded_nodes(bands, ztop, X0, X1, Y0, Y1, dims)
+        big = np.full((X1 - X0 + 1, Y1 - Y0 + 1, nz + 1), -1, np.int32)
+        big[qx - X0, qy - Y0, qz] = np.arange(qx.size, dtype=np.int32)
+        l8 = np.empty((gx.size, 8), np.int32)
+        for j in range(8):
+            l8[:, j] = big[gx - X0 + gs * (j & 1), gy - Y0 + gs * ((j >> 1) & 1), gz + gs * ((j >> 2) & 1)]
+        full = np.zeros((qx.size, 7))
+        _accumulate(full, l8, _elem_props(gx, gy, gz, *args, size=gs), dt, exact)
+        dq, bx_, by_ = _graded_dangling(qx, qy, qz, bands, ztop)
+        inside = np.ones(qx.size, bool)
+        for a in range(4):                                       # anchors inside the widened box
+            inside &= (dq <= a) | ((bx_[:, a] >= X0) & (bx_[:, a] <= X1) & (by_[:, a] >= Y0) & (by_[:, a] <= Y1))
+        ds = np.nonzero((dq > 0) & inside)[0]
+        dn = np.full((ds.size, 6), -1, np.int32)
+        dn[:, 0], dn[:, 1] = ds, dq[ds]
+        for a in range(4):
+            has = dq[ds] > a
+            dn[has, 2 + a] = big[bx_[ds[has], a] - X0, by_[ds[has], a] - Y0, qz[ds[has]]]
+        _distribute(full, dn)
+        nT = full[big[px - X0, py - Y0, pz]]
     edata = np.zeros((E, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
     if damping == BKT:
         edata[:, 4:14] = bkt_coefficients(pr["Vp"], pr["Vs"])
     K1, K2 = compute_K()
-    empty = MsgList()
-    mesh = HostMesh(lnid, pr["eT"], nT, dnode, edata, K1, K2, empty, MsgList(), MsgList(), MsgList())
+    mesh = HostMesh(lnid, pr["eT"], nT, dnode, edata, K1, K2, msg["dn_c"], msg["dn_s"], msg["an_c"], msg["an_s"])
+    etotal = sum(nl * (nx // sz) * (ny // sz) for nl, sz in bands)
+    lo = block_low(rank, world, etotal)
+    assert block_low(rank + 1, world, etotal) - lo == E
     info = dict(E=E, N=N, D=int(dnode.shape[0]), abase=abase, bbase=bbase, node_xyz=(px, py, pz),
                 node_order=(px * (ny + 1) + py) * (nz + 1) + pz, elem_xyz=(ex, ey, ez), elem_size=es,
-                origin=(0, 0, 0), dims=(nx, ny, nz), h=h, rank=0, nranks=1, etotal=E, bands=bands)
+                elem_geid=np.arange(lo, lo + E, dtype=np.int64), origin=(x0, y0, 0), dims=dims, h=h,
+                owner=owner, share=share, anchored=deps == 0, rank=rank, nranks=world, etotal=etotal,
+                bands=bands, region=(x0, x1, y0, y1))
     return mesh, info
+
+
+def _distribute(nT, dnode):
+    """compute_adjust(DISTRIBUTION) on nTable (psolve.c:3503-3504, 5943-5978): every dangling node of
+    the table adds value / deps to each of its anchors, in table order, anchors in list order."""
+    if not dnode.shape[0]:
+        return
+    deps = dnode[:, 1].astype(np.int64)
+    d = nT[dnode[:, 0]] / deps[:, None].astype(np.float64)               # darray = myvalue / deps
+    slot = np.arange(4)[None, :] < deps[:, None]
+    np.add.at(nT, dnode[:, 2:6][slot], np.repeat(d, deps, axis=0))
+
+
+def _column_discovery_order(ex, ey, es, regions, rank, dims):
+    """Neighbour ranks in the order com_allocpctl (octor.c:2639-2742) first meets them on a column
+    partition: local leaves in Morton order, per leaf 4 x 4 x 4 probe points half an edge apart starting
+    half an edge below the lowest corner (z outermost, x innermost), points outside the domain
+    skipped.  The rank of a probe point depends on x, y only."""
+    nx, ny, _ = dims
+    x0, x1, y0, y1 = regions[rank]
+    near = np.nonzero((ex - es < x0) | (ex + 2 * es > x1) | (ey - es < y0) | (ey + 2 * es > y1))[0]
+    first = {}
+    for j in range(4):
+        for i in range(4):
+            # doubled coordinates: 2 x - s + s i
+            p2x, p2y = 2 * ex[near] - es[near] + es[near] * i, 2 * ey[near] - es[near] + es[near] * j
+            ok = (p2x >= 0) & (p2x < 2 * nx) & (p2y >= 0) & (p2y < 2 * ny)
+            fx, fy = p2x // 2, p2y // 2
+            for r, (a0, a1, b0, b1) in enumerate(regions):
+                if r == rank:
+                    continue
+                hit = ok & (fx >= a0) & (fx < a1) & (fy >= b0) & (fy < b1)
+                if hit.any():
+                    kmin = int((near[hit].astype(np.int64) * 16 + (j * 4 + i)).min())
+                    if r not in first or kmin < first[r]:
+                        first[r] = kmin
+    return [r for r, _ in sorted(first.items(), key=lambda kv: kv[1])]
 
 
 def _discovery_order(mi, ex, ey, ez, origin, shape, rank, world):

@@ -101,3 +101,58 @@ def test_graded_mesh_matches_octor_and_solver_init(name, grid, bands, h, layers)
     fast, _ = meshgen.graded_halfspace(*grid, bands, h=h, dt=P["dt"], freq=P["freq"],
                                        damping=P["damping"], layers=layers)
     assert np.allclose(fast.nTable, g["nTable"], rtol=1e-13, atol=0)
+
+
+L3 = [(0, 1800, 866, 1800), (62.5, 3000, 1732, 2000), (250, 6000, 3464, 2700)]
+L2 = [(0, 3000, 1732, 2000), (125, 6000, 3464, 2700)]
+
+
+@pytest.mark.parametrize("name,world,grid,bands,h,layers", [
+    ("graded3_rayleigh_eff_np2", 2, (32, 32), ((2, 1), (3, 2), (2, 4)), 31.25, L3),
+    # with 4 ranks the reference's octor leaves no level-3 octants: two levels, 3840 leaves
+    ("graded3_rayleigh_eff_np4", 4, (32, 32), ((2, 1), (7, 2)), 31.25, L3),
+    ("graded2_bkt_np2", 2, (16, 16), ((2, 1), (3, 2)), 62.5, L2),
+])
+def test_graded_partition_matches_octor(name, world, grid, bands, h, layers):
+    """Partitioned adaptive meshes: element blocks, local node numbering, ownership, anchored flags,
+    share lists, the OWNED dangling-node table with its anchor lists, and all four halo schedules
+    (dangling / anchored x contribute / share) bit-exact with multi-rank runs of the unmodified
+    reference; nTable rows of owned nodes equal to rounding (complete sums in single-rank order)."""
+    from conftest import rank_view
+    from hercules_b200 import meshgen
+    g = load_golden(name)
+    for r in range(world):
+        v = rank_view(g, r); P = params_of(v)
+        mesh, info = meshgen.graded_halfspace(*grid, bands, h=h, dt=P["dt"], freq=P["freq"], damping=P["damping"],
+                                              layers=layers, exact=True, part=(r, world))
+        assert np.array_equal(info["elem_geid"], v["elem_geid"])
+        assert np.array_equal(mesh.elem_lnid, v["elem_lnid"])
+        tick = int(v["node_ticks"][v["node_ticks"] > 0].min())
+        assert np.array_equal(np.stack(info["node_xyz"], 1) * tick, v["node_ticks"])
+        ismine = v["node_flags"][:, 0].astype(bool)
+        assert np.array_equal(info["owner"] == r, ismine)
+        assert np.array_equal(info["owner"][~ismine], v["node_owner"][~ismine])
+        assert np.array_equal(info["anchored"], v["node_flags"][:, 1].astype(bool))
+        assert np.array_equal(info["share"], v["node_share"])
+        assert np.array_equal(mesh.dnode, v["dnode"])
+        for side in ("dn_c", "dn_s", "an_c", "an_s"):
+            ml = getattr(mesh, side)
+            hdr = np.stack([ml.peer, ml.nodes], 1).reshape(-1, 2)
+            assert np.array_equal(hdr, v[side + "_hdr"].reshape(-1, 2)), (r, side)
+            assert np.array_equal(ml.mapping, v[side + "_map"]), (r, side)
+        assert np.array_equal(mesh.eTable, v["eTable"])
+        if P["damping"] != 3:
+            assert np.array_equal(mesh.edata[:, :4], v["elem_edata"][:, :4])
+        assert np.allclose(mesh.nTable[ismine], v["nTable"][ismine], rtol=2e-15, atol=0)
+        assert (mesh.nTable[:, 0] > 0).all()
+
+
+def test_column_regions():
+    from hercules_b200 import meshgen
+    assert meshgen.column_regions(32, 32, 16, 2) == [(0, 32, 0, 16), (0, 32, 16, 32)]
+    assert meshgen.column_regions(32, 32, 16, 4) == [(0, 16, 0, 16), (16, 32, 0, 16), (0, 16, 16, 32), (16, 32, 16, 32)]
+    assert meshgen.column_regions(1024, 512, 512, 2) == [(0, 512, 0, 512), (512, 1024, 0, 512)]
+    r8 = meshgen.column_regions(2048, 1024, 512, 8)
+    assert r8[:4] == [(0, 512, 0, 512), (512, 1024, 0, 512), (0, 512, 512, 1024), (512, 1024, 512, 1024)] and r8[4][0] == 1024
+    with pytest.raises(ValueError):
+        meshgen.column_regions(32, 32, 32, 2)          # columns 16 wide would interleave in z

@@ -58,3 +58,19 @@ def test_tile_plan_rejects_bad_mesh():
     lnid = np.arange(8, dtype=np.int32).reshape(1, 8)
     with pytest.raises(solver.HerculesGpuError, match="out of range"):
         solver.plan_build(lnid, 4)
+
+
+@pytest.mark.parametrize("world,rank", [(2, 0), (4, 3), (8, 4)])
+def test_tile_plan_on_partitioned_adaptive_workload(world, rank):
+    """bench.py --workload adaptive --gpus N (configs[3]) at 1/512 of its size: the plan builds and
+    self-checks on a rank's share of the partitioned 3-level mesh; tiles owning shared or hanging
+    nodes become self tiles."""
+    import bench
+    from hercules_b200 import meshgen, solver
+    n = 64
+    cx, cy = bench.column_grid(world)
+    mesh, info = meshgen.graded_halfspace(n * cx, n * cy, bench.adaptive_bands(n), h=bench.H_M, dt=bench.DT,
+                                          layers=bench.adaptive_layers(n), part=(rank, world))
+    r = solver.plan_build(mesh.elem_lnid, info["N"], 0, mesh=mesh)
+    assert r["tile_elems_total"] >= info["E"] and r["early_tiles"] >= 1
+    assert r["smem_bytes"] <= 115712
