@@ -7,7 +7,7 @@ messenger lists prescribe: c-list -> owner with += in the owner's s-list order (
 s-list -> sharers with = (sharing).  Rank 0 compares every rank's final displacement field with a
 single-rank oracle run on the whole mesh, node by node (matched by coordinates).  This checks, with
 no GPU, that partitioned meshes + schedules + complete nTable rows describe the same problem as the
-whole mesh -- the host-side half of the multi-GPU path (the device half is tests/test_gpu_multirank.py).
+whole mesh -- the host-side half of the multi-GPU path (the device half is tests/test_multirank_gpu.py).
 
 usage: halo_worker.py <nx> <ny> <bands as n:s,n:s,...> <steps>     env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT
 """

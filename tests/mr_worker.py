@@ -1,5 +1,5 @@
 """Worker for the multi-rank tests: one process per rank (launched by torch.distributed.run or by
-tests/test_gpu_multirank.py).  Steps a multi-rank golden case of the unmodified reference through
+tests/test_multirank_gpu.py).  Steps a multi-rank golden case of the unmodified reference through
 libhercules_gpu.so with the halo exchange replacing schedule_senddata, and checks every rank's
 tm1 snapshots against what the reference's own MPI ranks held.
 

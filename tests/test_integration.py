@@ -47,11 +47,11 @@ def run_both(case: refcase.Case, nranks: int):
         with tempfile.TemporaryDirectory() as td:
             d = refcase.write_case(case, td)
             if which == "ref":
-                log = refcase.run("psolve_ref_O2", d, nranks=nranks, timeout=900)
+                log = refcase.run("psolve_ref_O2", d, nranks=nranks, timeout=300)
             else:
                 env = dict(os.environ, HMPI_NP=str(nranks))
                 p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=env, stdout=subprocess.PIPE,
-                                   stderr=subprocess.STDOUT, text=True, timeout=900)
+                                   stderr=subprocess.STDOUT, text=True, timeout=300)
                 assert p.returncode == 0, p.stdout[-4000:]
                 log = p.stdout
                 mon = (d / "out" / "monitor.txt").read_text()
@@ -147,7 +147,7 @@ def test_device_stations_write_the_same_files():
         with tempfile.TemporaryDirectory() as td:
             d = refcase.write_case(c, td)
             p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                               text=True, timeout=900, env=dict(os.environ, HMPI_NP="1", PSOLVE_GPU_HOST_STATIONS=host))
+                               text=True, timeout=300, env=dict(os.environ, HMPI_NP="1", PSOLVE_GPU_HOST_STATIONS=host))
             assert p.returncode == 0, p.stdout[-4000:]
             files[host] = [(d / "out" / "stations" / f"station.{i}").read_bytes() for i in range(len(c.stations))]
     assert files["0"] == files["1"]

@@ -25,7 +25,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(name, world, transport, devices, flags=0, timeout=300):
+def _run(name, world, transport, devices, flags=0, timeout=180):
     port = _free_port()
     procs = []
     for r in range(world):
