@@ -55,6 +55,14 @@ CASES = {
     "graded3_rayleigh_eff": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 1, 25),
     "graded3_rayleigh_eff_np2": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 2, 25),
     "graded3_rayleigh_eff_np4": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 4, 25),
+    # BASELINE.json configs[0] (examples/test1): homogeneous half-space 100 x 100 x 37.5 km (tick ratio 8:8:3),
+    # meshed for 0.1 Hz (32 x 32 x 12 elements of 3125 m), quadratic point source 1 km deep, 500 steps of 0.02 s;
+    # the unshipped labase.e is stood in for by a homogeneous etree of the same values (SURVEY.md 8d cfg 1)
+    "test1_homogeneous": (dict(cvm_level=3, cvm_n=(8, 8, 3), east_m=100000.0, layers=[(0.0, 6000.0, 3464.0, 2700.0)],
+                               freq_hz=0.1, ppw=8.0, vs_min=500.0, dt=0.02, end_t=10.0, damping="rayleigh",
+                               stiffness="effective", src_xyz=(50000.0, 50000.0, 1000.0),
+                               src_strike_dip_rake=(0.0, 90.0, 0.0), src_risetime=0.5, src_moment=1e15,
+                               stations=[(50000.0, 50000.0, 0.0), (62000.0, 41000.0, 0.0), (30000.0, 70000.0, 5000.0)]), 1, 100),
     "uniform_rayleigh_eff": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 1, 25),
     "uniform_rayleigh_eff_np3": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 3, 25),
     "uniform_rayleigh_eff_np4": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 4, 25),

@@ -156,3 +156,13 @@ def test_column_regions():
     assert r8[:4] == [(0, 512, 0, 512), (512, 1024, 0, 512), (0, 512, 512, 1024), (512, 1024, 512, 1024)] and r8[4][0] == 1024
     with pytest.raises(ValueError):
         meshgen.column_regions(32, 32, 32, 2)          # columns 16 wide would interleave in z
+
+
+def test_uniform_mesh_configs0_domain():
+    """BASELINE.json configs[0] (examples/test1): 100 x 100 x 37.5 km, tick ratio 8:8:3, 32 x 32 x 12
+    elements -- a domain whose depth is not a power of two -- bit-exact with the reference's mesh."""
+    from hercules_b200 import meshgen
+    g = load_golden("test1_homogeneous"); P = params_of(g)
+    mesh, info = meshgen.uniform_halfspace(32, 32, 12, h=3125.0, dt=P["dt"], freq=P["freq"], damping=P["damping"], exact=True)
+    assert np.array_equal(mesh.elem_lnid, g["elem_lnid"])
+    assert np.array_equal(mesh.eTable, g["eTable"]) and np.array_equal(mesh.nTable, g["nTable"])
