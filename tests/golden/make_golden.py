@@ -49,6 +49,11 @@ CASES = {
     "graded2_none_eff": (dict(**TWO_LAYER, **SRC, damping="none", stiffness="effective", end_t=0.06), 1, 20),
     "graded2_mass_eff": (dict(**TWO_LAYER, **SRC, damping="mass", stiffness="effective", end_t=0.06), 1, 20),
     "graded2_bkt": (dict(**TWO_LAYER, **SRC, damping="bkt", stiffness="effective", end_t=0.06), 1, 20),
+    # soft column with Vp/Vs = 3 and finite Qk (use_infinite_qk = no): BOTH memory-variable families of
+    # calc_conv / constant_Q_addforce are active in a whole run of the reference (damping.c:126-216, 256-371)
+    "graded2_bkt_qk": (dict(cvm_level=3, cvm_n=(8, 8, 4), vs_min=800, freq_hz=2.5,
+                            layers=[(0, 2400, 800, 2000), (125, 4800, 1600, 2300)], **SRC, damping="bkt",
+                            stiffness="effective", end_t=0.06, use_infinite_qk="no"), 1, 20),
     "graded2_bkt_np2": (dict(**TWO_LAYER, **SRC, damping="bkt", stiffness="effective", end_t=0.06), 2, 20),
     "graded2_accel": (dict(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.03,
                            print_accel="yes"), 1, 10),

@@ -20,7 +20,8 @@ REL_TOL_RUN = 1e-10
 
 SINGLE = ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded2_none_eff", "graded2_mass_eff",
           "graded2_bkt", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
-          "test1_homogeneous"]      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
+          "test1_homogeneous",      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
+          "graded2_bkt_qk"]         # BKT with finite Qk: shear AND kappa memory variables active
 
 
 @pytest.fixture(scope="module")

@@ -70,6 +70,10 @@ def test_bkt_coefficients_match_reference_edata():
     ed = load_golden("graded2_bkt")["elem_edata"]
     c = meshgen.bkt_coefficients(ed[:, 1], ed[:, 2], use_inf_qk=True)
     assert np.array_equal(c, ed[:, 4:14])
+    # finite Qk (use_infinite_qk = no) on a soft column: both families non-zero, bit-exact again
+    ed = load_golden("graded2_bkt_qk")["elem_edata"]
+    c = meshgen.bkt_coefficients(ed[:, 1], ed[:, 2], use_inf_qk=False)
+    assert np.array_equal(c, ed[:, 4:14]) and (c[:, 5:] != 0).all()
     # finite Qk: every element of a stiff layer still finds a table row, soft ones differ
     c2 = meshgen.bkt_coefficients(np.float32([4000, 6000, 1500]), np.float32([2000, 3464, 500]))
     assert c2.shape == (3, 10) and (c2[:, :5] > 0).all()
