@@ -360,6 +360,8 @@ def main() -> None:
     ap.add_argument("--tail-overlap", action="store_true",
                     help="multi-GPU, opt-in: shared-node update + displacement exchange beside the late tiles "
                          "(HGPU_FLAG_TAIL_OVERLAP)")
+    ap.add_argument("--wpass", action="store_true",
+                    help="opt-in step-kernel variant (HGPU_FLAG_WPASS): damped displacement formed once per staged node")
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
@@ -455,7 +457,7 @@ def main() -> None:
     s = hb.Solver(mesh, dt=DT, damping=damp, stiffness=hb.EFFECTIVE, freq=FREQ,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
                   tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0) |
-                  (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0))
+                  (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0) | (hb.FLAG_WPASS if args.wpass else 0))
     if world > 1:
         if args.halo == "nccl":
             uid = [hb.Solver.comm_unique_id() if rank == 0 else None]
@@ -564,7 +566,8 @@ def main() -> None:
                                       args.damping, info if adaptive else None),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm",
-                         "kernel": ("step_kernel<1,false,256> (stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"
+                         "kernel": (("step_kernel<1,false,256,true> (WPASS variant; " if args.wpass else "step_kernel<1,false,256> (") +
+                                    "stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"
                                     else "step_kernel<3,false,256> (BKT memory variables + constant-Q force + update, fused)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "peak_source": peak_src,

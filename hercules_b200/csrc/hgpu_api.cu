@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -139,6 +140,7 @@ struct hgpu_solver {
     int32_t *t_halo_id = nullptr;
     uint4 *t_ent_slot = nullptr;         // per entry 8 x uint16 = 3 * slot
     double *t_ent_coef = nullptr;        // per entry c1, c2, beta
+    double *t_beta = nullptr;            // per tile (processing order): the entries' common beta, or NaN
     uint2 *t_rec = nullptr;              // finish records
     int32_t *t_src = nullptr, *t_dep = nullptr;
     double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
@@ -460,8 +462,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             if (!iso || !(np[0] > 0.0)) cls[n] = NODE_SPECIAL;
             const double rm = np[0] > 0.0 ? 1.0 / np[0] : 1.0;
             nt3[3 * (size_t)n] = cls[n] == NODE_SPECIAL ? -rm : rm;
-            nt3[3 * (size_t)n + 1] = np[1];
-            nt3[3 * (size_t)n + 2] = np[4];
+            // m2, m1 are only ever applied to REGULAR nodes; zero for SPECIAL ones so that the WPASS
+            // variant can seed the accumulator with m2 u1 - m1 u2 without looking at the class
+            nt3[3 * (size_t)n + 1] = cls[n] == NODE_SPECIAL ? 0.0 : np[1];
+            nt3[3 * (size_t)n + 2] = cls[n] == NODE_SPECIAL ? 0.0 : np[4];
         }
         for (int32_t n = 0; n < N; n++) if (cls[n] == NODE_SPECIAL) slist.push_back(n);
         s->nS = (int32_t)slist.size();
@@ -532,6 +536,17 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 m[14] = t;
             }
             TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
+            // the Rayleigh ratio shared by all entries of a tile (one material), NaN otherwise
+            std::vector<double> tbeta((size_t)pl.ntiles, 0.0);
+            for (int32_t i = 0; i < pl.ntiles; i++) {
+                const int32_t t = order[i];
+                const int32_t e0 = pl.elem_off[t], e1 = pl.elem_off[(size_t)t + 1];
+                double b = e1 > e0 ? coef[3 * (size_t)e0 + 2] : 0.0;
+                for (int32_t k = e0 + 1; k < e1; k++)
+                    if (coef[3 * (size_t)k + 2] != b) { b = std::numeric_limits<double>::quiet_NaN(); break; }
+                tbeta[i] = b;
+            }
+            TRY(upload(s, &s->t_beta, tbeta.data(), tbeta.size()));
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
@@ -631,7 +646,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     dfree(s->mailbox); dfree(s->d_p2p_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id);
+    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta);
     dfree(s->conv); dfree(s->t_ent_bkt); dfree(s->entry_of_elem); dfree(s->conv_scratch);
     dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
@@ -684,6 +699,7 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.fuse_update = fuse ? 1 : 0;
     A.conv = s->conv; A.ent_bkt = s->t_ent_bkt;
     A.rmax = 2.0 * M_PI * s->P.freq * s->P.dt;                     // damping.c:114, 234
+    A.tile_beta = s->t_beta;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt;
     const int mode = tm.bkt ? 3 : tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
@@ -705,7 +721,9 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
             else                step_kernel<2, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
         }                                                                                        \
     } while (0)
-    if (B == 384) LAUNCH(384); else LAUNCH(256);
+    if (fuse && !dense && mode == 1 && B == 256 && (s->P.flags & HGPU_FLAG_WPASS))
+        step_kernel<1, false, 256, true><<<G, B, s->smem_u2, s->stream>>>(A);      // opt-in variant, see hgpu_kernels.cuh
+    else if (B == 384) LAUNCH(384); else LAUNCH(256);
 #undef LAUNCH
     CK(cudaGetLastError());
     s->tm.launches++;

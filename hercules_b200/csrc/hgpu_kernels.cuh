@@ -161,6 +161,9 @@ struct StepArgs {
     double *conv;                       // conv_shear_1|2, conv_kappa_1|2 in entry-chunked layout, see conv_index
     const double *__restrict__ ent_bkt; // per entry 8 doubles: c1, c2, then 10 floats a0s a1s bs g0s g1s a0k a1k bk g0k g1k, pad
     double rmax;                        // 2 pi f_max dt (damping.c:114)
+    // WPASS variant (MODE 1): per tile, in processing order, the Rayleigh ratio beta = c3/c1 shared by
+    // all its entries, or NaN when they differ (the tile then takes the per-corner path)
+    const double *__restrict__ tile_beta;
 };
 
 // BKT memory variables (psolve.h:308-311: conv_shear_1, conv_shear_2, conv_kappa_1, conv_kappa_2,
@@ -529,9 +532,17 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
     }
 }
 
-template <int MODE, bool DENSE, int THREADS>
+// WPASS (MODE 1, fused update; opt-in, HGPU_FLAG_WPASS): on a tile whose entries share one beta, the
+// damped displacement w = u1 + beta (u1 - u2) is formed ONCE PER STAGED NODE right after the tile has
+// landed (in place, over the u1 stage) instead of once per element corner, so the element phase
+// gathers 24 values per element instead of 48.  The inertia term m2 u1 - m1 u2 of the owned REGULAR
+// nodes, which needs u1 and u2, is put into the accumulator in the same pass (the forces are then
+// added on top of it and the sum is scaled by 1/mass where the default path adds the inertia term
+// last): m2, m1 of a tile's nodes are therefore prefetched one tile ahead.
+template <int MODE, bool DENSE, int THREADS, bool WPASS = false>
 __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 {
+    static_assert(!WPASS || (MODE == 1 && !DENSE), "WPASS is a variant of the Rayleigh + effective kernel");
     constexpr bool U2E = MODE != 0;          // elements read u2
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -589,6 +600,23 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         if (tid < mb.y - mb.x) enext = load_entry<MODE>(A, mb.x + tid);
     }
 
+    // WPASS: m2, m1 of the owned nodes and beta of the tile that is processed NEXT (registers)
+    double ntm[NT_PRE][2];
+    double beta_pref = 0.0;
+    if (WPASS) {
+        const int4 ma = meta_group(smeta[0], 0);
+#pragma unroll
+        for (int q = 0; q < NT_PRE; q++) {
+            const int i = tid + q * nthr;
+            ntm[q][0] = ntm[q][1] = 0.0;
+            if (i < ma.y - ma.x) {
+                const double *nt = A.nt3 + 3 * (size_t)(ma.x + i);
+                ntm[q][0] = ldg_f64_pinned(nt + 1); ntm[q][1] = ldg_f64_pinned(nt + 2);
+            }
+        }
+        beta_pref = ldg_f64_pinned(A.tile_beta + t);
+    }
+
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
         double *su2 = su1 + S3;
@@ -624,6 +652,47 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         const bool prv_pending = it > 0;
         double ntv[NT_PRE][3];
         unsigned int flag_value = A.epoch;
+        bool uni = false;                     // WPASS: this tile's entries share one beta
+        if (WPASS) {
+            const double beta_t = beta_pref;
+            uni = beta_t == beta_t;
+            const double *nt_own = A.nt3 + 3 * (size_t)n0;
+            // owned nodes: inertia term into the (zeroed) accumulator -- nt3 holds m2 = m1 = 0 for
+            // SPECIAL nodes, whose accumulator must end up as the plain force -- and w over u1
+#pragma unroll
+            for (int q = 0; q < NT_PRE; q++) {
+                const int i = tid + q * nthr;
+                if (i < nown) {
+                    const int k = 3 * i;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double x1 = su1[k + c], x2 = su2[k + c];
+                        acc[k + c] = ntm[q][0] * x1 - ntm[q][1] * x2;
+                        if (uni) su1[k + c] = fma(beta_t, x1 - x2, x1);
+                    }
+                }
+            }
+            for (int i = tid + NT_PRE * nthr; i < nown; i += nthr) {
+                const double m2 = __ldg(nt_own + 3 * i + 1), m1 = __ldg(nt_own + 3 * i + 2);
+                const int k = 3 * i;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const double x1 = su1[k + c], x2 = su2[k + c];
+                    acc[k + c] = m2 * x1 - m1 * x2;
+                    if (uni) su1[k + c] = fma(beta_t, x1 - x2, x1);
+                }
+            }
+            // gathered nodes
+            if (uni) {
+                const int4 ma = meta_group(m_cur, 0);
+                const int nh3 = 3 * (ma.w - ma.z);
+                for (int k = tid; k < nh3; k += nthr) {
+                    const double x1 = su1[nown3 + k], x2 = su2[nown3 + k];
+                    su1[nown3 + k] = fma(beta_t, x1 - x2, x1);
+                }
+            }
+            __syncthreads();
+        }
 
         // ---- element forces, accumulated per staged node ----------------------------------------
         for (int base = 0; base < ne; base += nthr) {
@@ -681,7 +750,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 for (int j = 0; j < 8; j++) {
                     const int o = sl[j];
                     const double ax = su1[o], ay = su1[o + 1], az = su1[o + 2];
-                    if (MODE == 0) { wx[j] = ax; wy[j] = ay; wz[j] = az; }
+                    if (MODE == 0 || (WPASS && uni)) { wx[j] = ax; wy[j] = ay; wz[j] = az; }
                     else {
                         const double dx = ax - su2[o], dy = ay - su2[o + 1], dz = az - su2[o + 2];
                         if (MODE == 1) { wx[j] = fma(ecur.beta, dx, ax); wy[j] = fma(ecur.beta, dy, ay); wz[j] = fma(ecur.beta, dz, az); }
@@ -724,8 +793,26 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 }
             }
             if (last) {
-                if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
+                if (WPASS) {                     // settle only scales: 1/mass of this tile's nodes
+#pragma unroll
+                    for (int q = 0; q < NT_PRE; q++) {
+                        const int i = tid + q * nthr;
+                        ntv[q][0] = i < nown ? ldg_f64_pinned(A.nt3 + 3 * (size_t)(n0 + i)) : 0.0;
+                    }
+                } else if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
                 if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
+                if (WPASS && has_next) {         // m2, m1 and beta of the next tile
+                    const int4 na = meta_group(m_nxt, 0);
+#pragma unroll
+                    for (int q = 0; q < NT_PRE; q++) {
+                        const int i = tid + q * nthr;
+                        if (i < na.y - na.x) {
+                            const double *nt = A.nt3 + 3 * (size_t)(na.x + i);
+                            ntm[q][0] = ldg_f64_pinned(nt + 1); ntm[q][1] = ldg_f64_pinned(nt + 2);
+                        }
+                    }
+                    beta_pref = ldg_f64_pinned(A.tile_beta + tn);
+                }
             }
             // A node is corner j of at most one element (leaf octants do not overlap), so within
             // pass j every accumulator is touched by at most one thread: no atomics, fixed order.
@@ -746,7 +833,25 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         if (ne == 0) {                          // a tile of element-less nodes: keep the pipeline fed
             if (tid < nxt_ne) enext = load_entry<MODE>(A, nxt_eb + tid);
             if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
-            if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
+            if (WPASS) {
+#pragma unroll
+                for (int q = 0; q < NT_PRE; q++) {
+                    const int i = tid + q * nthr;
+                    ntv[q][0] = i < nown ? ldg_f64_pinned(A.nt3 + 3 * (size_t)(n0 + i)) : 0.0;
+                }
+            } else if (fuse) load_node_tables(A, n0, nown, tid, nthr, ntv);
+            if (WPASS && has_next) {
+                const int4 na = meta_group(m_nxt, 0);
+#pragma unroll
+                for (int q = 0; q < NT_PRE; q++) {
+                    const int i = tid + q * nthr;
+                    if (i < na.y - na.x) {
+                        const double *nt = A.nt3 + 3 * (size_t)(na.x + i);
+                        ntm[q][0] = ldg_f64_pinned(nt + 1); ntm[q][1] = ldg_f64_pinned(nt + 2);
+                    }
+                }
+                beta_pref = ldg_f64_pinned(A.tile_beta + tn);
+            }
             if (prv_pending) {
                 const int4 md = meta_group(m_prv, 3);
                 if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_prv, tid));
@@ -767,7 +872,20 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             }
         }
         // ---- this tile's own share of the update, in place ---------------------------------------
-        if (fuse) {
+        if (fuse && WPASS) {
+            // the inertia term is in the accumulator already: scale by 1/mass
+#pragma unroll
+            for (int q = 0; q < NT_PRE; q++) {
+                const int i = tid + q * nthr;
+                if (i < nown && ntv[q][0] > 0.0) {
+                    acc[3 * i] *= ntv[q][0]; acc[3 * i + 1] *= ntv[q][0]; acc[3 * i + 2] *= ntv[q][0];
+                }
+            }
+            for (int i = tid + NT_PRE * nthr; i < nown; i += nthr) {
+                const double rm = __ldg(A.nt3 + 3 * (size_t)(n0 + i));
+                if (rm > 0.0) { acc[3 * i] *= rm; acc[3 * i + 1] *= rm; acc[3 * i + 2] *= rm; }
+            }
+        } else if (fuse) {
 #pragma unroll
             for (int q = 0; q < NT_PRE; q++) {
                 const int i = tid + q * nthr;

@@ -32,6 +32,7 @@ FLAG_NO_FUSE = 1
 FLAG_TIMERS = 2
 FLAG_NO_OVERLAP = 4
 FLAG_TAIL_OVERLAP = 8
+FLAG_WPASS = 16
 
 
 class HerculesGpuError(RuntimeError):

@@ -106,6 +106,9 @@ typedef struct hgpu_params {
 #define HGPU_FLAG_TAIL_OVERLAP 8 /* multi-GPU, opt-in: also run the update of the shared nodes and the displacement
                                    exchange on the communication stream, beside the late tiles */
 
+#define HGPU_FLAG_WPASS 16       /* opt-in step-kernel variant (Rayleigh + effective, fused): on tiles of one material
+                                   the damped displacement is formed once per staged node, not per element corner */
+
 typedef struct hgpu_solver hgpu_solver_t;
 
 /* Named per-phase device times in seconds, accumulated with CUDA events under the reference's

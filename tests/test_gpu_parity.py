@@ -357,3 +357,36 @@ def test_device_stations_bit_exact(hb, acc):
         b.stations_record(2)
     assert b.stations_pending() == 2
     s.close(); b.close()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("HGPU_TEST_WPASS") != "1",
+                    reason="HGPU_FLAG_WPASS was written after this round's GPU budget was spent and has not run on "
+                           "hardware yet; set HGPU_TEST_WPASS=1 to run its cases")
+@pytest.mark.parametrize("name", ["graded3_rayleigh_eff", "uniform_rayleigh_eff", "test1_homogeneous"])
+def test_wpass_variant(hb, name):
+    """Opt-in step-kernel variant (w = u1 + beta (u1 - u2) formed once per staged node on tiles of one
+    material): whole runs against the reference's snapshots, and against the default kernel on a
+    two-layer mesh where some tiles straddle the material interface (per-corner path)."""
+    from hercules_b200 import meshgen
+    g = load_golden(name)
+    s, P = make_solver(hb, g, flags=hb.FLAG_WPASS)
+    snaps = snapshots(g)
+    for k in range(P["steps"]):
+        s.step_begin(k)
+        if k in snaps and np.abs(snaps[k]).max() > 0:
+            assert rel_l2(s.fetch_all(hb.TM1), snaps[k]) < REL_TOL_RUN, k
+        s.compute_force_source(g["forces"][k]); s.compute_force_stiffness(); s.compute_force_damping()
+        s.send_force_and_adjust(); s.compute_displacement(); s.send_displacement_and_adjust()
+    s.close()
+    mesh, info = meshgen.uniform_halfspace(64, 64, 64, h=25.0, dt=0.002, layers=((0.0, 4000.0, 2000.0, 2600.0),
+                                                                                 (700.0, 6000.0, 3464.0, 2700.0)))
+    rng = np.random.default_rng(12)
+    u, v = rng.standard_normal((info["N"], 3)), rng.standard_normal((info["N"], 3))
+    out = []
+    for flags in (0, hb.FLAG_WPASS):
+        sol = hb.Solver(mesh, dt=0.002, damping=hb.RAYLEIGH, stiffness=hb.EFFECTIVE, flags=flags)
+        sol.store_all(hb.TM1, u); sol.store_all(hb.TM2, v)
+        sol.run(0, 6)
+        out.append(sol.fetch_all(hb.TM2))
+        sol.close()
+    assert rel_l2(out[1], out[0]) < 1e-13
