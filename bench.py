@@ -417,11 +417,12 @@ def main() -> None:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
         bands = adaptive_bands(n)
         cols = column_grid(world)
-        try:                                        # the host-side mesh tables peak at ~400 B per element
-            import psutil
-            need = 400 * sum(nl * (n // sz) ** 2 for nl, sz in bands)
+        try:                                        # host side: ~350 B per element while the mesh tables and the
+            import psutil                           # tile plan are built, on every rank of this box at once
+            need = 350 * sum(nl * (n // sz) ** 2 for nl, sz in bands) * world
             if psutil.virtual_memory().available < need:
-                raise SystemExit(f"--workload adaptive --edge {n}: needs ~{need >> 30} GiB of host memory for the mesh tables")
+                raise SystemExit(f"--workload adaptive --edge {n} --gpus {world}: needs ~{need >> 30} GiB of host memory for "
+                                 f"the mesh tables of {world} rank(s); use a smaller --edge")
         except ImportError:
             pass
         layers = adaptive_layers(n) if args.damping == "rayleigh" else LAYERS_BKT

@@ -93,6 +93,46 @@ def compute_setab(damping: int, freq: float):
     return 0.0, 0.0
 
 
+_SPREAD8 = None
+_PACK12 = None
+
+
+def _luts():
+    global _SPREAD8, _PACK12
+    if _SPREAD8 is None:
+        b = np.arange(256, dtype=np.uint64)
+        _SPREAD8 = _part1by2(b)                                  # 8 bits -> every third bit of 24
+        c = np.arange(4096, dtype=np.uint64)
+        x, y, z = (_compact1by2(c >> np.uint64(k)).astype(np.uint32) for k in range(3))
+        _PACK12 = x | (y << np.uint32(8)) | (z << np.uint32(16))   # 12 interleaved bits -> 4 bits of x, y, z
+    return _SPREAD8, _PACK12
+
+
+def morton3_fast(ix, iy, iz) -> np.ndarray:
+    """morton3 for coordinates below 2^16, two table look-ups per coordinate."""
+    S, _ = _luts()
+    out = None
+    for sh, v in ((0, ix), (1, iy), (2, iz)):
+        v = np.asarray(v).astype(np.uint32)
+        c = S[v & np.uint32(255)] | (S[v >> np.uint32(8)] << np.uint64(24))
+        c = c << np.uint64(sh) if sh else c
+        out = c if out is None else (out | c)
+    return out
+
+
+def demorton3_fast(codes: np.ndarray):
+    """Inverse of morton3 for codes below 2^36 (12-bit coordinates): x, y, z as int32."""
+    _, P = _luts()
+    x = y = z = None
+    for k in range(3):
+        t = P[(codes >> np.uint64(12 * k)) & np.uint64(4095)]
+        px, py, pz = (t & np.uint32(15)), ((t >> np.uint32(8)) & np.uint32(15)), (t >> np.uint32(16))
+        if k:
+            px, py, pz = px << np.uint32(4 * k), py << np.uint32(4 * k), pz << np.uint32(4 * k)
+        x, y, z = (px, py, pz) if x is None else (x | px, y | py, z | pz)
+    return x.astype(np.int32), y.astype(np.int32), z.astype(np.int32)
+
+
 def _compact1by2(v: np.ndarray) -> np.ndarray:
     v = v.astype(np.uint64) & np.uint64(0x1249249249249249)
     v = (v | (v >> np.uint64(2))) & np.uint64(0x10C30C30C30C30C3)
@@ -217,18 +257,30 @@ def bkt_coefficients(Vp, Vs, use_inf_qk: bool = False) -> np.ndarray:
 def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=None):
     """Per-element quantities of solver_init (psolve.c:3360-3473) for elements whose lowest corner
     is grid point (ex, ey, ez) of the h-grid and whose edge is size * h (size = 1 when None):
-    eTable rows, lumped mass, a, dashpot terms."""
+    eTable rows, lumped mass, a, dashpot terms.  Everything but the dashpots depends on the
+    element's (material layer, size) class only: evaluated once per class with the reference's
+    float / double sequence, then spread over the elements."""
     f32 = np.float32
     nx, ny, nz = dims
     E = ex.size
     sz = 1 if size is None else np.asarray(size, np.int64)
     dt, h = np.float64(dt), np.float64(h)      # a Python float would leave dt2 * edge in float32
     zc = (ez + 0.5 * sz) * h
-    Vp, Vs, rho = np.empty(E, f32), np.empty(E, f32), np.empty(E, f32)
-    for (zt, vp, vs, r) in layers:
-        sel = zc >= zt
-        Vp[sel], Vs[sel], rho[sel] = vp, vs, r
-    edge = np.full(E, h, f32) if size is None else (sz * h).astype(f32)
+    li = np.zeros(E, np.int64)                                    # the last layer whose top is above the centre
+    for k, (zt, _, _, _) in enumerate(layers):
+        li[zc >= zt] = k
+    del zc
+    szs = np.unique(sz) if size is not None else np.array([1], np.int64)
+    si = np.searchsorted(szs, sz) if size is not None else np.zeros(E, np.int64)
+    cls = li * szs.size + si                                      # class of every element
+    del li, si
+    C = len(layers) * szs.size
+    cl, cs = np.divmod(np.arange(C), szs.size)
+    # ---- per class ------------------------------------------------------------------------------
+    Vp, Vs, rho = np.empty(C, f32), np.empty(C, f32), np.empty(C, f32)
+    for k, (_, vp, vs, r) in enumerate(layers):
+        Vp[cl == k], Vs[cl == k], rho[cl == k] = vp, vs, r
+    edge = (szs[cs] * h).astype(f32) if size is not None else np.full(C, h, f32)
     # mu_and_lambda (psolve.c:3236-3272): float products, then double
     mu = (rho * Vs * Vs).astype(np.float64)
     big = Vp > (Vs.astype(np.float64) * thr_vpvs)
@@ -241,7 +293,7 @@ def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_
         Vp[neg] = (f[neg] * Vs[neg].astype(np.float64)).astype(f32)
         lam[neg] = (rho[neg] * Vp[neg] * Vp[neg]).astype(np.float64)
     dt2 = dt * dt
-    eT = np.empty((E, 4))
+    eT = np.empty((C, 4))
     eT[:, 0] = dt2 * edge * mu / 9
     eT[:, 1] = dt2 * edge * lam / 9
     zeta = (f32(10) / Vs).astype(np.float64)            # 10 / edata->Vs is a float division
@@ -252,6 +304,9 @@ def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_
     # lumped mass and dashpots (psolve.c:3411-3473, 5752-5804)
     M = (rho * edge * edge * edge).astype(np.float64) / 8
     scale = (rho * (edge / f32(2)) * (edge / f32(2))).astype(np.float64)
+    # ---- per element ----------------------------------------------------------------------------
+    cVp, cVs, cscale = Vp, Vs, scale
+    Vp, Vs, rho, edge, eT, M, a = Vp[cls], Vs[cls], rho[cls], edge[cls], eT[cls], M[cls], a[cls]
     # absorbing faces: x near/far, y near/far, z far; the top (z near) is free under HALFSPACE
     touch = ((ex == 0, ex + sz == nx), (ey == 0, ey + sz == ny), (np.zeros(E, bool), ez + sz == nz))
     boundary = touch[0][0] | touch[0][1] | touch[1][0] | touch[1][1] | touch[2][1]   # flag != 13
@@ -266,7 +321,7 @@ def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_
                 far = (j >> ax) & 1
                 bits[:, j] |= (touch[ax][far][bi].astype(np.int64) << ax)
         nb = (bits & 1) + ((bits >> 1) & 1) + ((bits >> 2) & 1)
-        Vpb, Vsb, sc = Vp[bi], Vs[bi], scale[bi]
+        Vpb, Vsb, sc = cVp[cls[bi]], cVs[cls[bi]], cscale[cls[bi]]
         vp_plus_2vs = (Vpb + f32(2) * Vsb).astype(np.float64)
         for c in range(3):
             on = ((bits >> c) & 1).astype(bool)
@@ -304,12 +359,21 @@ def _accumulate(nT, nodes8, pr, dt, exact, keep=None):
                 k3 = np.stack([ones, bnd & ones, ones], 1)
                 np.add.at(nT[:, col], idx[k3], val[k3])
         return
-    w8 = None if kf is None else kf.astype(np.float64)
-    def bc(vals):
-        return np.bincount(flat, vals if w8 is None else vals * w8, N)
-    nT[:, 0] += bc(np.repeat(M, 8))
-    base1 = bc(np.repeat(M - dt * a * M, 8))
-    base2 = bc(np.repeat(2 * M - dt * a * M, 8))
+    # grouped sums: per node sum(M) and sum(dt a M) over the incident (element, corner) pairs, one
+    # corner column at a time (no 8 E temporaries); mass_minusaM = sum(M) - sum(dt a M) - dashpots
+    sumM, sumaM = np.zeros(N), np.zeros(N)
+    daM = dt * a * M
+    for j in range(8):
+        idx = np.ascontiguousarray(nodes8[:, j], dtype=np.intp)
+        if keep is None:
+            sumM += np.bincount(idx, M, N)
+            sumaM += np.bincount(idx, daM, N)
+        else:
+            w = keep[:, j].astype(np.float64)
+            sumM += np.bincount(idx, M * w, N)
+            sumaM += np.bincount(idx, daM * w, N)
+    nT[:, 0] += sumM
+    base1, base2 = sumM - sumaM, 2 * sumM - sumaM
     bflat = nodes8[bi].reshape(-1)
     bw = None if keep is None else keep[bi].reshape(-1).astype(np.float64)
     for ax in range(3):
@@ -351,20 +415,40 @@ def uniform_halfspace(nx: int, ny: int, nz: int, h: float, dt: float, freq: floa
         hf = np.zeros((X, Y, Z), bool)
         for j in range(8):
             hf[lx + (j & 1), ly + ((j >> 1) & 1), lz + ((j >> 2) & 1)] = True
-    ix, iy, iz = np.nonzero(hf)
-    gx, gy, gz = ix + x0, iy + y0, iz + z0
-
     def key(g, n):
         return np.where(g == n, 2 * n - 1, 2 * g)
-    norder = np.argsort(morton3(key(gx, nx), key(gy, ny), key(gz, nz)), kind="stable")
-    ix, iy, iz, gx, gy, gz = ix[norder], iy[norder], iz[norder], gx[norder], gy[norder], gz[norder]
-    N = norder.size
-    del norder
-    nrank = np.full((X, Y, Z), -1, np.int32)
-    nrank[ix, iy, iz] = np.arange(N, dtype=np.int32)
+    # harbored nodes in octor's order: Morton codes of the half-step keys, sorted in place and decoded
+    if full:
+        kx, ky, kz = np.meshgrid(key(np.arange(x0, x0 + X, dtype=np.int64), nx), key(np.arange(y0, y0 + Y, dtype=np.int64), ny),
+                                 key(np.arange(z0, z0 + Z, dtype=np.int64), nz), indexing="ij")
+        kx, ky, kz = kx.ravel(), ky.ravel(), kz.ravel()
+    else:
+        ix, iy, iz = np.nonzero(hf)
+        kx, ky, kz = key(ix + x0, nx), key(iy + y0, ny), key(iz + z0, nz)
+        del ix, iy, iz
+    del hf
+    small = 2 * max(nx, ny, nz) < 4096
+    codes = morton3_fast(kx, ky, kz) if small else morton3(kx, ky, kz)
+    del kx, ky, kz
+    codes.sort()
+    if small:
+        kx, ky, kz = demorton3_fast(codes)
+    else:
+        kx, ky, kz = _compact1by2(codes), _compact1by2(codes >> np.uint64(1)), _compact1by2(codes >> np.uint64(2))
+    del codes
+    gx, gy, gz = ((kx + 1) >> 1).astype(np.int64), ((ky + 1) >> 1).astype(np.int64), ((kz + 1) >> 1).astype(np.int64)
+    del kx, ky, kz
+    ix, iy, iz = gx - x0, gy - y0, gz - z0
+    N = gx.size
+    SY, SX = Z, Y * Z
+    nrank = np.full(X * SX, -1, np.int32)
+    nrank[ix * SX + iy * SY + iz] = np.arange(N, dtype=np.int32)
     lnid = np.empty((E, 8), np.int32)
+    base = lx * SX + ly * SY + lz
     for j in range(8):
-        lnid[:, j] = nrank[lx + (j & 1), ly + ((j >> 1) & 1), lz + ((j >> 2) & 1)]
+        lnid[:, j] = nrank.take(base + ((j & 1) * SX + ((j >> 1) & 1) * SY + ((j >> 2) & 1)))
+    del base
+    nrank = nrank.reshape(X, Y, Z)
     # ---- solver tables from my own elements ------------------------------------------------------
     abase, bbase = compute_setab(damping, freq)
     args = ((nx, ny, nz), h, dt, layers, abase, bbase, thr_damping, thr_vpvs)
@@ -508,54 +592,82 @@ def column_regions(nx: int, ny: int, nz: int, world: int):
 
 
 def _graded_leaves(bands, ztop, x0, x1, y0, y1):
-    """Leaves of the banded mesh inside [x0,x1) x [y0,y1), Morton order of the lowest corner."""
-    ex, ey, ez, es = [], [], [], []
+    """Leaves of the banded mesh inside [x0,x1) x [y0,y1), Morton order of the lowest corner: the
+    Morton codes are sorted in place and decoded again (no index sort, no gathers)."""
+    codes = []
+    small = max(x1, y1, ztop[-1]) < 4096
+    enc = morton3_fast if small else morton3
     for (nl, sz), z0 in zip(bands, ztop):
         gx, gy, gz = np.meshgrid(np.arange(x0, x1, sz, dtype=np.int32), np.arange(y0, y1, sz, dtype=np.int32),
                                  np.arange(z0, z0 + nl * sz, sz, dtype=np.int32), indexing="ij")
-        ex.append(gx.ravel()); ey.append(gy.ravel()); ez.append(gz.ravel())
-        es.append(np.full(gx.size, sz, np.int32))
-    ex, ey, ez, es = (np.concatenate(v) for v in (ex, ey, ez, es))
-    o = np.argsort(morton3(ex, ey, ez), kind="stable")
-    return ex[o].astype(np.int64), ey[o].astype(np.int64), ez[o].astype(np.int64), es[o].astype(np.int64)
+        codes.append(enc(gx.ravel(), gy.ravel(), gz.ravel()))
+        del gx, gy, gz
+    codes = np.concatenate(codes)
+    codes.sort()
+    if small:
+        ex, ey, ez = demorton3_fast(codes)
+    else:
+        ex, ey, ez = _compact1by2(codes), _compact1by2(codes >> np.uint64(1)), _compact1by2(codes >> np.uint64(2))
+    del codes
+    size_of_z = np.zeros(ztop[-1] + 1, ex.dtype)
+    for (nl, sz), z0 in zip(bands, ztop):
+        size_of_z[z0:z0 + nl * sz] = sz
+    return ex, ey, ez, size_of_z[ez]
 
 
 def _graded_nodes(bands, ztop, x0, x1, y0, y1, dims):
-    """Mesh nodes inside the closed box [x0,x1] x [y0,y1], in octor's node order."""
+    """Mesh nodes inside the closed box [x0,x1] x [y0,y1], in octor's node order (Z-order of the
+    half-step keys 2 g, or 2 n - 1 on a far domain face): keys sorted in place and decoded."""
     nx, ny, nz = dims
-    px, py, pz = [], [], []
-    for k, ((nl, sz), z0) in enumerate(zip(bands, ztop)):
-        first = z0 if k == 0 else z0 + sz                       # a band's top plane belongs to the finer band above
-        gx, gy, gz = np.meshgrid(np.arange(x0, x1 + 1, sz, dtype=np.int32), np.arange(y0, y1 + 1, sz, dtype=np.int32),
-                                 np.arange(first, z0 + nl * sz + 1, sz, dtype=np.int32), indexing="ij")
-        px.append(gx.ravel()); py.append(gy.ravel()); pz.append(gz.ravel())
-    px, py, pz = (np.concatenate(v) for v in (px, py, pz))
 
     def key(g, n):
         return np.where(g == n, 2 * n - 1, 2 * g)
-    o = np.argsort(morton3(key(px, nx), key(py, ny), key(pz, nz)), kind="stable")
-    return px[o].astype(np.int64), py[o].astype(np.int64), pz[o].astype(np.int64)
+
+    def unkey(k):
+        return (k + 1) >> 1                                     # 2 g -> g, 2 n - 1 -> n
+    codes = []
+    small = 2 * max(nx, ny, nz) < 4096
+    enc = morton3_fast if small else morton3
+    for k, ((nl, sz), z0) in enumerate(zip(bands, ztop)):
+        first = z0 if k == 0 else z0 + sz                       # a band's top plane belongs to the finer band above
+        gx, gy, gz = np.meshgrid(key(np.arange(x0, x1 + 1, sz, dtype=np.int32), nx),
+                                 key(np.arange(y0, y1 + 1, sz, dtype=np.int32), ny),
+                                 key(np.arange(first, z0 + nl * sz + 1, sz, dtype=np.int32), nz), indexing="ij")
+        codes.append(enc(gx.ravel(), gy.ravel(), gz.ravel()))
+        del gx, gy, gz
+    codes = np.concatenate(codes)
+    codes.sort()
+    if small:
+        kx, ky, kz = demorton3_fast(codes)
+    else:
+        kx, ky, kz = _compact1by2(codes), _compact1by2(codes >> np.uint64(1)), _compact1by2(codes >> np.uint64(2))
+    return unkey(kx), unkey(ky), unkey(kz)
 
 
 def _graded_dangling(px, py, pz, bands, ztop):
-    """For nodes of the banded mesh: deps (0 = anchored, 2 = hangs on an edge, 4 = in a face) and the
-    coordinates of the anchors in the reference's list order (descending Z-order)."""
-    deps = np.zeros(px.size, np.int32)
-    ax, ay = np.zeros((px.size, 4), np.int64), np.zeros((px.size, 4), np.int64)
+    """Dangling nodes among the given nodes of the banded mesh: (idx, deps, ax, ay) with idx ascending,
+    deps = 2 (hangs on an edge) or 4 (in a face) and the anchors' x, y ([n][4], same z) in the
+    reference's list order (descending Z-order).  Only nodes on the planes between bands qualify."""
+    I, D, AX, AY = [], [], [], []
     for (_, sf), (_, sc), zp in zip(bands[:-1], bands[1:], ztop[1:]):
-        on = pz == zp
-        ox, oy = on & ((px % sc) != 0), on & ((py % sc) != 0)
+        on = np.nonzero(pz == zp)[0]
+        qx, qy = px[on].astype(np.int64), py[on].astype(np.int64)
+        ox, oy = (qx % sc) != 0, (qy % sc) != 0
         sel = ox | oy
+        on, qx, qy, ox, oy = on[sel], qx[sel], qy[sel], ox[sel], oy[sel]
         both = ox & oy
-        deps[sel] = np.where(both[sel], 4, 2)
-        xh, xl = np.where(ox, px + sf, px), np.where(ox, px - sf, px)
-        yh, yl = np.where(oy, py + sf, py), np.where(oy, py - sf, py)
+        xh, xl = np.where(ox, qx + sf, qx), np.where(ox, qx - sf, qx)
+        yh, yl = np.where(oy, qy + sf, qy), np.where(oy, qy - sf, qy)
         # 2 anchors: (high, low) along the hanging axis; 4 anchors: (xh,yh) (xl,yh) (xh,yl) (xl,yl)
-        ax[sel, 0], ay[sel, 0] = xh[sel], yh[sel]
-        ax[sel, 1], ay[sel, 1] = xl[sel], np.where(both, yh, yl)[sel]
-        ax[both, 2], ay[both, 2] = xh[both], yl[both]
-        ax[both, 3], ay[both, 3] = xl[both], yl[both]
-    return deps, ax, ay
+        ax = np.stack([xh, xl, np.where(both, xh, 0), np.where(both, xl, 0)], 1)
+        ay = np.stack([yh, np.where(both, yh, yl), np.where(both, yl, 0), np.where(both, yl, 0)], 1)
+        I.append(on); D.append(np.where(both, 4, 2).astype(np.int32)); AX.append(ax); AY.append(ay)
+    if not I:
+        z = np.zeros(0, np.int64)
+        return z, z.astype(np.int32), np.zeros((0, 4), np.int64), np.zeros((0, 4), np.int64)
+    I, D, AX, AY = np.concatenate(I), np.concatenate(D), np.concatenate(AX), np.concatenate(AY)
+    o = np.argsort(I, kind="stable")
+    return I[o], D[o], AX[o], AY[o]
 
 
 def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float = 1.0,
@@ -615,11 +727,15 @@ def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float =
     # ---- nodes ------------------------------------------------------------------------------------
     px, py, pz = _graded_nodes(bands, ztop, x0, x1, y0, y1, dims)
     N = px.size
-    nrank = np.full((x1 - x0 + 1, y1 - y0 + 1, nz + 1), -1, np.int32)
-    nrank[px - x0, py - y0, pz] = np.arange(N, dtype=np.int32)
+    SY, SX = nz + 1, (y1 - y0 + 1) * (nz + 1)                    # strides of the dense node look-up
+    nrank = np.full((x1 - x0 + 1) * SX, -1, np.int32)
+    nrank[(px - x0).astype(np.int64) * SX + (py - y0) * SY + pz] = np.arange(N, dtype=np.int32)
     lnid = np.empty((E, 8), np.int32)
+    base = (ex - x0).astype(np.int64) * SX + (ey - y0) * SY + ez
+    es64 = es.astype(np.int64)
     for j in range(8):
-        lnid[:, j] = nrank[ex - x0 + es * (j & 1), ey - y0 + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)]
+        lnid[:, j] = nrank.take(base + es64 * ((j & 1) * SX + ((j >> 1) & 1) * SY + ((j >> 2) & 1)))
+    del base, es64
     assert lnid.min() >= 0
     # ---- ownership --------------------------------------------------------------------------------
     owner = np.full(N, rank, np.int32)
@@ -629,13 +745,16 @@ def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float =
             owner[(qx >= a0) & (qx < a1) & (qy >= b0) & (qy < b1)] = r
     mine = owner == rank
     # ---- dangling nodes ---------------------------------------------------------------------------
-    deps, ax, ay = _graded_dangling(px, py, pz, bands, ztop)
-    dsel = np.nonzero((deps > 0) & mine)[0]                      # ascending lnid
+    didx, ddeps, ax, ay = _graded_dangling(px, py, pz, bands, ztop)
+    deps = np.zeros(N, np.int32)
+    deps[didx] = ddeps
+    om = mine[didx]                                              # the table holds the OWNED dangling nodes
+    dsel, dd, ax, ay = didx[om], ddeps[om], ax[om], ay[om]       # ascending lnid
     dnode = np.full((dsel.size, 6), -1, np.int32)
-    dnode[:, 0], dnode[:, 1] = dsel, deps[dsel]
+    dnode[:, 0], dnode[:, 1] = dsel, dd
     for a in range(4):
-        has = deps[dsel] > a
-        dnode[has, 2 + a] = nrank[ax[dsel[has], a] - x0, ay[dsel[has], a] - y0, pz[dsel[has]]]
+        has = dd > a
+        dnode[has, 2 + a] = nrank.take((ax[has, a] - x0) * SX + (ay[has, a] - y0) * SY + pz[dsel[has]])
     assert (dnode[:, 2:][dnode[:, 2:] != -1] >= 0).all()
     # ---- share lists and schedules ----------------------------------------------------------------
     msg = {k: MsgList() for k in ("dn_c", "dn_s", "an_c", "an_s")}
@@ -686,25 +805,28 @@ def graded_halfspace(nx: int, ny: int, bands, h: float, dt: float, freq: float =
         X0, X1, Y0, Y1 = max(0, x0 - m), min(nx, x1 + m), max(0, y0 - m), min(ny, y1 + m)
         gx, gy, gz, gs = _graded_leaves(bands, ztop, X0, X1, Y0, Y1)
         qx, qy, qz = _graded_nodes(bands, ztop, X0, X1, Y0, Y1, dims)
-        big = np.full((X1 - X0 + 1, Y1 - Y0 + 1, nz + 1), -1, np.int32)
-        big[qx - X0, qy - Y0, qz] = np.arange(qx.size, dtype=np.int32)
+        BY, BX = nz + 1, (Y1 - Y0 + 1) * (nz + 1)
+        big = np.full((X1 - X0 + 1) * BX, -1, np.int32)
+        big[(qx - X0).astype(np.int64) * BX + (qy - Y0) * BY + qz] = np.arange(qx.size, dtype=np.int32)
         l8 = np.empty((gx.size, 8), np.int32)
+        gb, gs64 = (gx - X0).astype(np.int64) * BX + (gy - Y0) * BY + gz, gs.astype(np.int64)
         for j in range(8):
-            l8[:, j] = big[gx - X0 + gs * (j & 1), gy - Y0 + gs * ((j >> 1) & 1), gz + gs * ((j >> 2) & 1)]
+            l8[:, j] = big.take(gb + gs64 * ((j & 1) * BX + ((j >> 1) & 1) * BY + ((j >> 2) & 1)))
+        del gb, gs64
         full = np.zeros((qx.size, 7))
         _accumulate(full, l8, _elem_props(gx, gy, gz, *args, size=gs), dt, exact)
-        dq, bx_, by_ = _graded_dangling(qx, qy, qz, bands, ztop)
-        inside = np.ones(qx.size, bool)
+        qi, dq, bx_, by_ = _graded_dangling(qx, qy, qz, bands, ztop)
+        inside = np.ones(qi.size, bool)
         for a in range(4):                                       # anchors inside the widened box
             inside &= (dq <= a) | ((bx_[:, a] >= X0) & (bx_[:, a] <= X1) & (by_[:, a] >= Y0) & (by_[:, a] <= Y1))
-        ds = np.nonzero((dq > 0) & inside)[0]
-        dn = np.full((ds.size, 6), -1, np.int32)
-        dn[:, 0], dn[:, 1] = ds, dq[ds]
+        qi, dq, bx_, by_ = qi[inside], dq[inside], bx_[inside], by_[inside]
+        dn = np.full((qi.size, 6), -1, np.int32)
+        dn[:, 0], dn[:, 1] = qi, dq
         for a in range(4):
-            has = dq[ds] > a
-            dn[has, 2 + a] = big[bx_[ds[has], a] - X0, by_[ds[has], a] - Y0, qz[ds[has]]]
+            has = dq > a
+            dn[has, 2 + a] = big.take((bx_[has, a] - X0) * BX + (by_[has, a] - Y0) * BY + qz[qi[has]])
         _distribute(full, dn)
-        nT = full[big[px - X0, py - Y0, pz]]
+        nT = full[big.take((px - X0).astype(np.int64) * BX + (py - Y0) * BY + pz)]
     edata = np.zeros((E, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
     if damping == BKT:
