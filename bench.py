@@ -440,7 +440,8 @@ def main() -> None:
     # rank 0 (other ranks carry no source, as in a real run where one rank holds the hypocentre)
     steps_hist = max(args.steps, args.warmup)
     if rank == 0:
-        ce = meshgen.element_index(info, n // 2, n // 2, min(n - 1, int(2000 / H_M)))
+        zsrc = min(n - 1, int(2000 / H_M)) if not adaptive else min(int(2000 / H_M), adaptive_bands(n)[0][0] - 1)
+        ce = meshgen.element_index(info, n // 2, n // 2, zsrc)       # adaptive: inside the band of finest elements
         loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
         tt = (np.arange(steps_hist) + 1) * DT
         ramp = np.minimum(1.0, (tt / 0.1) ** 2)[:, None, None]

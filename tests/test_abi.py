@@ -48,3 +48,25 @@ def test_product_does_not_touch_oracle():
         if p.is_file() and p.suffix in {".py", ".cu", ".cuh", ".cpp", ".h", ""} and p.name != "Makefile":
             txt = p.read_text(errors="ignore")
             assert "hercules_oracle" not in txt and "liboracle" not in txt and "oracle/" not in txt, p
+
+
+@pytest.mark.parametrize("argv", [["--edge", "32"], ["--edge", "64", "--workload", "adaptive"],
+                                  ["--edge", "32", "--damping", "bkt"]])
+def test_bench_builds_its_workload_and_needs_a_gpu(hb, argv, monkeypatch):
+    """bench.py up to the creation of the solver (argument handling, mesh tables, source and station
+    indices) runs on CPU; the solver itself refuses to exist without a CUDA device."""
+    import runpy
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "5", "--warmup", "3"] + argv)
+    fd = __import__("os").dup(1)
+    try:
+        with pytest.raises(hb.HerculesGpuError, match="CUDA"):
+            runpy.run_path(str(ROOT / "bench.py"), run_name="__main__")
+    finally:
+        __import__("os").dup2(fd, 1)          # bench.py points fd 1 at stderr until its JSON line is ready
+        __import__("os").close(fd)
