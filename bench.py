@@ -251,7 +251,9 @@ def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayle
     if info is not None and "bands" in info:
         cx, cy = column_grid(world)
         return {"workload": f"configs[{2 if world == 1 else 3}]: adaptive octree mesh, 3 refinement levels (element edge "
-                            f"{H_M:g}/{2*H_M:g}/{4*H_M:g} m by depth band, Vs 1000/2000/3464 m/s), {info['E']} elements, {info['N']} "
+                            f"{H_M:g}/{2*H_M:g}/{4*H_M:g} m by depth band, "
+                            f"{'Vs 1000/2000/3464 m/s' if damping == 'rayleigh' else 'soft sedimentary column Vs 500-1500 m/s (configs[4] damping model)'}"
+                            f"), {info['E']} elements, {info['N']} "
                             f"nodes, {info['D']} owned hanging (dangling) nodes per GPU on the two 2:1 interfaces, {damping} damping, "
                             "effective stiffness, point source, 5 stations per GPU; mesh tables in octor's layout from "
                             "meshgen.graded_halfspace (bit-exact with the reference's mesher and partition on "
