@@ -170,3 +170,56 @@ def test_uniform_mesh_configs0_domain():
     mesh, info = meshgen.uniform_halfspace(32, 32, 12, h=3125.0, dt=P["dt"], freq=P["freq"], damping=P["damping"], exact=True)
     assert np.array_equal(mesh.elem_lnid, g["elem_lnid"])
     assert np.array_equal(mesh.eTable, g["eTable"]) and np.array_equal(mesh.nTable, g["nTable"])
+
+
+def _pairwise_schedules_match(meshes, infos):
+    """c-lists and s-lists of every pair of ranks name the same nodes (by coordinates) in the same
+    order -- what the halo exchange relies on (psolve.c:4945-5079: the k-th value a messenger packs
+    is the k-th value its counterpart unpacks)."""
+    world = len(meshes)
+    total = 0
+    for side_c, side_s in (("an_c", "an_s"), ("dn_c", "dn_s")):
+        for a in range(world):
+            ca = getattr(meshes[a], side_c)
+            off = np.concatenate([[0], np.cumsum(ca.nodes)]).astype(int)
+            for i, b in enumerate(ca.peer.tolist()):
+                sb = getattr(meshes[b], side_s)
+                j = sb.peer.tolist().index(a)
+                offb = np.concatenate([[0], np.cumsum(sb.nodes)]).astype(int)
+                na, nb_ = ca.mapping[off[i]:off[i + 1]], sb.mapping[offb[j]:offb[j + 1]]
+                assert na.size == nb_.size > 0
+                xa = np.stack([c[na] for c in infos[a]["node_xyz"]], 1)
+                xb = np.stack([c[nb_] for c in infos[b]["node_xyz"]], 1)
+                assert np.array_equal(xa, xb), (side_c, a, b)
+                assert (infos[a]["owner"][na] == b).all() and (infos[b]["owner"][nb_] == b).all()
+                total += na.size
+            # every s-list entry has a c-list counterpart
+            sa = getattr(meshes[a], side_s)
+            for b in sa.peer.tolist():
+                assert a in getattr(meshes[b], side_c).peer.tolist()
+    return total
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_bench_partitions_are_consistent(world):
+    """The weak-scaling domains bench.py builds for N GPUs (uniform: N Morton blocks; adaptive: N
+    columns), at 1/16 of their edge: every node owned exactly once, schedules pairwise consistent."""
+    import bench
+    from hercules_b200 import meshgen
+    n = 16
+    bx, by, bz = bench.block_grid(world)
+    parts = [meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=25.0, dt=0.002, part=(r, world)) for r in range(world)]
+    assert _pairwise_schedules_match([p[0] for p in parts], [p[1] for p in parts]) > 0
+    owned = sum(int((p[1]["owner"] == r).sum()) for r, p in enumerate(parts))
+    assert owned == (n * bx + 1) * (n * by + 1) * (n * bz + 1)
+    assert all(p[1]["E"] == n ** 3 for p in parts)
+    n = 64
+    cx, cy = bench.column_grid(world)
+    parts = [meshgen.graded_halfspace(n * cx, n * cy, bench.adaptive_bands(n), h=25.0, dt=0.002,
+                                      layers=bench.adaptive_layers(n), part=(r, world)) for r in range(world)]
+    assert _pairwise_schedules_match([p[0] for p in parts], [p[1] for p in parts]) > 0
+    whole, winfo = meshgen.graded_halfspace(n * cx, n * cy, bench.adaptive_bands(n), h=25.0, dt=0.002,
+                                            layers=bench.adaptive_layers(n))
+    assert sum(int((p[1]["owner"] == r).sum()) for r, p in enumerate(parts)) == winfo["N"]
+    assert sum(p[1]["D"] for p in parts) == winfo["D"]
+    assert sum(p[1]["E"] for p in parts) == winfo["E"]
