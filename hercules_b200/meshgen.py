@@ -254,7 +254,7 @@ def bkt_coefficients(Vp, Vs, use_inf_qk: bool = False) -> np.ndarray:
     return out
 
 
-def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=None):
+def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=None, mat=None):
     """Per-element quantities of solver_init (psolve.c:3360-3473) for elements whose lowest corner
     is grid point (ex, ey, ez) of the h-grid and whose edge is size * h (size = 1 when None):
     eTable rows, lumped mass, a, dashpot terms.  Everything but the dashpots depends on the
@@ -266,9 +266,12 @@ def _elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_
     sz = 1 if size is None else np.asarray(size, np.int64)
     dt, h = np.float64(dt), np.float64(h)      # a Python float would leave dt2 * edge in float32
     zc = (ez + 0.5 * sz) * h
-    li = np.zeros(E, np.int64)                                    # the last layer whose top is above the centre
-    for k, (zt, _, _, _) in enumerate(layers):
-        li[zc >= zt] = k
+    if mat is not None:                                           # material index given per element
+        li = np.asarray(mat, np.int64)
+    else:
+        li = np.zeros(E, np.int64)                                # the last layer whose top is above the centre
+        for k, (zt, _, _, _) in enumerate(layers):
+            li[zc >= zt] = k
     del zc
     szs = np.unique(sz) if size is not None else np.array([1], np.int64)
     si = np.searchsorted(szs, sz) if size is not None else np.zeros(E, np.int64)

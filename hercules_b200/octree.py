@@ -1,0 +1,208 @@
+"""General single-rank octree meshes in the reference's layout.
+
+meshgen.py covers the two families the benchmarks need (uniform, depth-banded).  This module takes
+ANY material model that is piecewise constant on a grid and does what the reference's mesher does
+with it, vectorised in numpy:
+
+  refine     octor_refinetree + toexpand / vsrule (octor.c:4337, psolve.c:2185, quake_util.c:215):
+             an octant is split while its edge exceeds Vs(centre) / (points-per-wavelength * f_max)
+  balance    octor_balancetree (octor.c:4398-4700): 2:1 across faces AND edges (18 directions, not
+             corners), by prioritised ripple propagation from the finest level up -- the result is
+             the unique smallest balanced refinement, so any algorithm that reaches it agrees
+  extract    octor_extractmesh (octor.c:5268-6645): leaves in Morton order of their lowest corner,
+             nodes = distinct corners in Z-order with the far domain faces pulled in by one tick,
+             elem_t.lnid, and the hanging nodes with their anchors (node_setproperty octor.c:3294,
+             anchor lists octor.c:5863-5991)
+
+and then solver_init's tables through meshgen's helpers.  tests/test_octree.py pins all three stages
+bit for bit on meshes the unmodified reference produced (banded and laterally varying models).
+Coordinates are integers in units of the finest admissible edge h.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import meshgen as mg
+from .solver import HostMesh, MsgList, RAYLEIGH, BKT
+
+_DIRS18 = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1, 0, 1)
+           if 1 <= abs(dx) + abs(dy) + abs(dz) <= 2]
+
+
+def _code(x, y, z):
+    return mg.morton3(x, y, z)
+
+
+def refine(dims, smax: int, vs_of, factor_h: float, smin: int = 1):
+    """Top-down refinement.  dims = (nx, ny, nz) in units of h (multiples of smax, the largest octant
+    that fits the domain's alignment); vs_of(xc, yc, zc) -> Vs at points given in units of h;
+    factor_h = h * ppw * f_max: an octant of edge s is split when s * factor_h > Vs (vsrule).
+    Returns {size: (x, y, z)} of leaves."""
+    nx, ny, nz = dims
+    gx, gy, gz = np.meshgrid(np.arange(0, nx, smax), np.arange(0, ny, smax), np.arange(0, nz, smax), indexing="ij")
+    cur = (gx.ravel().astype(np.int64), gy.ravel().astype(np.int64), gz.ravel().astype(np.int64))
+    leaves, s = {}, smax
+    while cur[0].size:
+        x, y, z = cur
+        split = (s * factor_h > vs_of(x + 0.5 * s, y + 0.5 * s, z + 0.5 * s)) & (s > smin)
+        leaves[s] = (x[~split], y[~split], z[~split])
+        x, y, z = x[split], y[split], z[split]
+        hs = s // 2
+        cur = tuple(np.concatenate([c + hs * ((j >> k) & 1) for j in range(8)]) for k, c in enumerate((x, y, z)))
+        s = hs
+        if s == 0:
+            break
+    return {k: v for k, v in leaves.items() if v[0].size}
+
+
+def balance(leaves: dict, dims):
+    """2:1 balance across faces and edges, finest level first (prioritised ripple propagation)."""
+    nx, ny, nz = dims
+    sets = {s: np.unique(_code(*v)) for s, v in leaves.items()}
+    sizes = sorted(sets)
+    smax = max(sizes)
+    s = min(sizes)
+    while s * 2 < smax:
+        if s in sets and sets[s].size:
+            x, y, z = (mg._compact1by2(sets[s] >> np.uint64(k)) for k in range(3))
+            need = []
+            for dx, dy, dz in _DIRS18:
+                qx, qy, qz = x + dx * s, y + dy * s, z + dz * s
+                ok = (qx >= 0) & (qx < nx) & (qy >= 0) & (qy < ny) & (qz >= 0) & (qz < nz)
+                t = 2 * s
+                need.append(_code((qx[ok] // t) * t, (qy[ok] // t) * t, (qz[ok] // t) * t))
+            need = np.unique(np.concatenate(need))                 # cells of size 2 s that must not lie in a larger leaf
+            t = 4 * s
+            while t <= smax:
+                if t in sets and sets[t].size:
+                    nxq, nyq, nzq = (mg._compact1by2(need >> np.uint64(k)) for k in range(3))
+                    holder = _code((nxq // t) * t, (nyq // t) * t, (nzq // t) * t)
+                    hit = np.isin(holder, sets[t])
+                    if hit.any():
+                        # split every such leaf down to size 2 s along the way to each needed cell
+                        split = np.unique(holder[hit])
+                        sets[t] = np.setdiff1d(sets[t], split, assume_unique=True)
+                        targets = need[hit]
+                        u = t
+                        parents = split
+                        while u > 2 * s:
+                            hu = u // 2
+                            px, py, pz = (mg._compact1by2(parents >> np.uint64(k)) for k in range(3))
+                            kids = np.concatenate([_code(px + hu * (j & 1), py + hu * ((j >> 1) & 1), pz + hu * ((j >> 2) & 1))
+                                                   for j in range(8)])
+                            tx, ty, tz = (mg._compact1by2(targets >> np.uint64(k)) for k in range(3))
+                            on_path = np.unique(_code((tx // hu) * hu, (ty // hu) * hu, (tz // hu) * hu))
+                            if hu > 2 * s:
+                                stay = np.setdiff1d(kids, on_path)
+                                parents = np.intersect1d(kids, on_path)
+                            else:
+                                stay, parents = kids, np.zeros(0, np.uint64)
+                            sets[hu] = np.union1d(sets.get(hu, np.zeros(0, np.uint64)), stay)
+                            u = hu
+                t *= 2
+        s *= 2
+    return {s: tuple(mg._compact1by2(c >> np.uint64(k)) for k in range(3)) for s, c in sets.items() if c.size}
+
+
+def extract(leaves: dict, dims):
+    """Leaf set -> (ex, ey, ez, es) in Morton order, nodes (px, py, pz) in octor's order, lnid [E][8],
+    dnode [D][6]."""
+    nx, ny, nz = dims
+    ex = np.concatenate([v[0] for v in leaves.values()]).astype(np.int64)
+    ey = np.concatenate([v[1] for v in leaves.values()]).astype(np.int64)
+    ez = np.concatenate([v[2] for v in leaves.values()]).astype(np.int64)
+    es = np.concatenate([np.full(v[0].size, s, np.int64) for s, v in leaves.items()])
+    o = np.argsort(_code(ex, ey, ez), kind="stable")
+    ex, ey, ez, es = ex[o], ey[o], ez[o], es[o]
+    E = ex.size
+
+    def key(g, n):
+        return np.where(g == n, 2 * n - 1, 2 * g)
+
+    def ncode(x, y, z):
+        return _code(key(x, nx), key(y, ny), key(z, nz))
+    corner = [(ex + es * (j & 1), ey + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)) for j in range(8)]
+    allc = np.concatenate([ncode(*c) for c in corner])
+    codes, first = np.unique(allc, return_index=True)             # ascending = octor's node order
+    N = codes.size
+    lnid = np.stack([np.searchsorted(codes, ncode(*c)) for c in corner], 1).astype(np.int32)
+    px = np.concatenate([c[0] for c in corner])[first]
+    py = np.concatenate([c[1] for c in corner])[first]
+    pz = np.concatenate([c[2] for c in corner])[first]
+    # smallest leaf that has the node as a corner
+    smin = np.full(N, np.iinfo(np.int64).max, np.int64)
+    for j in range(8):
+        np.minimum.at(smin, lnid[:, j], es)
+    # ---- hanging nodes: a node is dangling when a leaf twice the size of its smallest leaf holds it
+    #      inside an edge (one coordinate off the 2 s grid) or inside a face (two coordinates off) ----
+    lcode = _code(ex, ey, ez)                                    # ascending (Morton order)
+
+    def is_leaf(x, y, z, s):
+        inb = (x >= 0) & (x + s <= nx) & (y >= 0) & (y + s <= ny) & (z >= 0) & (z + s <= nz)
+        c = _code(np.where(inb, x, 0), np.where(inb, y, 0), np.where(inb, z, 0))
+        i = np.minimum(np.searchsorted(lcode, c), E - 1)
+        return inb & (lcode[i] == c) & (es[i] == s)
+    P = np.stack([px, py, pz], 1)
+    t = 2 * smin
+    odd = (P % t[:, None]) != 0                                   # [N][3]
+    k = odd.sum(1)
+    dang = np.zeros(N, bool)
+    for m in range(8):
+        # the candidate leaves of size 2 s around the node: an off-grid coordinate fixes the candidate's
+        # start (s below the node); an on-grid one leaves two choices, the cell below or the cell at the node
+        # (combinations that only differ in an off-grid axis' bit repeat a candidate: harmless)
+        cand = np.empty((N, 3), np.int64)
+        for c in range(3):
+            cand[:, c] = np.where(odd[:, c], P[:, c] - smin, P[:, c] - t if (m >> c) & 1 else P[:, c])
+        dang |= (k >= 1) & (k <= 2) & is_leaf(cand[:, 0], cand[:, 1], cand[:, 2], t)
+    didx = np.nonzero(dang)[0]
+    dnode = np.full((didx.size, 6), -1, np.int32)
+    dnode[:, 0] = didx
+    dnode[:, 1] = np.where(k[didx] == 1, 2, 4)
+    # anchors in descending Z-order: +-s along the off-grid axes, the higher axis (z > y > x) varying slowest
+    for a in range(4):
+        q = P[didx].copy()
+        sm = smin[didx]
+        o_ = odd[didx]
+        # rank the off-grid axes: first (lowest) and second
+        ax1 = np.argmax(o_, axis=1)                               # lowest off-grid axis
+        ax2 = 2 - np.argmax(o_[:, ::-1], axis=1)                  # highest off-grid axis (== ax1 when k == 1)
+        two = k[didx] == 2
+        use = (a < 2) | two
+        s1 = np.where(a % 2 == 0, 1, -1)                          # lowest axis: +, -, +, -
+        s2 = np.where(a < 2, 1, -1)                               # highest axis: +, +, -, -
+        rows = np.arange(didx.size)
+        q[rows, ax1] += s1 * sm
+        q[rows[two], ax2[two]] += s2 * sm[two]
+        ids = np.searchsorted(codes, ncode(q[:, 0], q[:, 1], q[:, 2]))
+        ok = use & (ids < N)
+        ids = np.where(ok, ids, 0)
+        assert (codes[ids[use]] == ncode(q[use, 0], q[use, 1], q[use, 2])).all(), "an anchor is not a mesh node"
+        dnode[use, 2 + a] = ids[use]
+    return (ex, ey, ez, es), (px, py, pz), lnid, dnode
+
+
+def octree_halfspace(dims, smax: int, h: float, dt: float, materials, mat_of, ppw: float, fmax: float,
+                     freq: float | None = None, damping: int = RAYLEIGH, thr_damping: float = 0.05,
+                     thr_vpvs: float = 3.0, vs_min: float = 0.0, exact: bool = False):
+    """Mesh + solver tables for a model that is piecewise constant: materials = [(Vp, Vs, rho)],
+    mat_of(xc, yc, zc) -> material index at points in units of h.  Returns (HostMesh, info)."""
+    vs_tab = np.array([max(m[1], vs_min) for m in materials], np.float64)
+    leaves = balance(refine(dims, smax, lambda x, y, z: vs_tab[mat_of(x, y, z)], h * ppw * fmax), dims)
+    (ex, ey, ez, es), (px, py, pz), lnid, dnode = extract(leaves, dims)
+    abase, bbase = mg.compute_setab(damping, fmax if freq is None else freq)
+    layers = [(0.0, vp, vs, rho) for (vp, vs, rho) in materials]
+    mat = mat_of(ex + 0.5 * es, ey + 0.5 * es, ez + 0.5 * es).astype(np.int64)
+    pr = mg._elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=es, mat=mat)
+    nT = np.zeros((px.size, 7))
+    mg._accumulate(nT, lnid, pr, dt, exact)
+    mg._distribute(nT, dnode)
+    edata = np.zeros((ex.size, 14), np.float32)
+    edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
+    if damping == BKT:
+        edata[:, 4:14] = mg.bkt_coefficients(pr["Vp"], pr["Vs"])
+    K1, K2 = mg.compute_K()
+    mesh = HostMesh(lnid, pr["eT"], nT, dnode, edata, K1, K2, MsgList(), MsgList(), MsgList(), MsgList())
+    info = dict(E=ex.size, N=px.size, D=int(dnode.shape[0]), node_xyz=(px, py, pz), elem_xyz=(ex, ey, ez),
+                elem_size=es, dims=dims, h=h, origin=(0, 0, 0), abase=abase, bbase=bbase)
+    return mesh, info

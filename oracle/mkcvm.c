@@ -13,6 +13,9 @@
  *   Leaves are written at <level>; the region spans nx*ny*nz leaves, so the etree tick is
  *   east_m / (nx << (31-level)) (cvm_query derives it the same way, cvm.c:285).
  *   A leaf takes the material of the last layer whose ztop_m <= depth of the leaf centre.
+ *   MKCVM_BASIN="e0,e1,n0,n1,zbot,vp,vs,rho" (metres, optional): leaves whose centre lies in that box
+ *   (east e0..e1, north n0..n1, depth 0..zbot) take this material instead -- a laterally varying
+ *   model, so that octor refines next to coarser octants sideways as well as downwards.
  */
 #include <fcntl.h>
 #include <stdio.h>
@@ -59,6 +62,14 @@ int main(int argc, char **argv)
         return 2;
     }
     double leaf_m = east_m / nx;
+    double basin[8];
+    int have_basin = 0;
+    if (getenv("MKCVM_BASIN") &&
+        sscanf(getenv("MKCVM_BASIN"), "%lf,%lf,%lf,%lf,%lf,%lf,%lf,%lf", &basin[0], &basin[1], &basin[2], &basin[3],
+               &basin[4], &basin[5], &basin[6], &basin[7]) == 8)
+        have_basin = 1;
+    cvmpayload_t bmat;
+    bmat.Vp = (float)basin[5]; bmat.Vs = (float)basin[6]; bmat.rho = (float)basin[7];
 
     etree_t *ep = etree_open(path, O_CREAT | O_RDWR | O_TRUNC, 64, sizeof(cvmpayload_t), 3);
     if (!ep) { perror("etree_open"); return 1; }
@@ -85,7 +96,9 @@ int main(int argc, char **argv)
         etree_addr_t a;
         a.x = kx * leafticks; a.y = ky * leafticks; a.z = kz * leafticks;
         a.t = 0; a.level = level; a.type = ETREE_LEAF;
-        if (etree_append(ep, a, &mat[li]) != 0) {
+        const double xc = (kx + 0.5) * leaf_m, yc = (ky + 0.5) * leaf_m;      /* etree x = east, y = north */
+        const int inb = have_basin && xc >= basin[0] && xc < basin[1] && yc >= basin[2] && yc < basin[3] && zc < basin[4];
+        if (etree_append(ep, a, inb ? &bmat : &mat[li]) != 0) {
             fprintf(stderr, "mkcvm: append: %s\n", etree_strerror(etree_errno(ep)));
             return 1;
         }

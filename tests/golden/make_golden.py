@@ -68,6 +68,11 @@ CASES = {
                                stiffness="effective", src_xyz=(50000.0, 50000.0, 1000.0),
                                src_strike_dip_rake=(0.0, 90.0, 0.0), src_risetime=0.5, src_moment=1e15,
                                stations=[(50000.0, 50000.0, 0.0), (62000.0, 41000.0, 0.0), (30000.0, 70000.0, 5000.0)]), 1, 100),
+    # laterally varying model: a soft box (Vs 866) in the middle of the top of a stiff half-space, so that octor
+    # refines sideways too -- hanging nodes on x-, y- and z-faces and on edges of all three directions
+    "basin_rayleigh_eff": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
+                                basin=(375.0, 750.0, 250.0, 625.0, 125.0, 1800.0, 866.0, 1800.0), **SRC,
+                                damping="rayleigh", stiffness="effective", end_t=0.06), 1, 20),
     "uniform_rayleigh_eff": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 1, 25),
     "uniform_rayleigh_eff_np3": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 3, 25),
     "uniform_rayleigh_eff_np4": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 4, 25),
