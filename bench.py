@@ -241,6 +241,64 @@ def column_grid(world: int) -> tuple[int, int]:
     return cx, cy
 
 
+BASIN_MATS = ((1500.0, 500.0, 2000.0), (3000.0, 1000.0, 2200.0), (5000.0, 2000.0, 2500.0), (6928.0, 4000.0, 2800.0))
+
+
+def basin_workload(n: int, damping: int):
+    """configs[4] at single-GPU scale: the terashake box (300 x 600 x 84.375 km, tick ratio 32:64:9,
+    examples/terashake/physics.in) with a synthetic CVM-like model -- Vs 500 / 1000 / 2000 / 4000 m/s:
+    sediment basins (Gaussian blobs, fixed seed 20240901) over a depth-layered crust, piecewise constant
+    on cells of 4 h like a material etree -- meshed by hercules_b200.octree exactly as octor would
+    (vs rule, 2:1 balance, hanging nodes in every orientation): four octree levels.
+    n = h-cells along the 300 km edge.  Returns (mesh, info, dt, fmax, h)."""
+    from hercules_b200 import octree
+    dims = (n, 2 * n, 9 * n // 32)
+    if 9 * n % 32 or dims[2] % 4:
+        raise SystemExit("--workload basin needs --edge to be a multiple of 128")
+    g = int(np.gcd.reduce(dims))
+    smax = min(g & -g, 8)
+    h = 300000.0 / n
+    ppw = 8.0
+    fmax = 499.0 / (ppw * h)                       # an octant of edge s h is split while s * 499 > Vs
+    dt = 0.2 * h / 1500.0
+    rng = np.random.default_rng(20240901)
+    blobs = [(rng.uniform(0.1, 0.9) * dims[0], rng.uniform(0.1, 0.9) * dims[1], rng.uniform(0.08, 0.25) * dims[0],
+              rng.uniform(0.05, 0.2) * dims[2]) for _ in range(7)]
+
+    def mat_of(x, y, z):
+        x, y, z = (np.floor(np.asarray(v) / 4) * 4 + 2 for v in (x, y, z))      # the model's own grid: cells of 4 h
+        depth = np.zeros(np.shape(z))
+        for bx_, by_, r, dz in blobs:
+            depth = np.maximum(depth, dz * np.exp(-((x - bx_) ** 2 + (y - by_) ** 2) / r ** 2))
+        return np.where(z < depth, 0, np.where(z < 2 * depth + 0.06 * dims[2], 1,
+                        np.where(z < 0.45 * dims[2], 2, 3))).astype(np.int64)
+    mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
+    info["mat_of"] = mat_of
+    return mesh, info, dt, fmax, h
+
+
+def basin_config(n, info, damping, dt, fmax, h) -> dict:
+    sizes, counts = np.unique(info["elem_size"], return_counts=True)
+    return {"workload": f"configs[4] at single-GPU scale: terashake box 300 x 600 x 84.375 km (32:64:9), synthetic CVM-like model "
+                        f"(sediment basins, seed 20240901, Vs 500/1000/2000/4000 m/s on cells of 4 h, h = {h:g} m), meshed as octor "
+                        f"would (vs rule at {fmax:.4g} Hz, 8 points per wavelength, 2:1 balance): {info['E']} elements on "
+                        f"{len(sizes)} octree levels, {info['N']} nodes, {info['D']} hanging nodes on faces and edges of every "
+                        f"orientation; {damping} damping, effective stiffness, point source, 5 stations",
+            "elements_per_gpu": info["E"], "global_elements": info["E"], "hanging_nodes": info["D"],
+            "elements_by_size": {int(a): int(b) for a, b in zip(sizes, counts)}, "global_grid": list(info["dims"]), "dt": dt,
+            "partition": "single rank", "l2": "inputs larger than L2 for --edge >= 256; no explicit flush"}
+
+
+def containing_element(info: dict, x: float, y: float, z: float) -> int:
+    """Index of the leaf that holds the point (units of h)."""
+    ex, ey, ez = info["elem_xyz"]
+    es = info["elem_size"]
+    hit = np.nonzero((ex <= x) & (x < ex + es) & (ey <= y) & (y < ey + es) & (ez <= z) & (z < ez + es))[0]
+    if hit.size != 1:
+        raise ValueError(f"point ({x},{y},{z}) is not in exactly one element")
+    return int(hit[0])
+
+
 def adaptive_layers(n: int):
     """Vs doubles from band to band, which is what makes octor refine by one level per band."""
     z1, z2 = (n * 11 // 16) * H_M, (n * 11 // 16 + n // 4) * H_M
@@ -367,10 +425,12 @@ def main() -> None:
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
-    ap.add_argument("--workload", default="uniform", choices=["uniform", "adaptive", "graded"],
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "adaptive", "graded", "basin"],
                     help="uniform = configs[1] (the headline); adaptive = configs[2]: 3-level octree mesh with hanging "
                          "nodes, ~100 M elements at --edge 512 (meshgen.graded_halfspace, single GPU); graded = configs[2] "
-                         "at reduced size through the reference's own main and mesher (integration/psolve_gpu)")
+                         "at reduced size through the reference's own main and mesher (integration/psolve_gpu); basin = configs[4] at "
+                         "single-GPU scale: terashake box, synthetic CVM-like basins, four octree levels, BKT by default "
+                         "(hercules_b200.octree; --edge = h-cells along the 300 km side, multiple of 128)")
     ap.add_argument("--graded-freq", type=float, default=20.0, help="--workload graded: meshing frequency (Hz)")
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
@@ -414,7 +474,13 @@ def main() -> None:
     damp = hb.BKT if args.damping == "bkt" else hb.RAYLEIGH
     layers = LAYERS_BKT if args.damping == "bkt" else LAYERS
     adaptive = args.workload == "adaptive"
-    if adaptive:
+    basin = args.workload == "basin"
+    dt_run, freq_run, h_run = DT, FREQ, H_M
+    if basin:
+        if world != 1:
+            raise SystemExit("--workload basin is a single-GPU workload (hercules_b200.octree does not partition)")
+        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp)
+    elif adaptive:
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
         bands = adaptive_bands(n)
@@ -443,22 +509,26 @@ def main() -> None:
     steps_hist = max(args.steps, args.warmup)
     if rank == 0:
         zsrc = min(n - 1, int(2000 / H_M)) if not adaptive else min(int(2000 / H_M), adaptive_bands(n)[0][0] - 1)
-        ce = meshgen.element_index(info, n // 2, n // 2, zsrc)       # adaptive: inside the band of finest elements
+        if basin:
+            ce = containing_element(info, info["dims"][0] * 0.5, info["dims"][1] * 0.5, info["dims"][2] * 0.2)
+        else:
+            ce = meshgen.element_index(info, n // 2, n // 2, zsrc)   # adaptive: inside the band of finest elements
         loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
-        tt = (np.arange(steps_hist) + 1) * DT
-        ramp = np.minimum(1.0, (tt / 0.1) ** 2)[:, None, None]
+        tt = (np.arange(steps_hist) + 1) * dt_run
+        ramp = np.minimum(1.0, (tt / (50 * dt_run)) ** 2)[:, None, None]
         rng = np.random.default_rng(11)
         F_all = np.ascontiguousarray(ramp * 1e9 * rng.standard_normal((1, 8, 3)))
     else:
         loaded, F_all = np.zeros(0, np.int32), np.zeros((steps_hist, 0, 3))
     # 5 stations x 8 nodes on this rank's surface
-    st_elems = [meshgen.element_index(info, int(n * fx), int(n * fy), 0)
+    st_elems = [containing_element(info, info["dims"][0] * fx, info["dims"][1] * fy, 0.0) if basin else
+                meshgen.element_index(info, int(n * fx), int(n * fy), 0)
                 for fx, fy in ((.5, .5), (.6, .6), (.7, .7), (.8, .8), (.9, .9))]
     st_nodes = np.ascontiguousarray(mesh.elem_lnid[st_elems].reshape(-1), np.int32)
     t_mesh = time.time() - t0
 
     t0 = time.time()
-    s = hb.Solver(mesh, dt=DT, damping=damp, stiffness=hb.EFFECTIVE, freq=FREQ,
+    s = hb.Solver(mesh, dt=dt_run, damping=damp, stiffness=hb.EFFECTIVE, freq=freq_run,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
                   tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | (hb.FLAG_NO_OVERLAP if args.no_overlap else 0) |
                   (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0) | (hb.FLAG_WPASS if args.wpass else 0))
@@ -549,7 +619,7 @@ def main() -> None:
 
     # ---- cpu baseline (rank 0, N = 1 only) ---------------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.damping == "rayleigh" and not adaptive:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.damping == "rayleigh" and not adaptive and not basin:
         try:
             r = reference_sample(100)
             cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -566,8 +636,9 @@ def main() -> None:
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",
-                                      args.damping, info if adaptive else None),
+            "config": (basin_config(n, info, args.damping, dt_run, freq_run, h_run) if basin else
+                       workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",
+                                       args.damping, info if adaptive else None)),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "roofline": {"bound": "hbm",
                          "kernel": (("step_kernel<1,false,256,true> (WPASS variant; " if args.wpass else "step_kernel<1,false,256> (") +

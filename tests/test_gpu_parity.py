@@ -21,7 +21,8 @@ REL_TOL_RUN = 1e-10
 SINGLE = ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded2_none_eff", "graded2_mass_eff",
           "graded2_bkt", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
           "test1_homogeneous",      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
-          "graded2_bkt_qk"]         # BKT with finite Qk: shear AND kappa memory variables active
+          "graded2_bkt_qk",         # BKT with finite Qk: shear AND kappa memory variables active
+          "basin_rayleigh_eff"]     # laterally varying model: hanging nodes on faces / edges of every orientation
 
 
 @pytest.fixture(scope="module")
@@ -390,3 +391,39 @@ def test_wpass_variant(hb, name):
         out.append(sol.fetch_all(hb.TM2))
         sol.close()
     assert rel_l2(out[1], out[0]) < 1e-13
+
+
+def test_basin_workload_matches_oracle(hb, oracle):
+    """bench.py --workload basin (configs[4] at single-GPU scale) at --edge 128: 61 k elements on three
+    octree levels from hercules_b200.octree (itself bit-exact with octor on the goldens), 14 k hanging
+    nodes on faces and edges of every orientation, BKT damping with both memory-variable families
+    active: hgpu_run against the oracle stepping the same tables, and the hanging-node constraint."""
+    import bench
+    mesh, info, dt, fmax, h = bench.basin_workload(128, hb.BKT)
+    assert info["D"] > 10000 and len(np.unique(info["elem_size"])) == 3
+    ce = bench.containing_element(info, info["dims"][0] * 0.5, info["dims"][1] * 0.5, info["dims"][2] * 0.2)
+    loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
+    steps = 10
+    rng = np.random.default_rng(6)
+    F = 1e9 * rng.standard_normal((steps, 8, 3))
+    m = oracle.Mesh(mesh.elem_lnid, mesh.eTable, mesh.nTable, mesh.dnode, mesh.edata, mesh.K1, mesh.K2)
+    st = oracle.State(m, bkt=True)
+    u0 = 1e-3 * rng.standard_normal((m.N, 3)); v0 = 1e-3 * rng.standard_normal((m.N, 3))
+    st.tm1[:], st.tm2[:] = u0, v0
+    s = hb.Solver(mesh, dt=dt, damping=hb.BKT, stiffness=hb.EFFECTIVE, freq=fmax, loaded_lnid=loaded)
+    s.store_all(hb.TM1, u0); s.store_all(hb.TM2, v0)
+    s.run(0, steps, F)
+    for k in range(steps):
+        oracle.step(m, st, oracle.BKT, oracle.EFFECTIVE, fmax, dt, loaded, F[k])
+    got = s.fetch_all(hb.TM2)
+    assert rel_l2(got, st.tm2) < REL_TOL_RUN
+    for i, w in enumerate((hb.CONV_SHEAR_1, hb.CONV_SHEAR_2, hb.CONV_KAPPA_1, hb.CONV_KAPPA_2)):
+        assert np.abs(st.conv[i]).max() > 0 and rel_l2(s.fetch_all(w), st.conv[i]) < REL_TOL_RUN, i
+    d = mesh.dnode
+    deps = d[:, 1].astype(np.float64)
+    want = np.zeros((d.shape[0], 3))
+    for j in range(4):
+        sel = d[:, 1] > j
+        want[sel] += got[d[sel, 2 + j]] / deps[sel, None]
+    assert np.array_equal(got[d[:, 0]], want)
+    s.close()

@@ -16,7 +16,8 @@ from conftest import load_golden, params_of, rel_l2
 SINGLE = ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded2_none_eff", "graded2_mass_eff",
           "graded2_bkt", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
           "test1_homogeneous",      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
-          "graded2_bkt_qk"]         # BKT with finite Qk: shear AND kappa memory variables active
+          "graded2_bkt_qk",         # BKT with finite Qk: shear AND kappa memory variables active
+          "basin_rayleigh_eff"]     # laterally varying model: hanging nodes on faces / edges of every orientation
 
 
 def snapshots(g, which="tm1"):
