@@ -120,11 +120,11 @@ def morton3_fast(ix, iy, iz) -> np.ndarray:
     return out
 
 
-def demorton3_fast(codes: np.ndarray):
-    """Inverse of morton3 for codes below 2^36 (12-bit coordinates): x, y, z as int32."""
+def demorton3_fast(codes: np.ndarray, chunks: int = 3):
+    """Inverse of morton3 for codes below 2^(12 chunks) (4 chunks coordinate bits): x, y, z as int32."""
     _, P = _luts()
     x = y = z = None
-    for k in range(3):
+    for k in range(chunks):
         t = P[(codes >> np.uint64(12 * k)) & np.uint64(4095)]
         px, py, pz = (t & np.uint32(15)), ((t >> np.uint32(8)) & np.uint32(15)), (t >> np.uint32(16))
         if k:

@@ -30,7 +30,13 @@ _DIRS18 = [(dx, dy, dz) for dx in (-1, 0, 1) for dy in (-1, 0, 1) for dz in (-1,
 
 
 def _code(x, y, z):
-    return mg.morton3(x, y, z)
+    """Morton code, x the least significant interleaved bit (coordinates below 2^16)."""
+    return mg.morton3_fast(x, y, z)
+
+
+def _decode(codes):
+    x, y, z = mg.demorton3_fast(codes, 4)
+    return x.astype(np.int64), y.astype(np.int64), z.astype(np.int64)
 
 
 def refine(dims, smax: int, vs_of, factor_h: float, smin: int = 1):
@@ -64,7 +70,7 @@ def balance(leaves: dict, dims):
     s = min(sizes)
     while s * 2 < smax:
         if s in sets and sets[s].size:
-            x, y, z = (mg._compact1by2(sets[s] >> np.uint64(k)) for k in range(3))
+            x, y, z = _decode(sets[s])
             need = []
             for dx, dy, dz in _DIRS18:
                 qx, qy, qz = x + dx * s, y + dy * s, z + dz * s
@@ -75,7 +81,7 @@ def balance(leaves: dict, dims):
             t = 4 * s
             while t <= smax:
                 if t in sets and sets[t].size:
-                    nxq, nyq, nzq = (mg._compact1by2(need >> np.uint64(k)) for k in range(3))
+                    nxq, nyq, nzq = _decode(need)
                     holder = _code((nxq // t) * t, (nyq // t) * t, (nzq // t) * t)
                     hit = np.isin(holder, sets[t])
                     if hit.any():
@@ -87,10 +93,10 @@ def balance(leaves: dict, dims):
                         parents = split
                         while u > 2 * s:
                             hu = u // 2
-                            px, py, pz = (mg._compact1by2(parents >> np.uint64(k)) for k in range(3))
+                            px, py, pz = _decode(parents)
                             kids = np.concatenate([_code(px + hu * (j & 1), py + hu * ((j >> 1) & 1), pz + hu * ((j >> 2) & 1))
                                                    for j in range(8)])
-                            tx, ty, tz = (mg._compact1by2(targets >> np.uint64(k)) for k in range(3))
+                            tx, ty, tz = _decode(targets)
                             on_path = np.unique(_code((tx // hu) * hu, (ty // hu) * hu, (tz // hu) * hu))
                             if hu > 2 * s:
                                 stay = np.setdiff1d(kids, on_path)
@@ -101,7 +107,7 @@ def balance(leaves: dict, dims):
                             u = hu
                 t *= 2
         s *= 2
-    return {s: tuple(mg._compact1by2(c >> np.uint64(k)) for k in range(3)) for s, c in sets.items() if c.size}
+    return {s: _decode(c) for s, c in sets.items() if c.size}
 
 
 def extract(leaves: dict, dims):
@@ -122,10 +128,11 @@ def extract(leaves: dict, dims):
     def ncode(x, y, z):
         return _code(key(x, nx), key(y, ny), key(z, nz))
     corner = [(ex + es * (j & 1), ey + es * ((j >> 1) & 1), ez + es * ((j >> 2) & 1)) for j in range(8)]
-    allc = np.concatenate([ncode(*c) for c in corner])
-    codes, first = np.unique(allc, return_index=True)             # ascending = octor's node order
+    ccode = [ncode(*c) for c in corner]
+    codes, first = np.unique(np.concatenate(ccode), return_index=True)     # ascending = octor's node order
     N = codes.size
-    lnid = np.stack([np.searchsorted(codes, ncode(*c)) for c in corner], 1).astype(np.int32)
+    lnid = np.stack([np.searchsorted(codes, c) for c in ccode], 1).astype(np.int32)
+    del ccode
     px = np.concatenate([c[0] for c in corner])[first]
     py = np.concatenate([c[1] for c in corner])[first]
     pz = np.concatenate([c[2] for c in corner])[first]
@@ -199,8 +206,9 @@ def octree_halfspace(dims, smax: int, h: float, dt: float, materials, mat_of, pp
     mg._distribute(nT, dnode)
     edata = np.zeros((ex.size, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"], pr["Vp"], pr["Vs"], pr["rho"]
-    if damping == BKT:
-        edata[:, 4:14] = mg.bkt_coefficients(pr["Vp"], pr["Vs"])
+    if damping == BKT:                                            # one table search per material, not per element
+        mu, first, inv = np.unique(mat, return_index=True, return_inverse=True)
+        edata[:, 4:14] = mg.bkt_coefficients(pr["Vp"][first], pr["Vs"][first])[inv]
     K1, K2 = mg.compute_K()
     mesh = HostMesh(lnid, pr["eT"], nT, dnode, edata, K1, K2, MsgList(), MsgList(), MsgList(), MsgList())
     info = dict(E=ex.size, N=px.size, D=int(dnode.shape[0]), node_xyz=(px, py, pz), elem_xyz=(ex, ey, ez),
