@@ -413,7 +413,8 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--edge", dest="n", type=int, default=256, help="elements per edge per GPU")
+    ap.add_argument("--edge", dest="n", type=int, default=None,
+                    help="elements per edge per GPU (default 256; basin: h-cells along the 300 km side, default 768)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="multi-GPU: exchange after all tiles, one stream")
@@ -435,6 +436,8 @@ def main() -> None:
     ap.add_argument("--halo", default="p2p", choices=["p2p", "nccl"],
                     help="halo transport: peer-memory mailboxes over NVLink (default) or NCCL send/recv")
     args = ap.parse_args()
+    if args.n is None:
+        args.n = 768 if args.workload == "basin" else 256
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
