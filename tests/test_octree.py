@@ -22,6 +22,9 @@ def _leaves_of(g):
 CASES = {   # name: (dims in h, h, smax, cvm leaf in h, materials, basin box or None, layer tops, vs_min, ppw, fmax)
     "basin_rayleigh_eff": ((32, 32, 16), 31.25, 8, 2, [(6000., 3464., 2700.), (1800., 866., 1800.)],
                            (375., 750., 250., 625., 125.), [0.0], 800., 8., 2.5),
+    # the box in a corner of the domain, through its whole depth: hanging nodes ON absorbing faces and domain edges
+    "basin_corner_rayleigh_eff": ((32, 32, 16), 31.25, 8, 2, [(6000., 3464., 2700.), (1800., 866., 1800.)],
+                                  (0., 250., 0., 375., 500.), [0.0], 800., 8., 2.5),
     "graded3_rayleigh_eff": ((32, 32, 16), 31.25, 8, 2, [(1800., 866., 1800.), (3000., 1732., 2000.), (6000., 3464., 2700.)],
                              None, [0.0, 62.5, 250.0], 800., 8., 2.5),
     "graded2_rayleigh_eff": ((16, 16, 8), 62.5, 4, 2, [(3000., 1732., 2000.), (6000., 3464., 2700.)],
@@ -46,8 +49,8 @@ def _mat_of(case):
     return f
 
 
-@pytest.mark.parametrize("name", ["basin_rayleigh_eff", "graded3_rayleigh_eff", "graded2_rayleigh_eff",
-                                  "uniform_rayleigh_eff", "test1_homogeneous"])
+@pytest.mark.parametrize("name", ["basin_rayleigh_eff", "basin_corner_rayleigh_eff", "graded3_rayleigh_eff",
+                                  "graded2_rayleigh_eff", "uniform_rayleigh_eff", "test1_homogeneous"])
 def test_extract_reproduces_octor(name):
     """octor's own leaves in: leaf order, node numbering, elem_t.lnid and the dangling-node table
     (ids, deps, anchors in list order) out, bit for bit."""

@@ -17,7 +17,8 @@ SINGLE = ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded2_none_eff", "
           "graded2_bkt", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
           "test1_homogeneous",      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
           "graded2_bkt_qk",         # BKT with finite Qk: shear AND kappa memory variables active
-          "basin_rayleigh_eff"]     # laterally varying model: hanging nodes on faces / edges of every orientation
+          "basin_rayleigh_eff",     # laterally varying model: hanging nodes on faces / edges of every orientation
+          "basin_corner_rayleigh_eff"]   # ... and on the domain's absorbing faces and edges
 
 
 def snapshots(g, which="tm1"):

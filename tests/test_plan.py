@@ -11,7 +11,8 @@ from conftest import load_golden, rank_view
 
 @pytest.mark.parametrize("tile_nodes", [0, 2, 64, 200])
 @pytest.mark.parametrize("name", ["graded2_rayleigh_eff", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
-                                  "graded3_rayleigh_eff_np4", "basin_rayleigh_eff", "test1_homogeneous"])
+                                  "graded3_rayleigh_eff_np4", "basin_rayleigh_eff", "basin_corner_rayleigh_eff",
+                                  "test1_homogeneous"])
 def test_tile_plan_valid_on_octor_meshes(name, tile_nodes):
     from hercules_b200 import solver
     g = rank_view(load_golden(name), 1)
