@@ -214,3 +214,166 @@ def octree_halfspace(dims, smax: int, h: float, dt: float, materials, mat_of, pp
     info = dict(E=ex.size, N=px.size, D=int(dnode.shape[0]), node_xyz=(px, py, pz), elem_xyz=(ex, ey, ez),
                 elem_size=es, dims=dims, h=h, origin=(0, 0, 0), abase=abase, bbase=bbase)
     return mesh, info
+
+
+# ---- partition ----------------------------------------------------------------------------------------
+
+def bootstrap_size(dims, root: int, world: int) -> int:
+    """octor_newtree (octor.c:4170-4200) pushes the tree down until there are at least 10 tasks per rank,
+    and octor_refinetree splits every one of those data-less task octants once more (toexpand returns 1
+    for a leaf without data, psolve.c:2187): with `world` > 1 ranks no leaf is larger than half a task
+    octant.  root = edge of the root octant in units of h.  Returns that largest admissible leaf edge."""
+    if world == 1:
+        return root
+    s = root
+    while True:
+        tasks = 1
+        for n in dims:
+            tasks *= -(-n // s)
+        if tasks >= 10 * world or s == 1:
+            return max(s // 2, 1)
+        s //= 2
+
+
+def partition(dims, leaves, nodes, lnid, dnode, nT, rank: int, world: int):
+    """One rank's share of a mesh extracted on the whole domain, as octor_partitiontree +
+    octor_extractmesh + schedule_build make it:
+
+    * elements: the rank's block of the Morton-ordered leaf list (octor.c:685-746);
+    * a node belongs to the rank whose block holds the leaf that contains it (far faces pulled in,
+      octor.c:5466-5475); a rank harbors the corners of its elements, every node it owns (neighbours
+      report them, octor.c:5700-5760) and the anchors of the dangling nodes it owns (octor.c:5863-5991);
+    * share list of an owned node: the ranks that harbor it only as such an anchor, highest rank first,
+      then the ranks whose elements touch it in the order this rank discovered them (com_allocpctl);
+    * dnodeTable = the owned dangling nodes; schedules by schedule_build (psolve.c:4705-4863).
+    nT = nTable of the whole mesh: rows are taken over (complete sums, see meshgen.graded_halfspace).
+    Returns (elem range, harbored global node ids, local lnid, local dnode, owner, share, MsgLists)."""
+    nx, ny, nz = dims
+    ex, ey, ez, es = leaves
+    px, py, pz = nodes
+    E, N = ex.size, px.size
+    lcode = _code(ex, ey, ez)
+    holder = np.searchsorted(lcode, _code(np.minimum(px, nx - 1), np.minimum(py, ny - 1), np.minimum(pz, nz - 1)),
+                             side="right") - 1
+    owner = mg.block_owner(holder, world, E).astype(np.int32)
+    lo = [mg.block_low(r, world, E) for r in range(world + 1)]
+    dang = np.zeros(N, bool)
+    dang[dnode[:, 0]] = True
+    # what every rank harbors: corners of its elements (direct), owned nodes, anchors of owned dangling nodes
+    direct = np.zeros((world, N), bool)
+    harbor = np.zeros((world, N), bool)
+    for r in range(world):
+        direct[r, np.unique(lnid[lo[r]:lo[r + 1]])] = True
+        harbor[r] = direct[r] | (owner == r)
+        rows = dnode[owner[dnode[:, 0]] == r]
+        anc = rows[:, 2:6]
+        harbor[r, anc[anc >= 0]] = True
+    H = np.nonzero(harbor[rank])[0]                              # ascending global id = ascending Z-order
+    local = np.full(N, -1, np.int64)
+    local[H] = np.arange(H.size)
+    l_lnid = local[lnid[lo[rank]:lo[rank + 1]]].astype(np.int32)
+    rows = dnode[owner[dnode[:, 0]] == rank]
+    l_dnode = rows.copy()
+    l_dnode[:, 0] = local[rows[:, 0]]
+    for a in range(4):
+        has = rows[:, 2 + a] >= 0
+        l_dnode[has, 2 + a] = local[rows[has, 2 + a]]
+    assert l_lnid.min() >= 0 and (l_dnode[:, 0] >= 0).all()
+    mine = owner[H] == rank
+    anch = ~dang[H]
+
+    def make_list(nd, peers):
+        if nd.size == 0:
+            return MsgList()
+        order = list(dict.fromkeys(peers.tolist()))[::-1]        # messengers are pushed at the head (psolve.c:4733)
+        maps = [nd[peers == p_] for p_ in order]
+        return MsgList(np.array(order, np.int32), np.array([m.size for m in maps], np.int32),
+                       np.concatenate(maps).astype(np.int32))
+    msg = {}
+    ln = np.arange(H.size)
+    nm = ln[~mine]
+    an, dn = nm[anch[nm]], nm[~anch[nm]]
+    msg["an_c"] = make_list(an, owner[H[an]].astype(np.int64))
+    msg["dn_c"] = make_list(dn, owner[H[dn]].astype(np.int64))
+    # share lists of the nodes I own
+    disc = _discovery_order(dims, leaves, lcode, lo, rank, world, harbor, lnid)
+    pos = {p_: i for i, p_ in enumerate(disc)}
+    sh_n, sh_p, sh_k = [], [], []
+    own_l = ln[mine]
+    for s in range(world):
+        if s == rank:
+            continue
+        hit = own_l[harbor[s, H[own_l]]]
+        if not hit.size:
+            continue
+        ind = ~direct[s, H[hit]]                                 # harbored by s only as an anchor: listed first,
+        key = np.where(ind, -1 - s, pos.get(s, world))           # highest rank first; then discovery order
+        sh_n.append(hit); sh_p.append(np.full(hit.size, s, np.int64)); sh_k.append(key.astype(np.int64))
+    if sh_n:
+        sh_n, sh_p, sh_k = np.concatenate(sh_n), np.concatenate(sh_p), np.concatenate(sh_k)
+        o = np.lexsort((sh_k, sh_n))
+        sh_n, sh_p = sh_n[o], sh_p[o]
+        share = np.stack([sh_n, sh_p], 1).astype(np.int32)
+        msg["an_s"] = make_list(sh_n[anch[sh_n]], sh_p[anch[sh_n]])
+        msg["dn_s"] = make_list(sh_n[~anch[sh_n]], sh_p[~anch[sh_n]])
+    else:
+        share = np.zeros((0, 2), np.int32)
+        msg["an_s"], msg["dn_s"] = MsgList(), MsgList()
+    return (lo[rank], lo[rank + 1]), H, l_lnid, l_dnode, owner[H], share, anch, msg
+
+
+def _discovery_order(dims, leaves, lcode, lo, rank, world, harbor, lnid):
+    """Neighbour ranks in the order com_allocpctl (octor.c:2639-2742) first meets them: local leaves in
+    Morton order; per leaf 4 x 4 x 4 probe points half an edge apart, starting half an edge below the
+    lowest corner (z outermost, x innermost); a point outside the domain is skipped; the rank of a point
+    is the rank of the leaf that contains it."""
+    nx, ny, nz = dims
+    ex, ey, ez, es = leaves
+    E = ex.size
+    a, b = lo[rank], lo[rank + 1]
+    # only leaves with a corner that somebody else harbors can see a foreign leaf
+    shared_node = harbor.sum(0) > 1
+    cand = a + np.nonzero(shared_node[lnid[a:b]].any(1))[0]
+    x, y, z, s = ex[cand], ey[cand], ez[cand], es[cand]
+    first = {}
+    for k in range(4):
+        for j in range(4):
+            for i in range(4):
+                # doubled coordinates: 2 x - s + s i
+                p2 = (2 * x - s + s * i, 2 * y - s + s * j, 2 * z - s + s * k)
+                ok = (p2[0] >= 0) & (p2[0] < 2 * nx) & (p2[1] >= 0) & (p2[1] < 2 * ny) & (p2[2] >= 0) & (p2[2] < 2 * nz)
+                if not ok.any():
+                    continue
+                q = tuple(np.where(ok, c // 2, 0) for c in p2)
+                h_ = np.searchsorted(lcode, _code(*q), side="right") - 1
+                r = mg.block_owner(h_, world, E)
+                keyv = (cand - a).astype(np.int64) * 64 + (k * 16 + j * 4 + i)
+                for p_ in np.unique(r[ok]):
+                    if p_ == rank:
+                        continue
+                    m = int(keyv[ok & (r == p_)].min())
+                    if int(p_) not in first or m < first[int(p_)]:
+                        first[int(p_)] = m
+    return [p_ for p_, _ in sorted(first.items(), key=lambda kv: kv[1])]
+
+
+def octree_halfspace_part(dims, smax, h, dt, materials, mat_of, ppw, fmax, rank: int, world: int, root: int | None = None,
+                          **kw):
+    """octree_halfspace on `world` ranks: the whole mesh is built (with the coarsest leaves octor's
+    multi-rank bootstrap allows), then cut.  Returns (HostMesh of the rank, info)."""
+    if root is None:
+        root = 1
+        while root < max(dims):
+            root *= 2
+    smax = min(smax, bootstrap_size(dims, root, world))
+    mesh, info = octree_halfspace(dims, smax, h, dt, materials, mat_of, ppw, fmax, **kw)
+    leaves = (*info["elem_xyz"], info["elem_size"])
+    (a, b), H, l_lnid, l_dnode, owner, share, anch, msg = partition(dims, leaves, info["node_xyz"], mesh.elem_lnid,
+                                                                    mesh.dnode, mesh.nTable, rank, world)
+    part = HostMesh(l_lnid, mesh.eTable[a:b], mesh.nTable[H], l_dnode, mesh.edata[a:b], mesh.K1, mesh.K2,
+                    msg["dn_c"], msg["dn_s"], msg["an_c"], msg["an_s"])
+    pinfo = dict(E=b - a, N=H.size, D=int(l_dnode.shape[0]), node_xyz=tuple(c[H] for c in info["node_xyz"]),
+                 elem_xyz=tuple(c[a:b] for c in info["elem_xyz"]), elem_size=info["elem_size"][a:b],
+                 elem_geid=np.arange(a, b, dtype=np.int64), owner=owner, share=share, anchored=anch, dims=dims, h=h,
+                 rank=rank, nranks=world, etotal=info["E"], origin=(0, 0, 0), gnid=H)
+    return part, pinfo

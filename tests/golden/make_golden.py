@@ -78,6 +78,17 @@ CASES = {
     "basin_corner_rayleigh_eff": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
                                        basin=(0.0, 250.0, 0.0, 375.0, 500.0, 1800.0, 866.0, 1800.0), **SRC,
                                        damping="rayleigh", stiffness="effective", end_t=0.04), 1, 20),
+    # the laterally varying model on 2, 3 and 4 ranks: Morton blocks that cut through refinement levels, hanging
+    # nodes whose anchors belong to other ranks (indirect sharing, octor.c:5800-6000)
+    "basin_rayleigh_eff_np2": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
+                                    basin=(375.0, 750.0, 250.0, 625.0, 125.0, 1800.0, 866.0, 1800.0), **SRC,
+                                    damping="rayleigh", stiffness="effective", end_t=0.06), 2, 20),
+    "basin_rayleigh_eff_np3": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
+                                    basin=(375.0, 750.0, 250.0, 625.0, 125.0, 1800.0, 866.0, 1800.0), **SRC,
+                                    damping="rayleigh", stiffness="effective", end_t=0.06), 3, 20),
+    "basin_rayleigh_eff_np4": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
+                                    basin=(375.0, 750.0, 250.0, 625.0, 125.0, 1800.0, 866.0, 1800.0), **SRC,
+                                    damping="rayleigh", stiffness="effective", end_t=0.06), 4, 20),
     "uniform_rayleigh_eff": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 1, 25),
     "uniform_rayleigh_eff_np3": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 3, 25),
     "uniform_rayleigh_eff_np4": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 4, 25),

@@ -10,6 +10,8 @@ no GPU, that partitioned meshes + schedules + complete nTable rows describe the 
 whole mesh -- the host-side half of the multi-GPU path (the device half is tests/test_multirank_gpu.py).
 
 usage: halo_worker.py <nx> <ny> <bands as n:s,n:s,...> <steps>     env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT
+       halo_worker.py <nx> <ny> basin <steps>      the laterally varying model of tests/golden/basin_rayleigh_eff*.npz
+                                                   through hercules_b200.octree (general mesher and partition)
 """
 import os
 import sys
@@ -23,6 +25,14 @@ sys.path.insert(0, str(ROOT / "oracle"))
 
 H, DT, FREQ = 31.25, 1e-3, 2.5
 LAYERS = [(0, 1800, 866, 1800), (62.5, 3000, 1732, 2000), (250, 6000, 3464, 2700)]
+
+
+BASIN_MATS = [(6000.0, 3464.0, 2700.0), (1800.0, 866.0, 1800.0)]
+
+
+def basin_mat(x, y, z):
+    cx, cy, cz = ((np.floor(np.asarray(v) / 2) + 0.5) * 2 * H for v in (x, y, z))
+    return ((cy >= 375) & (cy < 750) & (cx >= 250) & (cx < 625) & (cz < 125)).astype(np.int64)
 
 
 def exchange(dist, rank, world, snd, rcv, v, contribution):
@@ -46,16 +56,21 @@ def exchange(dist, rank, world, snd, rcv, v, contribution):
 def main():
     import torch.distributed as dist
     import hercules_oracle as ho
-    from hercules_b200 import meshgen
+    from hercules_b200 import meshgen, octree
     nx, ny = int(sys.argv[1]), int(sys.argv[2])
-    bands = tuple(tuple(int(t) for t in b.split(":")) for b in sys.argv[3].split(","))
+    basin = sys.argv[3] == "basin"
+    bands = None if basin else tuple(tuple(int(t) for t in b.split(":")) for b in sys.argv[3].split(","))
     steps = int(sys.argv[4])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     dist.init_process_group("gloo", rank=rank, world_size=world)
     ho.build() if rank == 0 else None
     dist.barrier()
     L = ho.lib()
-    mesh, info = meshgen.graded_halfspace(nx, ny, bands, h=H, dt=DT, freq=FREQ, layers=LAYERS, part=(rank, world))
+    if basin:
+        mesh, info = octree.octree_halfspace_part((nx, ny, 16), 8, H, DT, BASIN_MATS, basin_mat, 8.0, FREQ, rank, world, vs_min=800.0)
+        info["dims"] = (nx, ny, 16)
+    else:
+        mesh, info = meshgen.graded_halfspace(nx, ny, bands, h=H, dt=DT, freq=FREQ, layers=LAYERS, part=(rank, world))
     m = ho.Mesh(mesh.elem_lnid, mesh.eTable, mesh.nTable, mesh.dnode, mesh.edata, mesh.K1, mesh.K2)
     st = ho.State(m)
     px, py, pz = info["node_xyz"]
@@ -65,7 +80,8 @@ def main():
     # the element loads it (a rank's loaded nodes are those of its own source elements)
     sx, sy, sz = nx // 2 - 1, ny // 2 - 1, 1
     ex, ey, ez = info["elem_xyz"]
-    hit = np.nonzero((ex == sx) & (ey == sy) & (ez == sz))[0]
+    es_ = info["elem_size"]
+    hit = np.nonzero((ex <= sx) & (sx < ex + es_) & (ey <= sy) & (sy < ey + es_) & (ez <= sz) & (sz < ez + es_))[0]
     rng = np.random.default_rng(7)
     F = 1e9 * rng.standard_normal((steps, 8, 3))
     loaded = np.sort(mesh.elem_lnid[hit[0]]).astype(np.int32) if hit.size else np.zeros(0, np.int32)
@@ -86,13 +102,19 @@ def main():
     res = [None] * world
     dist.all_gather_object(res, (gkey, st.tm2, info["owner"] == rank))
     if rank == 0:
-        whole, winfo = meshgen.graded_halfspace(nx, ny, bands, h=H, dt=DT, freq=FREQ, layers=LAYERS)
+        if basin:
+            # the whole mesh must be the one the ranks cut: same coarsest-leaf limit as the multi-rank bootstrap
+            smax = min(8, octree.bootstrap_size((nx, ny, 16), 32, world))
+            whole, winfo = octree.octree_halfspace((nx, ny, 16), smax, H, DT, BASIN_MATS, basin_mat, 8.0, FREQ, vs_min=800.0)
+        else:
+            whole, winfo = meshgen.graded_halfspace(nx, ny, bands, h=H, dt=DT, freq=FREQ, layers=LAYERS)
         wm = ho.Mesh(whole.elem_lnid, whole.eTable, whole.nTable, whole.dnode, whole.edata, whole.K1, whole.K2)
         ws = ho.State(wm)
         wx, wy, wz = winfo["node_xyz"]
         wkey = (wx * (ny + 1) + wy) * (nz + 1) + wz
         wex, wey, wez = winfo["elem_xyz"]
-        we = int(np.nonzero((wex == sx) & (wey == sy) & (wez == sz))[0][0])
+        wes = winfo["elem_size"]
+        we = int(np.nonzero((wex <= sx) & (sx < wex + wes) & (wey <= sy) & (sy < wey + wes) & (wez <= sz) & (sz < wez + wes))[0][0])
         wl = np.sort(whole.elem_lnid[we]).astype(np.int32)
         wo = np.argsort(whole.elem_lnid[we])
         for k in range(steps):

@@ -113,3 +113,45 @@ def test_balance_is_two_to_one_across_faces_and_edges():
         for a, b, c in zip(x, y, z):
             before[a:a + s, b:b + s, c:c + s] = s
     assert (size <= before).all() and (size < before).any()
+
+
+PART_CASES = {   # golden: (single-rank case it derives from, ranks)
+    "basin_rayleigh_eff_np2": ("basin_rayleigh_eff", 2), "basin_rayleigh_eff_np3": ("basin_rayleigh_eff", 3),
+    "basin_rayleigh_eff_np4": ("basin_rayleigh_eff", 4), "graded3_rayleigh_eff_np2": ("graded3_rayleigh_eff", 2),
+    "graded3_rayleigh_eff_np4": ("graded3_rayleigh_eff", 4),
+}
+
+
+@pytest.mark.parametrize("name", sorted(PART_CASES))
+def test_partition_reproduces_octor(name):
+    """The general partition against multi-rank runs of the unmodified reference: Morton blocks that cut
+    through refinement levels, the coarser-leaf limit of octor's multi-rank bootstrap (4 ranks: no 125 m
+    octants), nodes harbored only because they are owned or anchor an owned dangling node, share lists
+    with indirect sharers first, owned dangling tables, all four schedules -- bit for bit; nTable rows of
+    owned nodes to rounding (complete sums)."""
+    from conftest import rank_view
+    from hercules_b200 import octree
+    base, world = PART_CASES[name]
+    dims, h, smax, cl, mats, box, tops, vs_min, ppw, fmax = CASES[base]
+    g = load_golden(name)
+    for r in range(world):
+        v = rank_view(g, r); P = params_of(v)
+        mesh, info = octree.octree_halfspace_part(dims, smax, h, P["dt"], mats, _mat_of(CASES[base]), ppw, fmax, r, world,
+                                                  freq=P["freq"], damping=P["damping"], vs_min=vs_min, exact=True)
+        assert np.array_equal(info["elem_geid"], v["elem_geid"])
+        assert mesh.elem_lnid.shape == v["elem_lnid"].shape and np.array_equal(mesh.elem_lnid, v["elem_lnid"])
+        tick = int(v["node_ticks"][v["node_ticks"] > 0].min()) // int(np.stack(info["node_xyz"], 1)[np.stack(info["node_xyz"], 1) > 0].min())
+        assert np.array_equal(np.stack(info["node_xyz"], 1) * tick, v["node_ticks"])
+        ismine = v["node_flags"][:, 0].astype(bool)
+        assert np.array_equal(info["owner"] == r, ismine)
+        assert np.array_equal(info["owner"][~ismine], v["node_owner"][~ismine])
+        assert np.array_equal(info["anchored"], v["node_flags"][:, 1].astype(bool))
+        assert info["share"].shape == v["node_share"].shape and np.array_equal(info["share"], v["node_share"])
+        assert mesh.dnode.shape == v["dnode"].shape and np.array_equal(mesh.dnode, v["dnode"])
+        for side in ("dn_c", "dn_s", "an_c", "an_s"):
+            ml = getattr(mesh, side)
+            hdr = np.stack([ml.peer, ml.nodes], 1).reshape(-1, 2)
+            assert np.array_equal(hdr, v[side + "_hdr"].reshape(-1, 2)), (r, side)
+            assert np.array_equal(ml.mapping, v[side + "_map"]), (r, side)
+        assert np.array_equal(mesh.eTable, v["eTable"])
+        assert np.allclose(mesh.nTable[ismine], v["nTable"][ismine], rtol=2e-15, atol=0)
