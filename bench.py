@@ -244,7 +244,7 @@ def column_grid(world: int) -> tuple[int, int]:
 BASIN_MATS = ((1500.0, 500.0, 2000.0), (3000.0, 1000.0, 2200.0), (5000.0, 2000.0, 2500.0), (6928.0, 4000.0, 2800.0))
 
 
-def basin_workload(n: int, damping: int):
+def basin_workload(n: int, damping: int, part=None):
     """configs[4] at single-GPU scale: the terashake box (300 x 600 x 84.375 km, tick ratio 32:64:9,
     examples/terashake/physics.in) with a synthetic CVM-like model -- Vs 500 / 1000 / 2000 / 4000 m/s:
     sediment basins (Gaussian blobs, fixed seed 20240901) over a depth-layered crust, piecewise constant
@@ -272,7 +272,12 @@ def basin_workload(n: int, damping: int):
             depth = np.maximum(depth, dz * np.exp(-((x - bx_) ** 2 + (y - by_) ** 2) / r ** 2))
         return np.where(z < depth, 0, np.where(z < 2 * depth + 0.06 * dims[2], 1,
                         np.where(z < 0.45 * dims[2], 2, 3))).astype(np.int64)
-    mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
+    if part is None or part[1] == 1:
+        mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
+    else:
+        # every rank builds the whole mesh and takes its Morton block (octree.partition); fine up to a few 10 M elements
+        mesh, info = octree.octree_halfspace_part(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, part[0], part[1],
+                                                  damping=damping)
     info["mat_of"] = mat_of
     return mesh, info, dt, fmax, h
 
@@ -284,16 +289,21 @@ def basin_config(n, info, damping, dt, fmax, h) -> dict:
                         f"would (vs rule at {fmax:.4g} Hz, 8 points per wavelength, 2:1 balance): {info['E']} elements on "
                         f"{len(sizes)} octree levels, {info['N']} nodes, {info['D']} hanging nodes on faces and edges of every "
                         f"orientation; {damping} damping, effective stiffness, point source, 5 stations",
-            "elements_per_gpu": info["E"], "global_elements": info["E"], "hanging_nodes": info["D"],
+            "elements_per_gpu": info["E"], "global_elements": info.get("etotal", info["E"]), "hanging_nodes": info["D"],
             "elements_by_size": {int(a): int(b) for a, b in zip(sizes, counts)}, "global_grid": list(info["dims"]), "dt": dt,
-            "partition": "single rank", "l2": "inputs larger than L2 for --edge >= 256; no explicit flush"}
+            "partition": ("single rank" if info.get("nranks", 1) == 1 else
+                          f"{info['nranks']} blocks of the Morton-ordered leaf list (octree.partition, as octor_partitiontree cuts "
+                          "it); ONE mesh over all GPUs: strong scaling"),
+            "l2": "inputs larger than L2 for --edge >= 768; no explicit flush"}
 
 
-def containing_element(info: dict, x: float, y: float, z: float) -> int:
-    """Index of the leaf that holds the point (units of h)."""
+def containing_element(info: dict, x: float, y: float, z: float, missing_ok: bool = False) -> int:
+    """Index of the (local) leaf that holds the point (units of h); -1 if it is on another rank and missing_ok."""
     ex, ey, ez = info["elem_xyz"]
     es = info["elem_size"]
     hit = np.nonzero((ex <= x) & (x < ex + es) & (ey <= y) & (y < ey + es) & (ez <= z) & (z < ez + es))[0]
+    if hit.size == 0 and missing_ok:
+        return -1
     if hit.size != 1:
         raise ValueError(f"point ({x},{y},{z}) is not in exactly one element")
     return int(hit[0])
@@ -480,9 +490,7 @@ def main() -> None:
     basin = args.workload == "basin"
     dt_run, freq_run, h_run = DT, FREQ, H_M
     if basin:
-        if world != 1:
-            raise SystemExit("--workload basin is a single-GPU workload (hercules_b200.octree does not partition)")
-        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp)
+        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp, (rank, world))
     elif adaptive:
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
@@ -507,26 +515,30 @@ def main() -> None:
         mesh, info = meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=H_M, dt=DT, freq=FREQ,
                                                layers=layers, part=(rank, world), damping=damp)
     E, N = info["E"], info["N"]
+    e_global = info["etotal"] if basin and world > 1 else E * world      # basin on N GPUs cuts ONE mesh: strong scaling
     # point source: the 8 nodes of the element at the centre of this rank's block, 2000 m deep on
     # rank 0 (other ranks carry no source, as in a real run where one rank holds the hypocentre)
     steps_hist = max(args.steps, args.warmup)
-    if rank == 0:
+    if rank == 0 or basin:                  # basin: the rank that holds the hypocentre's element
         zsrc = min(n - 1, int(2000 / H_M)) if not adaptive else min(int(2000 / H_M), adaptive_bands(n)[0][0] - 1)
         if basin:
-            ce = containing_element(info, info["dims"][0] * 0.5, info["dims"][1] * 0.5, info["dims"][2] * 0.2)
+            ce = containing_element(info, info["dims"][0] * 0.5, info["dims"][1] * 0.5, info["dims"][2] * 0.2, missing_ok=world > 1)
         else:
             ce = meshgen.element_index(info, n // 2, n // 2, zsrc)   # adaptive: inside the band of finest elements
-        loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
+        loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32) if ce >= 0 else np.zeros(0, np.int32)
         tt = (np.arange(steps_hist) + 1) * dt_run
         ramp = np.minimum(1.0, (tt / (50 * dt_run)) ** 2)[:, None, None]
         rng = np.random.default_rng(11)
         F_all = np.ascontiguousarray(ramp * 1e9 * rng.standard_normal((1, 8, 3)))
+        if not loaded.size:
+            F_all = np.zeros((steps_hist, 0, 3))
     else:
         loaded, F_all = np.zeros(0, np.int32), np.zeros((steps_hist, 0, 3))
     # 5 stations x 8 nodes on this rank's surface
-    st_elems = [containing_element(info, info["dims"][0] * fx, info["dims"][1] * fy, 0.0) if basin else
+    st_elems = [containing_element(info, info["dims"][0] * fx, info["dims"][1] * fy, 0.0, missing_ok=world > 1) if basin else
                 meshgen.element_index(info, int(n * fx), int(n * fy), 0)
                 for fx, fy in ((.5, .5), (.6, .6), (.7, .7), (.8, .8), (.9, .9))]
+    st_elems = [e for e in st_elems if e >= 0] or [0]
     st_nodes = np.ascontiguousarray(mesh.elem_lnid[st_elems].reshape(-1), np.int32)
     t_mesh = time.time() - t0
 
@@ -610,7 +622,7 @@ def main() -> None:
         e2e_s = max_over_ranks(time.perf_counter() - t0)
         if not np.isfinite(final.a).all():
             raise SystemExit("non-finite displacements after the end-to-end run")
-        e2e = {"value": E * world * args.steps / e2e_s, "unit": UNIT,
+        e2e = {"value": e_global * args.steps / e2e_s, "unit": UNIT,
                "h2d_bytes_per_step": int(24 * loaded.size),
                "d2h_bytes_per_step": int(24 * st_nodes.size + final.a.nbytes / args.steps),
                "ms_per_step": 1e3 * e2e_s / args.steps,
@@ -635,9 +647,10 @@ def main() -> None:
         k_s = fused_s / max(tile_launches, 1)
         achieved = alg_bytes / k_s / 1e9 if k_s > 0 else None
         line = {
-            "metric": METRIC, "value": E * world * args.steps / dev_s, "unit": UNIT,
+            "metric": METRIC, "value": e_global * args.steps / dev_s, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
+            "scaling": "strong" if basin and world > 1 else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": (basin_config(n, info, args.damping, dt_run, freq_run, h_run) if basin else
                        workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",
