@@ -53,14 +53,19 @@ def _run(name, world, transport, devices, flags=0, timeout=180):
 FLAGS = [0, 4] + ([8] if os.environ.get("HGPU_TEST_TAIL_OVERLAP") == "1" else [])
 
 
+# the basin cases: Morton blocks cutting through refinement levels of a laterally varying model -- hanging nodes
+# whose anchors belong to another rank, nodes a rank harbors without having an element on them
+CASES = [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3),
+         ("graded2_bkt_np2", 2), ("basin_rayleigh_eff_np2", 2), ("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4)]
+
+
 def _ngpu():
     import torch
     return torch.cuda.device_count()
 
 
 @pytest.mark.parametrize("flags", FLAGS)
-@pytest.mark.parametrize("name,world", [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4),
-                                        ("uniform_rayleigh_eff_np3", 3), ("graded2_bkt_np2", 2)])
+@pytest.mark.parametrize("name,world", CASES)
 def test_nccl_halo_matches_reference_ranks(name, world, flags):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs for NCCL (one rank per device)")
@@ -68,8 +73,7 @@ def test_nccl_halo_matches_reference_ranks(name, world, flags):
 
 
 @pytest.mark.parametrize("flags", FLAGS)
-@pytest.mark.parametrize("name,world", [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4),
-                                        ("uniform_rayleigh_eff_np3", 3), ("graded2_bkt_np2", 2)])
+@pytest.mark.parametrize("name,world", CASES)
 def test_p2p_halo_matches_reference_ranks(name, world, flags):
     """Peer-memory transport; ranks are spread over the GPUs present (all on one device on a
     single-GPU box: the mailboxes are then IPC mappings of the same device's memory)."""

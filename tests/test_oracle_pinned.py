@@ -168,3 +168,66 @@ def test_effective_equals_conventional(oracle):
     L.ho_addforce_effective(E, ln, et, t1, a)
     L.ho_addforce_conventional(E, ln, et, K1.reshape(-1), K2.reshape(-1), t1, b)
     assert rel_l2(a, b) < 1e-14
+
+
+@pytest.mark.parametrize("name,world", [("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4),
+                                        ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3)])
+def test_multirank_oracle_bit_exact(oracle, name, world):
+    """The oracle's per-rank arithmetic plus the four schedule_senddata exchanges of a step (psolve.c:4036-4154,
+    4945-5079; contribution = += in the receiver's messenger order, sharing = overwrite), carried out in
+    process on the tables every rank of the unmodified reference held, reproduces every rank's tm1 snapshots
+    bit for bit -- the multi-rank half of the oracle, and the expectation tests/test_multirank_gpu.py holds the
+    CUDA path to."""
+    from conftest import rank_view
+    from hercules_b200.solver import MsgList
+    ho = oracle
+    g = load_golden(name)
+    V = [rank_view(g, r) for r in range(world)]
+    P = params_of(V[0])
+    M = [ho.Mesh.from_dump(v) for v in V]
+    S = [ho.State(m) for m in M]
+    ML = [{k: MsgList.from_dump(v[k + "_hdr"], v[k + "_map"]) for k in ("dn_c", "dn_s", "an_c", "an_s")} for v in V]
+    L = ho.lib()
+
+    def exchange(snd, rcv, arrs, contribution):
+        out = []
+        for r in range(world):
+            m = ML[r][snd]
+            off = np.concatenate([[0], np.cumsum(m.nodes)]).astype(int)
+            out.append({int(p): arrs[r][m.mapping[off[i]:off[i + 1]]].copy() for i, p in enumerate(m.peer)})
+        for r in range(world):
+            m = ML[r][rcv]
+            off = 0
+            for p, n in zip(m.peer.tolist(), m.nodes.tolist()):
+                rows = m.mapping[off:off + n]
+                if contribution:
+                    arrs[r][rows] += out[p][r]
+                else:
+                    arrs[r][rows] = out[p][r]
+                off += n
+    snaps = [{int(k[len("tm1_step"):]): a for k, a in v.items() if k.startswith("tm1_step")} for v in V]
+    checked = 0
+    with np.errstate(all="ignore"):            # a node harbored without mass holds 0/0 until its owner's value arrives
+        for k in range(P["steps"]):
+            for r in range(world):
+                S[r].tm1, S[r].tm2 = S[r].tm2, S[r].tm1
+                if k in snaps[r]:
+                    assert np.array_equal(S[r].tm1, snaps[r][k]), (r, k)
+                    checked += int(np.abs(snaps[r][k]).max() > 0)
+                ll = V[r]["loaded_lnid"]
+                if ll.size:
+                    L.ho_addforce_s(ll.size, np.ascontiguousarray(ll, np.int32),
+                                    np.ascontiguousarray(V[r]["forces"][k]).reshape(-1), P["dt2"], S[r].force.reshape(-1))
+                ho.add_forces(M[r], S[r], P["damping"], P["stiffness"], P["freq"], P["dt"])
+            exchange("dn_c", "dn_s", [s.force for s in S], True)
+            for r in range(world):
+                L.ho_compute_adjust(M[r].D, M[r].dnode.reshape(-1), S[r].force.reshape(-1), 3, ho.DISTRIBUTION)
+            exchange("an_c", "an_s", [s.force for s in S], True)
+            for r in range(world):
+                L.ho_compute_displacement(M[r].N, M[r].nTable.reshape(-1), S[r].tm1.reshape(-1), S[r].tm2.reshape(-1), None,
+                                          S[r].force.reshape(-1))
+            exchange("an_s", "an_c", [s.tm2 for s in S], False)
+            for r in range(world):
+                L.ho_compute_adjust(M[r].D, M[r].dnode.reshape(-1), S[r].tm2.reshape(-1), 3, ho.ASSIGNMENT)
+            exchange("dn_s", "dn_c", [s.tm2 for s in S], False)
+    assert checked >= world
