@@ -153,15 +153,22 @@ def extract(leaves: dict, dims):
     t = 2 * smin
     odd = (P % t[:, None]) != 0                                   # [N][3]
     k = odd.sum(1)
-    dang = np.zeros(N, bool)
+    # a node that is a corner of 8 leaves is interior and anchored (node_setproperty, octor.c:3316): only
+    # the others -- interfaces between levels and the domain boundary -- need the look-ups
+    touches = np.bincount(lnid.reshape(-1), minlength=N)
+    ci = np.nonzero((touches < 8) & (k >= 1) & (k <= 2))[0]
+    Pc, sc, tc, oc = P[ci], smin[ci], t[ci], odd[ci]
+    hit = np.zeros(ci.size, bool)
     for m in range(8):
         # the candidate leaves of size 2 s around the node: an off-grid coordinate fixes the candidate's
         # start (s below the node); an on-grid one leaves two choices, the cell below or the cell at the node
         # (combinations that only differ in an off-grid axis' bit repeat a candidate: harmless)
-        cand = np.empty((N, 3), np.int64)
+        cand = np.empty((ci.size, 3), np.int64)
         for c in range(3):
-            cand[:, c] = np.where(odd[:, c], P[:, c] - smin, P[:, c] - t if (m >> c) & 1 else P[:, c])
-        dang |= (k >= 1) & (k <= 2) & is_leaf(cand[:, 0], cand[:, 1], cand[:, 2], t)
+            cand[:, c] = np.where(oc[:, c], Pc[:, c] - sc, Pc[:, c] - tc if (m >> c) & 1 else Pc[:, c])
+        hit |= is_leaf(cand[:, 0], cand[:, 1], cand[:, 2], tc)
+    dang = np.zeros(N, bool)
+    dang[ci[hit]] = True
     didx = np.nonzero(dang)[0]
     dnode = np.full((didx.size, 6), -1, np.int32)
     dnode[:, 0] = didx
