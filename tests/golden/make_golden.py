@@ -89,6 +89,9 @@ CASES = {
     "basin_rayleigh_eff_np4": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 6000, 3464, 2700)],
                                     basin=(375.0, 750.0, 250.0, 625.0, 125.0, 1800.0, 866.0, 1800.0), **SRC,
                                     damping="rayleigh", stiffness="effective", end_t=0.06), 4, 20),
+    "basin_bkt_np3": (dict(cvm_level=4, cvm_n=(16, 16, 8), vs_min=800, freq_hz=2.5, layers=[(0, 4800, 1600, 2300)],
+                           basin=(375.0, 750.0, 250.0, 625.0, 125.0, 2400.0, 800.0, 2000.0), **SRC,
+                           damping="bkt", stiffness="effective", end_t=0.06, use_infinite_qk="no"), 3, 20),
     "uniform_rayleigh_eff": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 1, 25),
     "uniform_rayleigh_eff_np3": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 3, 25),
     "uniform_rayleigh_eff_np4": (dict(**SRC, damping="rayleigh", stiffness="effective", end_t=0.05), 4, 25),

@@ -56,7 +56,8 @@ FLAGS = [0, 4] + ([8] if os.environ.get("HGPU_TEST_TAIL_OVERLAP") == "1" else []
 # the basin cases: Morton blocks cutting through refinement levels of a laterally varying model -- hanging nodes
 # whose anchors belong to another rank, nodes a rank harbors without having an element on them
 CASES = [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3),
-         ("graded2_bkt_np2", 2), ("basin_rayleigh_eff_np2", 2), ("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4)]
+         ("graded2_bkt_np2", 2), ("basin_rayleigh_eff_np2", 2), ("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4),
+         ("basin_bkt_np3", 3)]
 
 
 def _ngpu():

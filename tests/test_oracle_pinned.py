@@ -171,7 +171,8 @@ def test_effective_equals_conventional(oracle):
 
 
 @pytest.mark.parametrize("name,world", [("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4),
-                                        ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3)])
+                                        ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3),
+                                        ("graded2_bkt_np2", 2), ("basin_bkt_np3", 3)])
 def test_multirank_oracle_bit_exact(oracle, name, world):
     """The oracle's per-rank arithmetic plus the four schedule_senddata exchanges of a step (psolve.c:4036-4154,
     4945-5079; contribution = += in the receiver's messenger order, sharing = overwrite), carried out in
@@ -185,7 +186,7 @@ def test_multirank_oracle_bit_exact(oracle, name, world):
     V = [rank_view(g, r) for r in range(world)]
     P = params_of(V[0])
     M = [ho.Mesh.from_dump(v) for v in V]
-    S = [ho.State(m) for m in M]
+    S = [ho.State(m, bkt=(P["damping"] == ho.BKT)) for m in M]
     ML = [{k: MsgList.from_dump(v[k + "_hdr"], v[k + "_map"]) for k in ("dn_c", "dn_s", "an_c", "an_s")} for v in V]
     L = ho.lib()
 
