@@ -317,8 +317,8 @@ def adaptive_layers(n: int):
 
 def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh", info: dict | None = None) -> dict:
     if info is not None and "bands" in info:
-        cx, cy = column_grid(world)
-        return {"workload": f"configs[{2 if world == 1 else 3}]: adaptive octree mesh, 3 refinement levels (element edge "
+        cx, cy = column_grid(8 if info.get("strong") else world)
+        return {"workload": f"configs[{3 if world > 1 or info.get('strong') else 2}]: adaptive octree mesh, 3 refinement levels (element edge "
                             f"{H_M:g}/{2*H_M:g}/{4*H_M:g} m by depth band, "
                             f"{'Vs 1000/2000/3464 m/s' if damping == 'rayleigh' else 'soft sedimentary column Vs 500-1500 m/s (configs[4] damping model)'}"
                             f"), {info['E']} elements, {info['N']} "
@@ -328,7 +328,8 @@ def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayle
                             "tests/golden/graded{2,3}_*.npz)",
                 "elements_per_gpu": info["E"], "global_elements": info["etotal"], "hanging_nodes": info["D"],
                 "global_grid": [n * cx, n * cy, n], "bands": [list(b) for b in info["bands"]], "dt": DT,
-                "partition": (f"{world} columns of {n}^3 h-cells = octor's equal blocks of the Morton-ordered leaf list, halo "
+                "partition": ((f"{world} columns" if not info.get("strong") else f"8 columns cut into {world} blocks") +
+                              f" of {n}^3 h-cells = octor's equal blocks of the Morton-ordered leaf list, halo "
                               f"exchange over {halo} overlapped with interior tiles" if world > 1 else "single rank"),
                 "l2": "inputs larger than L2; no explicit flush"}
     bx, by, bz = block_grid(world)
@@ -431,6 +432,9 @@ def main() -> None:
     ap.add_argument("--tail-overlap", action="store_true",
                     help="multi-GPU, opt-in: shared-node update + displacement exchange beside the late tiles "
                          "(HGPU_FLAG_TAIL_OVERLAP)")
+    ap.add_argument("--strong", action="store_true",
+                    help="--workload adaptive: cut ONE mesh of 8 columns (4 x 2; --edge 384: 326 M elements, configs[3]'s ~400 M) "
+                         "over the GPUs instead of one column per GPU")
     ap.add_argument("--wpass", action="store_true",
                     help="opt-in step-kernel variant (HGPU_FLAG_WPASS): damped displacement formed once per staged node")
     ap.add_argument("--tile-nodes", type=int, default=0)
@@ -495,10 +499,12 @@ def main() -> None:
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
         bands = adaptive_bands(n)
-        cols = column_grid(world)
+        if args.strong and world not in (1, 2, 4, 8):
+            raise SystemExit("--strong cuts 8 columns: 1, 2, 4 or 8 GPUs")
+        cols = column_grid(8 if args.strong else world)
         try:                                        # host side: ~350 B per element while the mesh tables and the
             import psutil                           # tile plan are built, on every rank of this box at once
-            need = 350 * sum(nl * (n // sz) ** 2 for nl, sz in bands) * world
+            need = 350 * sum(nl * (n // sz) ** 2 for nl, sz in bands) * (8 if args.strong else world)
             if psutil.virtual_memory().available < need:
                 raise SystemExit(f"--workload adaptive --edge {n} --gpus {world}: needs ~{need >> 30} GiB of host memory for "
                                  f"the mesh tables of {world} rank(s); use a smaller --edge")
@@ -509,13 +515,15 @@ def main() -> None:
         # of the Morton-ordered leaf list are then exactly the columns (meshgen.column_regions)
         mesh, info = meshgen.graded_halfspace(n * cols[0], n * cols[1], bands, h=H_M, dt=DT, freq=FREQ, layers=layers,
                                               damping=damp, part=(rank, world) if world > 1 else None)
+        info["strong"] = bool(args.strong)
     elif world == 1:
         mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
     else:
         mesh, info = meshgen.uniform_halfspace(n * bx, n * by, n * bz, h=H_M, dt=DT, freq=FREQ,
                                                layers=layers, part=(rank, world), damping=damp)
     E, N = info["E"], info["N"]
-    e_global = info["etotal"] if basin and world > 1 else E * world      # basin on N GPUs cuts ONE mesh: strong scaling
+    strong = (basin and world > 1) or (adaptive and args.strong)       # ONE mesh cut over the GPUs
+    e_global = info["etotal"] if strong else E * world
     # point source: the 8 nodes of the element at the centre of this rank's block, 2000 m deep on
     # rank 0 (other ranks carry no source, as in a real run where one rank holds the hypocentre)
     steps_hist = max(args.steps, args.warmup)
@@ -650,7 +658,7 @@ def main() -> None:
             "metric": METRIC, "value": e_global * args.steps / dev_s, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s / args.steps, "higher_is_better": True,
-            "scaling": "strong" if basin and world > 1 else "weak",
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": (basin_config(n, info, args.damping, dt_run, freq_run, h_run) if basin else
                        workload_config(world, n, "peer-memory mailboxes (NVLink P2P)" if args.halo == "p2p" else "NCCL send/recv",

@@ -51,7 +51,8 @@ def test_product_does_not_touch_oracle():
 
 
 @pytest.mark.parametrize("argv", [["--edge", "32"], ["--edge", "64", "--workload", "adaptive"],
-                                  ["--edge", "32", "--damping", "bkt"]])
+                                  ["--edge", "32", "--damping", "bkt"], ["--edge", "64", "--workload", "adaptive", "--strong"],
+                                  ["--edge", "128", "--workload", "basin", "--damping", "bkt"]])
 def test_bench_builds_its_workload_and_needs_a_gpu(hb, argv, monkeypatch):
     """bench.py up to the creation of the solver (argument handling, mesh tables, source and station
     indices) runs on CPU; the solver itself refuses to exist without a CUDA device."""

@@ -223,3 +223,21 @@ def test_bench_partitions_are_consistent(world):
     assert sum(int((p[1]["owner"] == r).sum()) for r, p in enumerate(parts)) == winfo["N"]
     assert sum(p[1]["D"] for p in parts) == winfo["D"]
     assert sum(p[1]["E"] for p in parts) == winfo["E"]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_bench_strong_scaling_partitions_are_consistent(world):
+    """bench.py --workload adaptive --strong: ONE mesh of 8 columns cut over 2 or 4 ranks (2 x 2 and 2 x 1
+    columns per rank), at 1/6 of its edge."""
+    import bench
+    from hercules_b200 import meshgen
+    n = 64
+    cx, cy = bench.column_grid(8)
+    parts = [meshgen.graded_halfspace(n * cx, n * cy, bench.adaptive_bands(n), h=25.0, dt=0.002,
+                                      layers=bench.adaptive_layers(n), part=(r, world)) for r in range(world)]
+    assert _pairwise_schedules_match([p[0] for p in parts], [p[1] for p in parts]) > 0
+    assert len({p[1]["E"] for p in parts}) == 1 and sum(p[1]["E"] for p in parts) == parts[0][1]["etotal"]
+    whole = (n * cx + 1) * (n * cy + 1)            # nodes per fine plane; every node owned exactly once:
+    owned = sum(int((p[1]["owner"] == r).sum()) for r, p in enumerate(parts))
+    _, winfo = meshgen.graded_halfspace(n * cx, n * cy, bench.adaptive_bands(n), h=25.0, dt=0.002, layers=bench.adaptive_layers(n))
+    assert owned == winfo["N"] and whole > 0
