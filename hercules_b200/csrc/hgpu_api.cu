@@ -108,6 +108,9 @@ struct MsgList {
     PushSeg *d_push = nullptr;                     // [2 parities][messenger]
     PullSeg *d_pull = nullptr;                     // [2 parities][messenger]
     unsigned long long seq_out = 0, seq_in = 0;
+    // contribution receive side in ONE launch: node-major CSR over all messengers (list order kept)
+    int32_t csr_nodes = 0;
+    int32_t *d_csr_node = nullptr, *d_csr_off = nullptr, *d_csr_src[2] = {nullptr, nullptr};
 };
 
 enum ForceState { F_CLEAN = 0, F_PENDING = 1, F_MATERIALIZED = 2, F_FUSED_DONE = 3 };
@@ -175,7 +178,9 @@ struct hgpu_solver {
     char *mailbox = nullptr; size_t mailbox_bytes = 0;
     std::vector<void *> peer_base;           // [rank] IPC-mapped mailbox of each peer
     bool p2p_ready = false;
-    int *d_p2p_err = nullptr;
+    bool cooperative = true;                 // step kernels are launched cooperatively (HGPU_COOPERATIVE=0 turns it off)
+    int *h_err = nullptr, *d_err = nullptr;  // error word: page-locked host memory mapped into the device
+    long long p2p_timeout_cycles = 0;        // halo wait bound in SM cycles (HGPU_P2P_TIMEOUT_S, default 600 s; 0 = none)
     // step state
     bool want_stiff = false, want_damp = false;
     ForceState fstate = F_CLEAN;
@@ -271,6 +276,17 @@ struct PhaseTimer {
     }
     ~PhaseTimer() { if (p) cudaEventRecord(p->b, st); }
 };
+
+// The device error word (mapped host memory), read after a synchronisation of the solver's streams.
+static int check_device_error(hgpu_solver *s)
+{
+    const int e = s->h_err ? *(volatile int *)s->h_err : 0;
+    if (e == 1) return fail(HGPU_ECOMM, "halo exchange timed out waiting for a peer (HGPU_P2P_TIMEOUT_S); "
+                                        "nothing was applied from that exchange on: the state is not valid");
+    if (e == 2) return fail(HGPU_ECUDA, "a tile waited for its lower tiles for too long (a CTA of the step kernel "
+                                        "was not resident?); the state is not valid");
+    return HGPU_OK;
+}
 
 extern "C" const char *hgpu_last_error(void) { return g_err.c_str(); }
 extern "C" int hgpu_abi_version(void) { return HGPU_ABI_VERSION; }
@@ -369,6 +385,17 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                     s->dev, prop.major, prop.minor);
     }
     TRYCU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TRYCU(cudaHostAlloc((void **)&s->h_err, sizeof(int), cudaHostAllocMapped));
+    *s->h_err = 0;
+    TRYCU(cudaHostGetDevicePointer((void **)&s->d_err, s->h_err, 0));
+    {
+        // halo wait bound: host-side skew between ranks (a peer writing a checkpoint or a 4D frame)
+        // is legitimate and unbounded in principle, so the default is long; 0 waits for ever
+        double secs = 600.0;
+        const char *tenv = getenv("HGPU_P2P_TIMEOUT_S");
+        if (tenv) secs = atof(tenv);
+        s->p2p_timeout_cycles = secs > 0 ? (long long)(secs * 1e3 * (double)prop.clockRate) : 0;
+    }
 
     const int32_t E = s->E, N = s->N, D = s->D;
     const size_t n3 = 3 * (size_t)N;
@@ -605,11 +632,23 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaFuncSetAttribute(step_kernel<1, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<3, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
 #undef SETUP
+        if (s->block == 256 && (params->flags & HGPU_FLAG_WPASS)) {
+            int occ_w = 0;
+            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, step_kernel<1, false, 256, true>, 256, s->smem_u2));
+            occ = std::min(occ, occ_w);
+        }
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
+        {
+            int coop = 0;
+            TRYCU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, s->dev));
+            const char *cenv = getenv("HGPU_COOPERATIVE");
+            s->cooperative = coop != 0 && !(cenv && atoi(cenv) == 0);
+        }
         s->ctas_per_sm = occ;
         // every CTA of a launch must be resident: a tile's finish phase spins on flags raised by
         // CTAs of the same launch
@@ -634,7 +673,11 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
 template <typename T>
 static void dfree(T *&p) { if (p) cudaFree(p); p = nullptr; }
 
-static void free_msglist(MsgList &m) { dfree(m.d_map); dfree(m.d_send); dfree(m.d_recv); dfree(m.d_counters); dfree(m.d_push); dfree(m.d_pull); }
+static void free_msglist(MsgList &m)
+{
+    dfree(m.d_map); dfree(m.d_send); dfree(m.d_recv); dfree(m.d_counters); dfree(m.d_push); dfree(m.d_pull);
+    dfree(m.d_csr_node); dfree(m.d_csr_off); dfree(m.d_csr_src[0]); dfree(m.d_csr_src[1]);
+}
 
 extern "C" int hgpu_finalize(hgpu_solver_t *s)
 {
@@ -643,7 +686,8 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (size_t r = 0; r < s->peer_base.size(); r++) if (s->peer_base[r]) cudaIpcCloseMemHandle(s->peer_base[r]);
-    dfree(s->mailbox); dfree(s->d_p2p_err);
+    dfree(s->mailbox);
+    if (s->h_err) cudaFreeHost(s->h_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
     dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta);
@@ -700,6 +744,7 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.conv = s->conv; A.ent_bkt = s->t_ent_bkt;
     A.rmax = 2.0 * M_PI * s->P.freq * s->P.dt;                     // damping.c:114, 234
     A.tile_beta = s->t_beta;
+    A.err = s->d_err;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt;
     const int mode = tm.bkt ? 3 : tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
@@ -707,24 +752,39 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
     const int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin), B = s->block;
     if (begin == 0) A.epoch = ++s->epoch;       // a new pass over the tiles (a split pass shares one epoch)
-#define LAUNCH(T)                                                                                \
-    do {                                                                                         \
-        if (dense) {                                                                             \
-            if (mode == 0)      step_kernel<0, true, T><<<G, B, s->smem_nou2, s->stream>>>(A);   \
-            else if (mode == 1) step_kernel<1, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
-            else                step_kernel<2, true, T><<<G, B, s->smem_u2, s->stream>>>(A);     \
-        } else if (mode == 3) {                                                                  \
-            step_kernel<3, false, T><<<G, B, s->smem_u2, s->stream>>>(A);                        \
-        } else {                                                                                 \
-            if (mode == 0)      step_kernel<0, false, T><<<G, B, s->smem_nou2, s->stream>>>(A);  \
-            else if (mode == 1) step_kernel<1, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
-            else                step_kernel<2, false, T><<<G, B, s->smem_u2, s->stream>>>(A);    \
-        }                                                                                        \
+    // Cooperative launch: a tile's finish spins on flags raised by other CTAs of the same launch, so
+    // every CTA must be resident -- the driver then either co-schedules the whole grid or fails the launch
+    // (it never starts a part of it), whatever else shares the device.
+    const void *fn = nullptr;
+    size_t smem = (size_t)s->smem_u2;
+#define PICK(T)                                                                                   \
+    do {                                                                                          \
+        if (dense) {                                                                              \
+            if (mode == 0)      { fn = (const void *)step_kernel<0, true, T>; smem = (size_t)s->smem_nou2; } \
+            else if (mode == 1) fn = (const void *)step_kernel<1, true, T>;                       \
+            else                fn = (const void *)step_kernel<2, true, T>;                       \
+        } else if (mode == 3) {                                                                   \
+            fn = (const void *)step_kernel<3, false, T>;                                          \
+        } else {                                                                                  \
+            if (mode == 0)      { fn = (const void *)step_kernel<0, false, T>; smem = (size_t)s->smem_nou2; } \
+            else if (mode == 1) fn = (const void *)step_kernel<1, false, T>;                      \
+            else                fn = (const void *)step_kernel<2, false, T>;                      \
+        }                                                                                         \
     } while (0)
     if (fuse && !dense && mode == 1 && B == 256 && (s->P.flags & HGPU_FLAG_WPASS))
-        step_kernel<1, false, 256, true><<<G, B, s->smem_u2, s->stream>>>(A);      // opt-in variant, see hgpu_kernels.cuh
-    else if (B == 384) LAUNCH(384); else LAUNCH(256);
-#undef LAUNCH
+        fn = (const void *)step_kernel<1, false, 256, true>;       // opt-in variant, see hgpu_kernels.cuh
+    else if (B == 384) PICK(384); else PICK(256);
+#undef PICK
+    {
+        void *kargs[] = {(void *)&A};
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)G); cfg.blockDim = dim3((unsigned)B);
+        cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
+        cfg.attrs = at; cfg.numAttrs = s->cooperative ? 1 : 0;
+        CK(cudaLaunchKernelExC(&cfg, fn, kargs));
+    }
     CK(cudaGetLastError());
     s->tm.launches++;
     return HGPU_OK;
@@ -841,17 +901,20 @@ static int exchange(hgpu_solver *s, MsgList &c, MsgList &sl, double *v, bool con
             s->tm.launches++;
         }
         if (nrcv && contribution) {
-            for (int i = 0; i < nrcv; i++) {
-                const int gx = std::max(1, std::min(max_gx, (3 * rcv.nodes[i] + 255) / 256));
-                p2p_pull_kernel<<<dim3(gx, 1), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv + i, v, si, 1, s->d_p2p_err);
-                CK(cudaGetLastError());
-                s->tm.launches++;
-            }
+            // every messenger of the list in ONE launch: a thread owns a (node, component) and adds the
+            // node's contributions in messenger order (psolve.c:5035-5073)
+            PullAll pa{rcv.d_csr_node, rcv.d_csr_off, rcv.d_csr_src[si & 1],
+                       (const double *)(s->mailbox + rcv.mb_data_off),
+                       (const unsigned long long *)(s->mailbox + rcv.mb_flag_off), rcv.csr_nodes, nrcv, (int32_t)(si & 1)};
+            const int gx = std::max(1, std::min(max_gx, (3 * rcv.csr_nodes + 255) / 256));
+            p2p_pull_all_kernel<<<gx, 256, 0, st>>>(pa, v, si, s->d_err, s->p2p_timeout_cycles);
+            CK(cudaGetLastError());
+            s->tm.launches++;
         } else if (nrcv) {
             int maxn = 1;
             for (int32_t n : rcv.nodes) maxn = std::max(maxn, n);
             const int gx = std::max(1, std::min(max_gx, (3 * maxn + 255) / 256));
-            p2p_pull_kernel<<<dim3(gx, nrcv), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv, v, si, 0, s->d_p2p_err);
+            p2p_pull_kernel<<<dim3(gx, nrcv), 256, 0, st>>>(rcv.d_pull + (si & 1) * nrcv, v, si, 0, s->d_err, s->p2p_timeout_cycles);
             CK(cudaGetLastError());
             s->tm.launches++;
         }
@@ -1146,7 +1209,7 @@ extern "C" int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out)
     if (is_conv(which) && (rc = conv_convert(s, which, 1))) return rc;
     CK(cudaMemcpyAsync(out, p, cnt * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    return HGPU_OK;
+    return check_device_error(s);       // never hand out a field computed past a failed exchange
 }
 
 extern "C" int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in)
@@ -1191,7 +1254,7 @@ extern "C" int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *
     s->tm.launches++;
     CK(cudaMemcpyAsync(out, s->d_fetch_out, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
     CK(cudaStreamSynchronize(s->stream));
-    return HGPU_OK;
+    return check_device_error(s);
 }
 
 // ---- stations on the device ---------------------------------------------------------
@@ -1255,7 +1318,7 @@ extern "C" int hgpu_stations_drain(hgpu_solver_t *s, double *rows, int32_t *step
     if (steps) memcpy(steps, s->st_steps.data(), (size_t)s->st_count * sizeof(int32_t));
     *nrows = s->st_count;
     s->st_count = 0; s->st_steps.clear();
-    return HGPU_OK;
+    return check_device_error(s);
 }
 
 extern "C" void *hgpu_host_alloc(size_t bytes)
@@ -1274,12 +1337,7 @@ extern "C" int hgpu_sync(hgpu_solver_t *s)
     CK(cudaSetDevice(s->dev));
     CK(cudaStreamSynchronize(s->stream));
     if (s->comm_stream) CK(cudaStreamSynchronize(s->comm_stream));
-    if (s->d_p2p_err) {
-        int e = 0;
-        CK(cudaMemcpy(&e, s->d_p2p_err, sizeof e, cudaMemcpyDeviceToHost));
-        if (e) return fail(HGPU_ECOMM, "halo exchange timed out waiting for a peer");
-    }
-    return HGPU_OK;
+    return check_device_error(s);
 }
 
 extern "C" int hgpu_get_timers(hgpu_solver_t *s, hgpu_timers_t *out)
@@ -1507,8 +1565,29 @@ extern "C" int hgpu_comm_p2p_connect(hgpu_solver_t *s, const void *const *blobs,
         if ((rc = upload(s, &m->d_push, push.data(), push.size()))) return rc;
         if ((rc = upload(s, &m->d_pull, pull.data(), pull.size()))) return rc;
     }
-    if ((rc = dalloc(s, &s->d_p2p_err, 1))) return rc;
-    CK(cudaMemset(s->d_p2p_err, 0, sizeof(int)));
+    // contribution lists (the s-lists receive): node-major CSR over all messengers, list order kept
+    for (MsgList *m : {&s->dn_s, &s->an_s}) {
+        std::vector<std::pair<int32_t, int32_t>> ent;      // (node, position in the concatenated mapping)
+        std::vector<int32_t> map_host((size_t)m->total);
+        if (m->total) CK(cudaMemcpy(map_host.data(), m->d_map, (size_t)m->total * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int32_t k = 0; k < m->total; k++) ent.emplace_back(map_host[k], k);
+        std::stable_sort(ent.begin(), ent.end(), [](const std::pair<int32_t, int32_t> &a, const std::pair<int32_t, int32_t> &b) { return a.first < b.first; });
+        std::vector<int32_t> node, off, src0, src1;
+        std::vector<int32_t> msg_of((size_t)m->total);
+        for (size_t i = 0; i < m->peer.size(); i++) for (int32_t k = m->off[i]; k < m->off[i + 1]; k++) msg_of[k] = (int32_t)i;
+        for (size_t j = 0; j < ent.size(); j++) {
+            if (j == 0 || ent[j].first != ent[j - 1].first) { node.push_back(ent[j].first); off.push_back((int32_t)j); }
+            const int32_t k = ent[j].second, i = msg_of[k], idx = k - m->off[i];
+            src0.push_back(2 * m->off[i] + idx);
+            src1.push_back(2 * m->off[i] + m->nodes[i] + idx);
+        }
+        off.push_back((int32_t)ent.size());
+        m->csr_nodes = (int32_t)node.size();
+        if ((rc = upload(s, &m->d_csr_node, node.data(), node.size()))) return rc;
+        if ((rc = upload(s, &m->d_csr_off, off.data(), off.size()))) return rc;
+        if ((rc = upload(s, &m->d_csr_src[0], src0.data(), src0.size()))) return rc;
+        if ((rc = upload(s, &m->d_csr_src[1], src1.data(), src1.size()))) return rc;
+    }
     if ((rc = make_comm_stream(s))) return rc;
     s->p2p_ready = true;
     return HGPU_OK;

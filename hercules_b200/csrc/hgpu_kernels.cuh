@@ -164,6 +164,7 @@ struct StepArgs {
     // WPASS variant (MODE 1): per tile, in processing order, the Rayleigh ratio beta = c3/c1 shared by
     // all its entries, or NaN when they differ (the tile then takes the per-corner path)
     const double *__restrict__ tile_beta;
+    int *err;                           // error word (mapped host memory), see report_error
 };
 
 // BKT memory variables (psolve.h:308-311: conv_shear_1, conv_shear_2, conv_kappa_1, conv_kappa_2,
@@ -180,6 +181,15 @@ __host__ __device__ __forceinline__ size_t conv_index(size_t entry, int k)
 constexpr int META_INTS = 16;           // per tile
 constexpr int META_RING = 8;
 constexpr int CAP_DEPS = 64;            // dependency ids staged in shared memory per tile
+constexpr long long WAIT_DEPS_CYCLES = 40000000000LL;   // ~20 s at 1.9 GHz
+
+// The error word lives in page-locked host memory mapped into the device (the host reads it after
+// every synchronisation without a copy): 1 = a halo peer never arrived, 2 = a tile's publishers never did.
+__device__ __forceinline__ void report_error(int *err, int code)
+{
+    *reinterpret_cast<volatile int *>(err) = code;
+    __threadfence_system();
+}
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc)
 {
@@ -221,9 +231,11 @@ __device__ __forceinline__ int ldg_i32_pinned(const int32_t *p)
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// Flags are polled with relaxed loads and raised with a relaxed store after a gpu-scope fence;
-// the data they guard (partial forces) is written with st.cg and read with cp.async.cg / ld.cg,
-// i.e. at L2, where the fence has made it visible -- no L1 invalidation is needed on either side.
+// Flags are polled with relaxed loads and raised with a relaxed store after a gpu-scope fence; the
+// consumer issues a gpu-scope fence after it has seen the flags (wait_deps).  The data they guard
+// (partial forces) is written with st.cg and read with 8-byte cp.async.ca: a line of partial[] has
+// one writer per pass and is read once per pass, and L1 does not survive a kernel boundary, so a
+// reader never finds a stale copy of it in its own L1.
 __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int *p)
 {
     unsigned int v;
@@ -385,11 +397,27 @@ __device__ __forceinline__ void wait_deps(const StepArgs &A, const int4 md, cons
 {
     const int ndep = md.y - md.x;
     unsigned int v = first_value;
+    bool waited = false;
     for (int d = tid; d < ndep; d += nthr) {
         const unsigned int *f = dep_flag(A, md, buf, d);
         if (d != tid) v = ld_relaxed_u32(f);
-        while ((int)(v - A.epoch) < 0) { __nanosleep(32); v = ld_relaxed_u32(f); }
+        if ((int)(v - A.epoch) < 0) {
+            // Lower tiles are started before this one and every CTA of the launch is resident
+            // (cooperative launch), so this wait is short; the bound only turns a broken
+            // invariant (a lost CTA, a foreign context holding the SMs) into an error the host
+            // sees at its next hgpu_sync instead of a hang.
+            const long long t0 = clock64();
+            do {
+                __nanosleep(32);
+                v = ld_relaxed_u32(f);
+                if (clock64() - t0 > WAIT_DEPS_CYCLES) { report_error(A.err, 2); break; }
+            } while ((int)(v - A.epoch) < 0);
+        }
+        waited = true;
     }
+    // acquire side of the publishers' fence + flag store: orders the partial-force reads that follow
+    // (after the next barrier) behind the flag reads of this thread
+    if (waited) asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
 
 // Request the partial forces a tile reads, and the node-table entry of its record nodes
@@ -1095,23 +1123,66 @@ struct PullSeg {
 // messenger (sharing only: the overwrite lists of different owners are disjoint; contributions are
 // applied one messenger per launch, in list order, so sums keep the reference's order).
 __global__ void p2p_pull_kernel(const PullSeg *__restrict__ segs, double *__restrict__ v,
-                                unsigned long long seq, int add, int *__restrict__ err)
+                                unsigned long long seq, int add, int *__restrict__ err, long long timeout_cycles)
 {
     const PullSeg sg = segs[blockIdx.y];
+    __shared__ int ok;
     if (threadIdx.x == 0) {
         const volatile unsigned long long *f = sg.flag;
         const long long t0 = clock64();
+        int good = 1;
         while (*f < seq) {
             __nanosleep(200);
-            if (clock64() - t0 > 20000000000LL) { atomicExch(err, 1); break; }   // ~10 s: peer lost
+            // a peer that never arrives: report, and do NOT apply whatever the mailbox holds
+            if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { report_error(err, 1); good = 0; break; }
         }
+        ok = good;
     }
     __syncthreads();
+    if (!ok) return;
     const int n3 = 3 * sg.n;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += gridDim.x * blockDim.x) {
         const size_t g = 3 * (size_t)sg.mapping[k / 3] + (k % 3);
         const double x = __ldcg(sg.local + k);
         v[g] = add ? v[g] + x : x;
+    }
+}
+
+// The same for ALL messengers of a contribution list in one launch (the reference applies them one
+// after another, psolve.c:5035-5073, so that a node shared with several neighbours receives its
+// contributions in list order): one thread per (entry of the node-major CSR, component) walks the
+// node's contributions in messenger order.  csr_node[i] = local node, csr_off[i..i+1) into csr_src,
+// csr_src[j] = index of the double triple inside this list's receive area for this parity
+// (p2p_alloc_mailbox: messenger i occupies triples [2 off_i, 2 off_i + 2 n_i), parity p its second half).
+struct PullAll {
+    const int32_t *csr_node, *csr_off, *csr_src;
+    const double *local;                    // receive area of this list and parity
+    const unsigned long long *flags;        // [nmsg][2 parities] sequence flags
+    int32_t nnodes, nmsg, parity;
+};
+__global__ void p2p_pull_all_kernel(const PullAll pa, double *__restrict__ v, unsigned long long seq,
+                                    int *__restrict__ err, long long timeout_cycles)
+{
+    __shared__ int ok;
+    if (threadIdx.x == 0) ok = 1;
+    __syncthreads();
+    for (int m = threadIdx.x; m < pa.nmsg; m += blockDim.x) {
+        const volatile unsigned long long *f = pa.flags + 2 * m + pa.parity;
+        const long long t0 = clock64();
+        while (*f < seq) {
+            __nanosleep(200);
+            if (timeout_cycles > 0 && clock64() - t0 > timeout_cycles) { report_error(err, 1); ok = 0; break; }
+        }
+    }
+    __syncthreads();
+    if (!ok) return;
+    const int n3 = 3 * pa.nnodes;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n3; k += gridDim.x * blockDim.x) {
+        const int i = k / 3, c = k - 3 * i;
+        const size_t g = 3 * (size_t)pa.csr_node[i] + c;
+        double s = v[g];
+        for (int j = pa.csr_off[i]; j < pa.csr_off[i + 1]; j++) s += __ldcg(pa.local + 3 * (size_t)pa.csr_src[j] + c);
+        v[g] = s;
     }
 }
 

@@ -150,10 +150,70 @@ static void write_station_rows(const double *rows, const int32_t *steps, int32_t
         }
 }
 
+/* Device times under the reference's timer names.  The host timers around the hgpu_* calls hold launch
+ * time only (the calls enqueue work); what print_timing_stat (psolve.c:6041-6266) and
+ * solver_run_collect_timers (psolve.c:4186-4235) should report is the time the DEVICE spent in each
+ * phase (CUDA events, hgpu_get_timers).  timers.c keeps its table in a non-static array of
+ * { char name[128]; double starttime, elapsed, max, min, average; int running; enum flags } entries
+ * (timers.c:10-25), so the cumulative `elapsed` of an existing timer can be replaced from here.
+ * The fused launches (element forces + update of the regular nodes in one kernel) have no timer of
+ * their own in the reference: they are booked under "Compute addforces e".  Phases that ran on the
+ * communication stream beside the late tiles are counted in full, so the parts can add up to more
+ * than "Solver". */
+struct hgpu_ref_timer { char name[128]; double starttime, elapsed, max, min, average; int running; int flags; };
+extern struct hgpu_ref_timer Timers[];
+
+static void set_ref_timer(const char *name, double seconds)
+{
+    for (int i = 0; i < 100 && Timers[i].name[0]; i++)          /* MAXTIMERS, timers.c:8 */
+        if (strcmp(Timers[i].name, name) == 0) { Timers[i].elapsed = seconds; return; }
+}
+
+static void device_times_to_reference_timers(const hgpu_timers_t *tm)
+{
+    const double physics = tm->addforce_s + tm->addforce_e + tm->damping + tm->fused_step + tm->new_disp;
+    const double comm = tm->send_dn_force + tm->adjust_force + tm->send_an_force +
+                        tm->send_an_disp + tm->adjust_disp + tm->send_dn_disp;
+    set_ref_timer("Compute addforces s", tm->addforce_s);
+    set_ref_timer("Compute addforces e", tm->addforce_e + tm->fused_step);
+    set_ref_timer("Damping addforce", tm->damping);
+    set_ref_timer("1st schedule send data (contribution)", tm->send_dn_force);
+    set_ref_timer("1st compute adjust (distribution)", tm->adjust_force);
+    set_ref_timer("2nd schedule send data (contribution)", tm->send_an_force);
+    set_ref_timer("Compute new displacement", tm->new_disp);
+    set_ref_timer("3rd schedule send data (sharing)", tm->send_an_disp);
+    set_ref_timer("2nd compute adjust (assignment)", tm->adjust_disp);
+    set_ref_timer("4th schadule send data (sharing)", tm->send_dn_disp);
+    set_ref_timer("Compute Physics", physics);
+    set_ref_timer("Communication", comm);
+}
+
 static void gpu_solver_run(void)
 {
     int32_t step, startingStep;
     mysolver_t *sv = Global.mySolver;
+
+    /* What this loop does NOT carry over from solver_run (psolve.c:4281-4307): the nonlinear state and
+     * forces, gravity / geostatic fix (solver_nonlinear_state, solver_compute_force_gravity/_nonlinear,
+     * solver_geostatic_fix: all behind Param.includeNonlinearAnalysis, psolve.c:3911, 4016, 4026, 4119), the
+     * buildings' fixed-base displacements (solver_load_fixedbase_displacements, behind get_fixedbase_flag(),
+     * psolve.c:3942-3949) and the DRM taps (solver_output_drm_nodes, solver_read_drm_displacements,
+     * solver_compute_effective_drm_force: Param.drmImplement).  It also treats every element as linear,
+     * where the reference walks myLinearElementsMapper (the identity map without nonlinear analysis or
+     * buildings, stiffness.c:101-118).  An input deck that switches any of those on must not run here
+     * and produce silently different results: abort, as the reference does on every other unsupported
+     * configuration (solver_abort, util.h:128). */
+    if (Param.includeNonlinearAnalysis == YES)
+        solver_abort("gpu_solver_run", NULL, "nonlinear analysis (include_nonlinear_analysis = yes) is not "
+                     "carried by the GPU time loop; run the CPU psolve for this deck\n");
+    if (Param.includeBuildings == YES)
+        solver_abort("gpu_solver_run", NULL, "buildings (include_buildings = yes: fixed-base displacements, "
+                     "non-identity linear-element map) are not carried by the GPU time loop\n");
+    if (Param.drmImplement == YES)
+        solver_abort("gpu_solver_run", NULL, "DRM (implement_drm = yes) is not carried by the GPU time loop\n");
+    if (sizeof(solver_float) != sizeof(double))
+        solver_abort("gpu_solver_run", NULL, "libhercules_gpu.so takes the double-precision tables "
+                     "(build without -DSINGLE_PRECISION_SOLVER, psolve.h:60-64)\n");
 
     gpu_attach();
     if (Param.theUseCheckPoint == 1) {                          /* psolve.c:4248-4253 */
@@ -309,7 +369,7 @@ static void gpu_solver_run(void)
     {
         hgpu_timers_t tm;
         GPU(hgpu_get_timers(theGpu, &tm));
-        if (Global.myID == 0)
+        if (Global.myID == 0) {
             monitor_print("gpu_solver_run() host time: taps %.6f s, reference I/O block %.6f s, hgpu calls %.6f s\n",
                           host_tap, host_io, host_gpu);
             monitor_print("gpu_solver_run() done: %lld steps, %lld kernel launches, loop wall %.6f s; device time: "
@@ -320,6 +380,8 @@ static void gpu_solver_run(void)
                           (tm.adjust_force + tm.adjust_disp) - (tm_warm.adjust_force + tm_warm.adjust_disp),
                           (tm.send_dn_force + tm.send_an_force + tm.send_an_disp + tm.send_dn_disp) -
                           (tm_warm.send_dn_force + tm_warm.send_an_force + tm_warm.send_an_disp + tm_warm.send_dn_disp));
+        }
+        device_times_to_reference_timers(&tm);
     }
     GPU(hgpu_finalize(theGpu));
     theGpu = NULL;

@@ -16,6 +16,7 @@
 #define _GNU_SOURCE
 #include "mpi.h"
 
+#include <sched.h>
 #include <errno.h>
 #include <fcntl.h>
 #include <pthread.h>
@@ -279,6 +280,19 @@ int MPI_Init(int *argc, char ***argv)
         g_shm->pids[r] = pid;
     }
     if (g_rank == 0) atexit(reap_children);
+    /* HMPI_PIN=1: rank r stays on the (r mod n)-th cpu this process may use, so that timing runs do not
+     * depend on where the scheduler happens to put (and migrate) the forked ranks */
+    e = getenv("HMPI_PIN");
+    if (e && atoi(e) > 0) {
+        cpu_set_t allowed, mine;
+        if (sched_getaffinity(0, sizeof allowed, &allowed) == 0) {
+            int n = CPU_COUNT(&allowed), want = g_rank % (n > 0 ? n : 1), seen = 0;
+            for (int c = 0; c < CPU_SETSIZE; c++) {
+                if (!CPU_ISSET(c, &allowed)) continue;
+                if (seen++ == want) { CPU_ZERO(&mine); CPU_SET(c, &mine); sched_setaffinity(0, sizeof mine, &mine); break; }
+            }
+        }
+    }
 
     memset(g_comm, 0, sizeof g_comm);
     g_comm[0].used = 1; g_comm[0].ctx = 0; g_comm[0].size = g_np; g_comm[0].rank = g_rank;

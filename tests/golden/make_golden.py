@@ -60,6 +60,8 @@ CASES = {
     "graded3_rayleigh_eff": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 1, 25),
     "graded3_rayleigh_eff_np2": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 2, 25),
     "graded3_rayleigh_eff_np4": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 4, 25),
+    # 8 ranks = one per GPU of an 8 x B200 box: what bench.py replays on the real devices before it times N = 8
+    "graded3_rayleigh_eff_np8": (dict(**THREE_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.1), 8, 50),
     # BASELINE.json configs[0] (examples/test1): homogeneous half-space 100 x 100 x 37.5 km (tick ratio 8:8:3),
     # meshed for 0.1 Hz (32 x 32 x 12 elements of 3125 m), quadratic point source 1 km deep, 500 steps of 0.02 s;
     # the unshipped labase.e is stood in for by a homogeneous etree of the same values (SURVEY.md 8d cfg 1)

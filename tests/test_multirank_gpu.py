@@ -57,7 +57,7 @@ FLAGS = [0, 4] + ([8] if os.environ.get("HGPU_TEST_TAIL_OVERLAP") == "1" else []
 # whose anchors belong to another rank, nodes a rank harbors without having an element on them
 CASES = [("graded3_rayleigh_eff_np2", 2), ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3),
          ("graded2_bkt_np2", 2), ("basin_rayleigh_eff_np2", 2), ("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4),
-         ("basin_bkt_np3", 3)]
+         ("basin_bkt_np3", 3), ("graded3_rayleigh_eff_np8", 8)]
 
 
 def _ngpu():

@@ -118,7 +118,7 @@ def test_balance_is_two_to_one_across_faces_and_edges():
 PART_CASES = {   # golden: (single-rank case it derives from, ranks)
     "basin_rayleigh_eff_np2": ("basin_rayleigh_eff", 2), "basin_rayleigh_eff_np3": ("basin_rayleigh_eff", 3),
     "basin_rayleigh_eff_np4": ("basin_rayleigh_eff", 4), "graded3_rayleigh_eff_np2": ("graded3_rayleigh_eff", 2),
-    "graded3_rayleigh_eff_np4": ("graded3_rayleigh_eff", 4),
+    "graded3_rayleigh_eff_np4": ("graded3_rayleigh_eff", 4), "graded3_rayleigh_eff_np8": ("graded3_rayleigh_eff", 8),
 }
 
 

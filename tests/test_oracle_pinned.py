@@ -171,7 +171,8 @@ def test_effective_equals_conventional(oracle):
 
 
 @pytest.mark.parametrize("name,world", [("basin_rayleigh_eff_np3", 3), ("basin_rayleigh_eff_np4", 4),
-                                        ("graded3_rayleigh_eff_np4", 4), ("uniform_rayleigh_eff_np3", 3),
+                                        ("graded3_rayleigh_eff_np4", 4), ("graded3_rayleigh_eff_np8", 8),
+                                        ("uniform_rayleigh_eff_np3", 3),
                                         ("graded2_bkt_np2", 2), ("basin_bkt_np3", 3)])
 def test_multirank_oracle_bit_exact(oracle, name, world):
     """The oracle's per-rank arithmetic plus the four schedule_senddata exchanges of a step (psolve.c:4036-4154,
