@@ -785,7 +785,7 @@ def main() -> None:
             "layout": {k: layout[k] for k in ("tile_nodes", "ntiles", "max_tile_nodes", "tile_elems_total",
                                               "tile_halo_total", "n_regular", "n_special", "device_bytes",
                                               "smem_bytes", "block_threads", "grid_ctas", "ctas_per_sm",
-                                              "early_tiles")},
+                                              "early_tiles", "struct_tiles")},
             "phases_ms_per_step": phases_ms,
             "setup_s": {"mesh": round(t_mesh, 1), "hgpu_init": round(t_init, 1)},
         }

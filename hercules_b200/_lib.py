@@ -48,7 +48,7 @@ class Layout(C.Structure):
                 ("n_regular", i64), ("n_special", i64), ("device_bytes", i64),
                 ("smem_bytes", i32), ("block_threads", i32), ("grid_ctas", i32), ("ctas_per_sm", i32), ("early_tiles", i32),
                 ("est_gather_wavefronts", f64), ("est_scatter_wavefronts", f64),
-                ("max_tile_acc", i32), ("max_tile_recs", i32), ("max_tile_srcs", i32), ("pad_", i32),
+                ("max_tile_acc", i32), ("max_tile_recs", i32), ("max_tile_srcs", i32), ("struct_tiles", i32),
                 ("partial_slots", i64), ("deps_total", i64)]
 
 

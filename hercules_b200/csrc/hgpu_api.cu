@@ -144,6 +144,8 @@ struct hgpu_solver {
     uint4 *t_ent_slot = nullptr;         // per entry 8 x uint16 = 3 * slot
     double *t_ent_coef = nullptr;        // per entry c1, c2, beta
     double *t_beta = nullptr;            // per tile (processing order): the entries' common beta, or NaN
+    double *t_coef = nullptr;            // per tile (processing order): {c1, c2, beta, -} of a structured tile
+    int32_t n_struct = 0;                // structured tiles of one material (take the STRUCT path of the step kernel)
     uint2 *t_rec = nullptr;              // finish records
     int32_t *t_src = nullptr, *t_dep = nullptr;
     double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
@@ -317,7 +319,7 @@ static int step_smem_bytes(bool u2e, int32_t cap_slots, int32_t cap_acc, int32_t
 // Two CTAs per SM: each may use half of the SM's shared memory minus the 1 KB the system reserves
 // per CTA.  Per CTA: 2 stages x (u1 + u2) x cap_slots nodes + the accumulator (owned + published
 // nodes) + the pending buffer (owned nodes) + 2 finish buffers.
-static TileCaps tile_caps(int max_smem, int32_t tile_nodes)
+static TileCaps tile_caps(int max_smem, int32_t tile_nodes, bool allow_struct = false)
 {
     const int per_cta = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
     TileCaps c;
@@ -329,13 +331,18 @@ static TileCaps tile_caps(int max_smem, int32_t tile_nodes)
     c.elem_block = 512;
     const char *eenv = getenv("HGPU_ELEM_BLOCK");
     if (eenv && atoi(eenv) > 0) c.elem_block = atoi(eenv);
+    // with structured tiles the accumulator holds three padded planes (SP_TOTAL doubles > 3 x 9^3): a little
+    // less is left for the stages and the finish buffers (224 / 272 cover the far-face tiles of a uniform mesh)
+    if (allow_struct) { c.max_recs = 224; c.max_srcs = 272; }
     const int budget = (per_cta - finish_smem_bytes(c.max_recs, c.max_srcs)) / 8;     // doubles
     // an interior tile of a uniform region stages and accumulates 9^3 nodes and owns 8^3 of them
-    const int32_t rest = budget / 15;                      // 12 S + 3 A with S = A
+    const int32_t rest = allow_struct ? (budget - SP_TOTAL) / 12      // 12 S + the padded planes
+                                      : budget / 15;                  // 12 S + 3 A with S = A
     c.max_owned = cap_owned;
     c.max_acc = std::max(16, std::min(rest, 65535 / 3) & ~15);
     c.max_slots = c.max_acc;
     c.max_owned = std::min(c.max_owned, c.max_acc);
+    c.allow_struct = allow_struct ? 1 : 0;
     return c;
 }
 
@@ -505,7 +512,6 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         int max_smem = 0, nsm = 0;
         TRYCU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->dev));
         TRYCU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->dev));
-        const TileCaps caps = tile_caps(max_smem, params->tile_nodes);
         // tiles owning a node of the exchange / hanging-node phases must not wait for anybody
         // ("self" tiles); without the fused update every node's force goes to the force array and
         // no node needs a record of its own
@@ -513,9 +519,27 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // BKT: an element's memory variables are advanced by its one core evaluation, so no tile may
         // re-evaluate foreign elements: no self tiles, the exchange follows the whole pass
         const bool bkt = params->damping == HGPU_DAMPING_BKT;
-        if (!build_tile_plan(E, N, mesh->elem_lnid, caps, (params->nranks > 1 && !bkt) ? early_node.data() : nullptr,
-                             fused ? cls.data() : nullptr, s->plan, err)) {
-            hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
+        // structured tiles (aligned uniform 8x8x8 cells): the fused effective-stiffness kernels only
+        bool want_struct = fused && !bkt && params->stiffness == HGPU_STIFFNESS_EFFECTIVE &&
+                           !(params->flags & (HGPU_FLAG_WPASS | HGPU_FLAG_NO_STRUCT));
+        { const char *senv = getenv("HGPU_STRUCT"); if (senv && atoi(senv) == 0) want_struct = false; }
+        const int smem_cap0 = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
+        TileCaps caps = tile_caps(max_smem, params->tile_nodes, want_struct);
+        for (;;) {
+            if (!build_tile_plan(E, N, mesh->elem_lnid, caps, (params->nranks > 1 && !bkt) ? early_node.data() : nullptr,
+                                 fused ? cls.data() : nullptr, s->plan, err)) {
+                hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
+            }
+            if (!caps.allow_struct) break;
+            // the padded accumulator of the structured path (SP_TOTAL doubles) must fit beside the stages
+            const TilePlan &q = s->plan;
+            bool any = false;
+            for (uint8_t f : q.tile_struct) any = any || f;
+            const int need = step_smem_bytes(true, (q.max_tile_nodes + 15) & ~15, std::max((q.max_tile_acc + 15) & ~15, any ? SP_C : 0),
+                                             (q.max_tile_owned + 15) & ~15, std::min(caps.max_recs, (q.max_tile_recs + 15) & ~15),
+                                             std::min(caps.max_srcs, (q.max_tile_srcs + 15) & ~15));
+            if (!any || need <= smem_cap0) break;
+            caps.allow_struct = 0;              // does not fit next to this mesh's largest generic tile: plain plan
         }
         TilePlan &pl = s->plan;
         const size_t entries = pl.elem_id.size();
@@ -562,7 +586,6 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 m[12] = pl.dep_off[t]; m[13] = pl.dep_off[(size_t)t + 1];
                 m[14] = t;
             }
-            TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
             // the Rayleigh ratio shared by all entries of a tile (one material), NaN otherwise
             std::vector<double> tbeta((size_t)pl.ntiles, 0.0);
             for (int32_t i = 0; i < pl.ntiles; i++) {
@@ -574,6 +597,23 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 tbeta[i] = b;
             }
             TRY(upload(s, &s->t_beta, tbeta.data(), tbeta.size()));
+            // structured tiles of ONE material (c1, c2, c3/c1 equal bit for bit over the cell): coefficients per tile
+            std::vector<double> tcoef(4 * (size_t)pl.ntiles, 0.0);
+            s->n_struct = 0;
+            for (int32_t i = 0; i < pl.ntiles; i++) {
+                const int32_t t = order[i];
+                if (pl.tile_struct.empty() || !pl.tile_struct[t]) continue;
+                const int32_t e0 = pl.elem_off[t], e1 = pl.elem_off[(size_t)t + 1];
+                bool same = e1 > e0;
+                for (int32_t k = e0 + 1; k < e1 && same; k++)
+                    same = memcmp(&coef[3 * (size_t)k], &coef[3 * (size_t)e0], 3 * sizeof(double)) == 0;
+                if (!same) continue;
+                for (int c = 0; c < 3; c++) tcoef[4 * (size_t)i + c] = coef[3 * (size_t)e0 + c];
+                meta[(size_t)META_INTS * (size_t)i + 15] = 1;
+                s->n_struct++;
+            }
+            TRY(upload(s, &s->t_coef, tcoef.data(), tcoef.size()));
+            TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
@@ -611,6 +651,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRYCU(cudaMemset(s->t_flag, 0, std::max<size_t>(1, (size_t)pl.ntiles) * sizeof(unsigned int)));
         // shared memory actually needed by this plan
         s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_acc = (pl.max_tile_acc + 15) & ~15;
+        if (s->n_struct > 0) s->cap_acc = std::max(s->cap_acc, (int)SP_C);      // padded planes of the structured path
         s->cap_owned = (pl.max_tile_owned + 15) & ~15;
         s->cap_recs = std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15);
         s->cap_srcs = std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15);
@@ -623,6 +664,9 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // share so that solvers with different plans can coexist in one process
         const int smem_cap = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
         if (s->smem_u2 > smem_cap) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan needs %d bytes of shared memory (> %d)", s->smem_u2, smem_cap); }
+        if (s->n_struct > 0 && 3 * s->cap_slots + 3 * s->cap_owned < SP_TOTAL + STRUCT_OWNED) {
+            hgpu_finalize(s); return fail(HGPU_EINVAL, "internal: stage too small for the structured path");
+        }
 #define SETUP(T)                                                                                             \
         do {                                                                                                 \
             TRYCU(cudaFuncSetAttribute(step_kernel<0, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
@@ -633,6 +677,8 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<3, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<0, false, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
@@ -641,6 +687,12 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             int occ_w = 0;
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, step_kernel<1, false, 256, true>, 256, s->smem_u2));
             occ = std::min(occ, occ_w);
+        }
+        if (s->block != 256) s->n_struct = 0;     // the structured path is written for 256 threads
+        if (s->n_struct > 0) {
+            int occ_s = 0;
+            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, false, 256, false, true>, 256, s->smem_u2));
+            occ = std::min(occ, occ_s);
         }
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
         {
@@ -690,7 +742,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     if (s->h_err) cudaFreeHost(s->h_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta);
+    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta); dfree(s->t_coef);
     dfree(s->conv); dfree(s->t_ent_bkt); dfree(s->entry_of_elem); dfree(s->conv_scratch);
     dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
@@ -744,6 +796,7 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.conv = s->conv; A.ent_bkt = s->t_ent_bkt;
     A.rmax = 2.0 * M_PI * s->P.freq * s->P.dt;                     // damping.c:114, 234
     A.tile_beta = s->t_beta;
+    A.tile_coef = s->t_coef;
     A.err = s->d_err;
     const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt;
     const int mode = tm.bkt ? 3 : tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
@@ -773,6 +826,11 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     } while (0)
     if (fuse && !dense && mode == 1 && B == 256 && (s->P.flags & HGPU_FLAG_WPASS))
         fn = (const void *)step_kernel<1, false, 256, true>;       // opt-in variant, see hgpu_kernels.cuh
+    else if (fuse && !dense && (mode == 0 || mode == 1) && B == 256 && s->n_struct > 0) {
+        // structured tiles of the plan take the z-pair path, the others the generic one, in one launch
+        if (mode == 0) { fn = (const void *)step_kernel<0, false, 256, false, true>; smem = (size_t)s->smem_nou2; }
+        else fn = (const void *)step_kernel<1, false, 256, false, true>;
+    }
     else if (B == 384) PICK(384); else PICK(256);
 #undef PICK
     {
@@ -1361,7 +1419,9 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     if (mesh->lenum < 0 || mesh->nharbored <= 0) return fail(HGPU_EINVAL, "bad mesh counts");
     TilePlan pl;
     std::string err;
-    const TileCaps caps = tile_caps(232448, tile_nodes);
+    // structured tiles recognised as hgpu_init does for the fused effective-stiffness kernels (HGPU_STRUCT=0: not)
+    const char *senv = getenv("HGPU_STRUCT");
+    const TileCaps caps = tile_caps(232448, tile_nodes, !(senv && atoi(senv) == 0));
     // nodes of the halo schedules and the hanging-node lists (when given) make their tiles "self"
     // tiles, as hgpu_init does on a multi-rank mesh
     std::vector<uint8_t> self_node;
@@ -1393,13 +1453,16 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     out->tile_elems_total = (int64_t)pl.elem_id.size();
     out->tile_halo_total = pl.halo_nodes_total;
     estimate_wavefronts(pl, &out->est_gather_wavefronts, &out->est_scatter_wavefronts);
-    out->smem_bytes = step_smem_bytes(true, (pl.max_tile_nodes + 15) & ~15, (pl.max_tile_acc + 15) & ~15,
+    bool any_struct = false;
+    for (uint8_t f : pl.tile_struct) any_struct = any_struct || f;
+    out->smem_bytes = step_smem_bytes(true, (pl.max_tile_nodes + 15) & ~15, std::max((pl.max_tile_acc + 15) & ~15, any_struct ? (int)SP_C : 0),
                                       (pl.max_tile_owned + 15) & ~15, std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15),
                                       std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15));
     out->block_threads = 256;
     for (int32_t t = 0; t < pl.ntiles; t++) out->early_tiles += pl.tile_self[t];
     out->max_tile_acc = pl.max_tile_acc; out->max_tile_recs = pl.max_tile_recs; out->max_tile_srcs = pl.max_tile_srcs;
     out->partial_slots = (int64_t)pl.halo_id.size(); out->deps_total = (int64_t)pl.dep.size();
+    for (uint8_t f : pl.tile_struct) out->struct_tiles += f;       // geometric count (materials are not looked at here)
     return HGPU_OK;
 }
 
@@ -1419,6 +1482,7 @@ extern "C" int hgpu_get_layout(hgpu_solver_t *s, hgpu_layout_t *out)
     out->grid_ctas = s->grid; out->ctas_per_sm = s->ctas_per_sm; out->early_tiles = s->n_early;
     out->max_tile_acc = pl.max_tile_acc; out->max_tile_recs = pl.max_tile_recs; out->max_tile_srcs = pl.max_tile_srcs;
     out->partial_slots = (int64_t)pl.halo_id.size(); out->deps_total = (int64_t)pl.dep.size();
+    out->struct_tiles = s->n_struct;
     return HGPU_OK;
 }
 

@@ -42,6 +42,7 @@ struct TilePlan {
     int32_t max_tile_recs = 0, max_tile_srcs = 0;
     std::vector<int32_t>  node_off;   // [ntiles+1]
     std::vector<uint8_t>  tile_self;  // [ntiles]
+    std::vector<uint8_t>  tile_struct; // [ntiles] 1: an aligned 8x8x8 cell of equal elements in canonical layout (see struct_*)
     std::vector<int32_t>  elem_off;   // [ntiles+1] into elem_id / elem_slot
     std::vector<int32_t>  elem_core;  // [ntiles] the first elem_core[t] entries of a tile are its core elements
     std::vector<int32_t>  elem_id;    // element evaluated by this tile entry
@@ -65,7 +66,32 @@ struct TileCaps {
     int32_t max_acc;      // owned + published slots (shared-memory accumulator)
     int32_t max_slots;    // staged nodes
     int32_t max_recs, max_srcs;
+    int32_t allow_struct; // recognise aligned uniform 8x8x8 cells and give them the canonical halo order
 };
+
+// ---- structured tiles ---------------------------------------------------------------------------------
+// A tile is STRUCTURED when it is exactly one aligned 8x8x8 cell of equal elements: it owns the 512
+// nodes at the lower corners of its 512 core elements, in Morton order (slot = interleave of x, y, z
+// bits, x lowest), has no extra entries, and its 217 gathered nodes -- the x = 8, y = 8 and z = 8 faces
+// of the 9x9x9 node block -- take the slots 512 + h in this canonical order:
+//   h in [0, 81)    : z = 8 face,          x = h % 9,  y = h / 9
+//   h in [81, 153)  : y = 8 face, z < 8,   x = k % 9,  z = k / 9     (k = h - 81)
+//   h in [153, 217) : x = 8 face, y, z < 8, y = k % 8, z = k / 8     (k = h - 153)
+// The step kernel then needs no per-element slot table for such a tile (hgpu_kernels.cuh).
+constexpr int STRUCT_OWNED = 512, STRUCT_HALO = 217, STRUCT_NODES = 729;
+inline int struct_morton3(int x, int y, int z)
+{
+    int m = 0;
+    for (int b = 0; b < 3; b++) m |= (((x >> b) & 1) << (3 * b)) | (((y >> b) & 1) << (3 * b + 1)) | (((z >> b) & 1) << (3 * b + 2));
+    return m;
+}
+inline int struct_slot(int x, int y, int z)     // x, y, z in 0..8
+{
+    if (z == 8) return STRUCT_OWNED + 9 * y + x;
+    if (y == 8) return STRUCT_OWNED + 81 + 9 * z + x;
+    if (x == 8) return STRUCT_OWNED + 153 + 8 * z + y;
+    return struct_morton3(x, y, z);
+}
 
 // Builds the plan; returns false and sets err on inconsistent input.  self_node (may be null):
 // tiles owning a flagged node become "self" tiles.  special_node (may be null): SPECIAL flags.

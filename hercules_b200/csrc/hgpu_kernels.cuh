@@ -18,6 +18,8 @@
 
 namespace hgpu {
 
+#define HGPU_HD __host__ __device__ __forceinline__
+
 // ------------------------------------------------------------------------------------------
 // Element operator in the factored ("effective") form of stiffness.c:180-237.
 //
@@ -29,7 +31,7 @@ namespace hgpu {
 // ------------------------------------------------------------------------------------------
 
 // forward: w[j], j = jx + 2 jy + 4 jz  ->  t[k], k in the reference's mode numbering
-__device__ __forceinline__ void wht_forward(const double (&w)[8], double (&t)[8])
+HGPU_HD void wht_forward(const double (&w)[8], double (&t)[8])
 {
     // x stage: s = sum, d = (x=+1) - (x=-1)
     double sx0 = w[0] + w[1], dx0 = w[1] - w[0];
@@ -53,7 +55,7 @@ __device__ __forceinline__ void wht_forward(const double (&w)[8], double (&t)[8]
 }
 
 // inverse (au, stiffness.c:388-413): f[j] = sum_k S[k][j] v[k]
-__device__ __forceinline__ void wht_inverse(const double (&v)[8], double (&f)[8])
+HGPU_HD void wht_inverse(const double (&v)[8], double (&f)[8])
 {
     // z stage: combine each (bx,by) pair of modes into jz = 0 / 1 values
     double a0 = v[0] - v[1], a1 = v[0] + v[1];   // (0,0): 1 , z
@@ -74,7 +76,7 @@ __device__ __forceinline__ void wht_inverse(const double (&v)[8], double (&f)[8]
 
 // firstVector (stiffness.c:291-319) with a = -0.5625 (c2 + 2 c1), c = -0.5625 c2, b = -0.5625 c1.
 // Divisions by 3 and 9 are multiplications by the rounded reciprocals (<= 1 ulp apart).
-__device__ __forceinline__ void scale_modes(const double (&tx)[8], const double (&ty)[8],
+HGPU_HD void scale_modes(const double (&tx)[8], const double (&ty)[8],
                                             const double (&tz)[8], double a, double c, double b,
                                             double (&vx)[8], double (&vy)[8], double (&vz)[8])
 {
@@ -164,6 +166,8 @@ struct StepArgs {
     // WPASS variant (MODE 1): per tile, in processing order, the Rayleigh ratio beta = c3/c1 shared by
     // all its entries, or NaN when they differ (the tile then takes the per-corner path)
     const double *__restrict__ tile_beta;
+    // STRUCT variant: per tile, in processing order, {c1, c2, beta, -} of a structured tile of one material
+    const double *__restrict__ tile_coef;
     int *err;                           // error word (mapped host memory), see report_error
 };
 
@@ -231,8 +235,8 @@ __device__ __forceinline__ int ldg_i32_pinned(const int32_t *p)
     asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 }
-// Flags are polled with relaxed loads and raised with a relaxed store after a gpu-scope fence; the
-// consumer issues a gpu-scope fence after it has seen the flags (wait_deps).  The data they guard
+// Flags are polled with relaxed loads and raised with a relaxed store after a gpu-scope fence.
+// The data they guard
 // (partial forces) is written with st.cg and read with 8-byte cp.async.ca: a line of partial[] has
 // one writer per pass and is read once per pass, and L1 does not survive a kernel boundary, so a
 // reader never finds a stale copy of it in its own L1.
@@ -397,7 +401,6 @@ __device__ __forceinline__ void wait_deps(const StepArgs &A, const int4 md, cons
 {
     const int ndep = md.y - md.x;
     unsigned int v = first_value;
-    bool waited = false;
     for (int d = tid; d < ndep; d += nthr) {
         const unsigned int *f = dep_flag(A, md, buf, d);
         if (d != tid) v = ld_relaxed_u32(f);
@@ -413,11 +416,10 @@ __device__ __forceinline__ void wait_deps(const StepArgs &A, const int4 md, cons
                 if (clock64() - t0 > WAIT_DEPS_CYCLES) { report_error(A.err, 2); break; }
             } while ((int)(v - A.epoch) < 0);
         }
-        waited = true;
     }
-    // acquire side of the publishers' fence + flag store: orders the partial-force reads that follow
-    // (after the next barrier) behind the flag reads of this thread
-    if (waited) asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    // No fence on this side: a gpu-scope fence makes ptxas invalidate the SM's whole L1 (CCTL.IVALL), once
+    // per tile, which cost 4 % of the kernel when measured (r02 call 1).  The partial forces read after the
+    // next barrier cannot be stale without it: see the comment above ld_relaxed_u32.
 }
 
 // Request the partial forces a tile reads, and the node-table entry of its record nodes
@@ -560,6 +562,83 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// STRUCTURED tiles (hgpu_internal.h): one aligned 8x8x8 cell of equal elements of one material.
+// No slot table is needed: thread (x, y, zq) evaluates the two elements (x, y, 2 zq) and
+// (x, y, 2 zq + 1) of the cell -- a z pair -- from a copy of the damped displacement
+// w = u1 + beta (u1 - u2) that is formed ONCE PER NODE (729 nodes) right after the tile has landed,
+// in a padded structure-of-arrays layout [component][z][y][x] with row stride 12 and plane stride
+// 108: lanes = (x & 3, y), so the 16 lanes of a half-warp (4 x values, 4 consecutive rows) always hit
+// 16 different 8-byte banks (12 y mod 16 = 0, 12, 8, 4) -- gathers and accumulator updates are
+// conflict-free.  What the two elements add to the 4 nodes they share (the middle level) is summed
+// in registers before the last two butterfly stages of the inverse transform, so a z pair makes
+// 36 gathers and 36 accumulator updates where two single elements make 96 and 48.
+// Accumulator updates are ordered by (dx, level class): within a warp by __syncwarp (the y
+// neighbours are lanes of the same warp), between warps by four barriers per tile:
+//   A: lower level, dx = 0   B: lower level, dx = 1   C: middle + upper level, dx = 0   D: ..., dx = 1
+// (warps = (x >> 2, zq): the x = 4 column and the even levels are shared between warps).
+// ------------------------------------------------------------------------------------------
+constexpr int SP_ROW = 12, SP_Z = 108, SP_C = 972, SP_TOTAL = 3 * SP_C;     // doubles
+
+// tile-local slot (Morton for the 512 owned nodes, canonical far-face order for the 217 others,
+// hgpu_internal.h) -> offset of the node inside one component plane
+HGPU_HD int sp_of_slot(int s)
+{
+    int x, y, z;
+    if (s < 512) {
+        x = (s & 1) | ((s >> 2) & 2) | ((s >> 4) & 4);
+        y = ((s >> 1) & 1) | ((s >> 3) & 2) | ((s >> 5) & 4);
+        z = ((s >> 2) & 1) | ((s >> 4) & 2) | ((s >> 6) & 4);
+    } else {
+        const int h = s - 512;
+        if (h < 81)       { z = 8; y = h / 9; x = h - 9 * y; }
+        else if (h < 153) { const int k = h - 81; y = 8; z = k / 9; x = k - 9 * z; }
+        else              { const int k = h - 153; x = 8; z = k >> 3; y = k & 7; }
+    }
+    return z * SP_Z + y * SP_ROW + x;
+}
+
+// z stage of wht_inverse taken apart: lo = what goes to the element's lower face, hi = to its upper
+// face; the y and x stages (face_inverse) are linear, so the contributions of two stacked elements
+// to the level they share are added BEFORE them.
+HGPU_HD void zsplit(const double (&v)[8], double (&lo)[4], double (&hi)[4])
+{
+    lo[0] = v[0] - v[1]; hi[0] = v[0] + v[1];
+    lo[1] = v[2] - v[4]; hi[1] = v[2] + v[4];
+    lo[2] = v[3] - v[5]; hi[2] = v[3] + v[5];
+    lo[3] = v[6] - v[7]; hi[3] = v[6] + v[7];
+}
+HGPU_HD void face_inverse(const double (&m)[4], double (&f)[4])      // f[jx + 2 jy]
+{
+    const double p0 = m[0] - m[1], p1 = m[0] + m[1], q0 = m[2] - m[3], q1 = m[2] + m[3];
+    f[0] = p0 - q0; f[1] = p0 + q0; f[2] = p1 - q1; f[3] = p1 + q1;
+}
+
+// the four nodes (x + dx, y + dy) of one level of a thread's column, one component plane
+HGPU_HD void gather_face(const double *plane, int o, double &w0, double &w1, double &w2, double &w3)
+{
+    w0 = plane[o]; w1 = plane[o + 1]; w2 = plane[o + SP_ROW]; w3 = plane[o + SP_ROW + 1];
+}
+
+// One element of a structured tile: w = corner values (j = jx + 2 jy + 4 jz) per component ->
+// scaled modes split by face.
+HGPU_HD void struct_element(const double (&wx)[8], const double (&wy)[8], const double (&wz)[8],
+                                               double a, double c, double b,
+                                               double (&lo)[3][4], double (&hi)[3][4])
+{
+    double tx[8], ty[8], tz[8], vx[8], vy[8], vz[8];
+    wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+    scale_modes(tx, ty, tz, a, c, b, vx, vy, vz);
+    zsplit(vx, lo[0], hi[0]); zsplit(vy, lo[1], hi[1]); zsplit(vz, lo[2], hi[2]);
+}
+
+// accumulator update of one (dx, dy) node of one level: f = per component value
+HGPU_HD void acc_add3(double *acc, int o, double fx, double fy, double fz)
+{
+    acc[o] += fx; acc[o + SP_C] += fy; acc[o + 2 * SP_C] += fz;
+}
+
 // WPASS (MODE 1, fused update; opt-in, HGPU_FLAG_WPASS): on a tile whose entries share one beta, the
 // damped displacement w = u1 + beta (u1 - u2) is formed ONCE PER STAGED NODE right after the tile has
 // landed (in place, over the u1 stage) instead of once per element corner, so the element phase
@@ -567,10 +646,12 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
 // nodes, which needs u1 and u2, is put into the accumulator in the same pass (the forces are then
 // added on top of it and the sum is scaled by 1/mass where the default path adds the inertia term
 // last): m2, m1 of a tile's nodes are therefore prefetched one tile ahead.
-template <int MODE, bool DENSE, int THREADS, bool WPASS = false>
+template <int MODE, bool DENSE, int THREADS, bool WPASS = false, bool STRUCT = false>
 __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 {
     static_assert(!WPASS || (MODE == 1 && !DENSE), "WPASS is a variant of the Rayleigh + effective kernel");
+    static_assert(!STRUCT || ((MODE == 0 || MODE == 1) && !DENSE && !WPASS && THREADS == 256),
+                  "STRUCT: effective stiffness with or without Rayleigh damping, 256 threads");
     constexpr bool U2E = MODE != 0;          // elements read u2
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -655,6 +736,20 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         const int *m_nn = smeta[(it + 2) & (META_RING - 1)], *m_prv = smeta[(it - 1) & (META_RING - 1)];
         const char *fb_prv = fbuf + ((it - 1) & 1) * fbuf_bytes;
         char *fb_cur = fbuf + (it & 1) * fbuf_bytes;
+        // STRUCT: node-table rows of this thread's two owned nodes and the tile's coefficients, requested
+        // before the landing wait so that the pre-pass finds them (no register is carried between tiles)
+        const bool st = STRUCT && fuse && m_cur[15] != 0;
+        double snt[2][3], scf[3];
+        if (STRUCT && st) {
+            const int n0e = meta_group(m_cur, 0).x;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const double *nt = A.nt3 + 3 * (size_t)(n0e + tid + 256 * q);
+                snt[q][0] = ldg_f64_pinned(nt); snt[q][1] = ldg_f64_pinned(nt + 1); snt[q][2] = ldg_f64_pinned(nt + 2);
+            }
+            const double *tc = A.tile_coef + 4 * (size_t)t;
+            scf[0] = ldg_f64_pinned(tc); scf[1] = ldg_f64_pinned(tc + 1); scf[2] = ldg_f64_pinned(tc + 2);
+        }
         cp_async_wait_all();
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1's stage
         if (it > 0 && tid == 0) publish_flag(A.flag + meta_group(m_prv, 3).z, A.epoch);
@@ -680,6 +775,133 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         const bool prv_pending = it > 0;
         double ntv[NT_PRE][3];
         unsigned int flag_value = A.epoch;
+        if (STRUCT && st) {
+            // ---- structured tile (see the comment above sp_of_slot) ------------------------------------
+            const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
+            // pre-pass, read side: w of this thread's (up to) three staged nodes -- slots tid, tid + 256 and
+            // 512 + tid -- and the inertia term m2 u1 - m1 u2 of the two owned ones (0 for SPECIAL nodes)
+            double wv[3][3], iv[2][3];
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const int k = 3 * (q < 2 ? tid + 256 * q : 512 + tid);
+                if (q < 2 || tid < 217) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double x1 = su1[k + c];
+                        double x2 = 0.0;
+                        if (MODE == 1 || q < 2) x2 = su2[k + c];
+                        wv[q][c] = MODE == 1 ? fma(scf[2], x1 - x2, x1) : x1;
+                        if (q < 2) iv[q][c] = snt[q][1] * x1 - snt[q][2] * x2;
+                    }
+                }
+            }
+            __syncthreads();                    // the raw stage has been read by everybody
+            double *W = su1;                    // three padded planes over the raw stage ...
+            double *srm_own = su1 + SP_TOTAL;   // ... and 1/mass of the owned nodes behind them
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                if (q < 2 || tid < 217) {
+                    const int sl = q < 2 ? tid + 256 * q : 512 + tid;
+                    const int sp = sp_of_slot(sl);
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        W[sp + c * SP_C] = wv[q][c];
+                        if (q < 2) acc[sp + c * SP_C] = iv[q][c];       // the accumulator starts from the inertia term
+                    }
+                    if (q < 2) srm_own[sl] = snt[q][0];
+                }
+            }
+            if (prv_pending) {                  // flags of the previous tile's publishers: checked after pass A
+                const int4 md = meta_group(m_prv, 3);
+                if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_prv, tid));
+            }
+            __syncthreads();
+            const double ca = -0.5625 * (scf[1] + 2.0 * scf[0]), cc = -0.5625 * scf[1], cb = -0.5625 * scf[0];
+            const int o0 = (2 * zq) * SP_Z + y * SP_ROW + x;
+            double wx[8], wy[8], wz[8], mid[3][4];
+            // ---- lower element of the pair: levels 2 zq, 2 zq + 1 ----
+            gather_face(W, o0, wx[0], wx[1], wx[2], wx[3]);
+            gather_face(W + SP_C, o0, wy[0], wy[1], wy[2], wy[3]);
+            gather_face(W + 2 * SP_C, o0, wz[0], wz[1], wz[2], wz[3]);
+            gather_face(W, o0 + SP_Z, wx[4], wx[5], wx[6], wx[7]);
+            gather_face(W + SP_C, o0 + SP_Z, wy[4], wy[5], wy[6], wy[7]);
+            gather_face(W + 2 * SP_C, o0 + SP_Z, wz[4], wz[5], wz[6], wz[7]);
+            {
+                double lo[3][4], fl[3][4];
+                struct_element(wx, wy, wz, ca, cc, cb, lo, mid);
+#pragma unroll
+                for (int c = 0; c < 3; c++) face_inverse(lo[c], fl[c]);
+                // pass A: lower level, dx = 0
+                acc_add3(acc, o0, fl[0][0], fl[1][0], fl[2][0]);
+                __syncwarp();
+                acc_add3(acc, o0 + SP_ROW, fl[0][2], fl[1][2], fl[2][2]);
+                if (prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
+                __syncthreads();
+                if (prv_pending) {
+                    request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
+                    cp_async_commit();
+                }
+                // pass B: lower level, dx = 1
+                acc_add3(acc, o0 + 1, fl[0][1], fl[1][1], fl[2][1]);
+                __syncwarp();
+                acc_add3(acc, o0 + SP_ROW + 1, fl[0][3], fl[1][3], fl[2][3]);
+            }
+            // ---- upper element: levels 2 zq + 1 (kept in registers), 2 zq + 2 ----
+#pragma unroll
+            for (int j = 0; j < 4; j++) { wx[j] = wx[4 + j]; wy[j] = wy[4 + j]; wz[j] = wz[4 + j]; }
+            gather_face(W, o0 + 2 * SP_Z, wx[4], wx[5], wx[6], wx[7]);
+            gather_face(W + SP_C, o0 + 2 * SP_Z, wy[4], wy[5], wy[6], wy[7]);
+            gather_face(W + 2 * SP_C, o0 + 2 * SP_Z, wz[4], wz[5], wz[6], wz[7]);
+            __syncthreads();                    // pass B is complete before anybody starts pass C
+            {
+                double lo[3][4], top[3][4], fm[3][4], ft[3][4];
+                struct_element(wx, wy, wz, ca, cc, cb, lo, top);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) mid[c][k] += lo[c][k];      // the shared level, complete in z
+                    face_inverse(mid[c], fm[c]); face_inverse(top[c], ft[c]);
+                }
+                // what the next tile needs in registers
+                if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
+                if (has_next && m_nxt[15] == 0 && tid < nxt_ne) enext = load_entry<MODE>(A, nxt_eb + tid);
+                // pass C: middle and upper level, dx = 0
+                acc_add3(acc, o0 + SP_Z, fm[0][0], fm[1][0], fm[2][0]);
+                acc_add3(acc, o0 + 2 * SP_Z, ft[0][0], ft[1][0], ft[2][0]);
+                __syncwarp();
+                acc_add3(acc, o0 + SP_Z + SP_ROW, fm[0][2], fm[1][2], fm[2][2]);
+                acc_add3(acc, o0 + 2 * SP_Z + SP_ROW, ft[0][2], ft[1][2], ft[2][2]);
+                __syncthreads();
+                // pass D: dx = 1
+                acc_add3(acc, o0 + SP_Z + 1, fm[0][1], fm[1][1], fm[2][1]);
+                acc_add3(acc, o0 + 2 * SP_Z + 1, ft[0][1], ft[1][1], ft[2][1]);
+                __syncwarp();
+                acc_add3(acc, o0 + SP_Z + SP_ROW + 1, fm[0][3], fm[1][3], fm[2][3]);
+                acc_add3(acc, o0 + 2 * SP_Z + SP_ROW + 1, ft[0][3], ft[1][3], ft[2][3]);
+            }
+            __syncthreads();
+            // ---- publish the three far faces (slots 512 + h = partial force h of this tile) ----
+            if (tid < 217) {
+                double *dst = A.partial + 3 * ((size_t)meta_group(m_cur, 0).z + tid);
+                const int sp = sp_of_slot(512 + tid);
+#pragma unroll
+                for (int c = 0; c < 3; c++) { __stcg(dst + c, acc[sp + c * SP_C]); acc[sp + c * SP_C] = 0.0; }
+            }
+            // ---- this tile's own share of the update: scale by 1/mass (REGULAR nodes), hand it on ----
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int sl = tid + 256 * q, sp = sp_of_slot(sl);
+                const double rm = srm_own[sl];
+                double *o = A.unext + 3 * (size_t)(n0 + sl);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    double v = acc[sp + c * SP_C];
+                    if (rm > 0.0) v *= rm;
+                    acc[sp + c * SP_C] = v;         // record nodes take it from here (pend)
+                    o[c] = v;
+                }
+            }
+        } else {
         bool uni = false;                     // WPASS: this tile's entries share one beta
         if (WPASS) {
             const double beta_t = beta_pref;
@@ -924,6 +1146,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 settle_node(acc, su1, su2, i, __ldg(nt), __ldg(nt + 1), __ldg(nt + 2));
             }
         }
+        }
         cp_async_wait_all();                    // partial forces of the previous tile, this tile's finish data
         __syncthreads();                        // ... and every thread's published partial forces are written
         // (the flag is raised at the top of the next iteration: by then the stores have long been
@@ -940,7 +1163,12 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 if (tid < nrec_prv) { own_prv[0] = fb.pend[3 * tid]; own_prv[1] = fb.pend[3 * tid + 1]; own_prv[2] = fb.pend[3 * tid + 2]; }
                 if (tid < nrec) {
                     const int slot3 = reinterpret_cast<const uint2 *>(fb_cur)[tid].x & 0xffff;
-                    fb.pend[3 * tid] = acc[slot3]; fb.pend[3 * tid + 1] = acc[slot3 + 1]; fb.pend[3 * tid + 2] = acc[slot3 + 2];
+                    if (STRUCT && st) {
+                        const int sp = sp_of_slot(slot3 / 3);
+                        fb.pend[3 * tid] = acc[sp]; fb.pend[3 * tid + 1] = acc[sp + SP_C]; fb.pend[3 * tid + 2] = acc[sp + 2 * SP_C];
+                    } else {
+                        fb.pend[3 * tid] = acc[slot3]; fb.pend[3 * tid + 1] = acc[slot3 + 1]; fb.pend[3 * tid + 2] = acc[slot3 + 2];
+                    }
                 }
             }
         }
@@ -949,7 +1177,14 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         //      rows of SPECIAL nodes by the special-node update --------------------------------
         {
             const size_t g0 = 3 * (size_t)n0;
-            if (fuse) {
+            if (STRUCT && st) {
+                // handed on already; leave the accumulator clean for the next tile
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const int sp = sp_of_slot(tid + 256 * q);
+                    acc[sp] = 0.0; acc[sp + SP_C] = 0.0; acc[sp + 2 * SP_C] = 0.0;
+                }
+            } else if (fuse) {
                 double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);         // g0 is even
                 for (int k = tid; k < (nown3 >> 1); k += nthr) {
                     dst[k] = make_double2(acc[2 * k], acc[2 * k + 1]);

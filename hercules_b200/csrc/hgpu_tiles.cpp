@@ -154,6 +154,41 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
         }
         std::sort(halo.begin(), halo.begin() + npub);
         std::sort(halo.begin() + npub, halo.end());
+        // Structured tile?  (hgpu_internal.h)  The 9x9x9 node block is read off the core elements: element k
+        // of the Morton-ordered cell sits at (x, y, z) = de-interleave(k), its corner j at (x + jx, y + jy, z + jz).
+        bool is_struct = false;
+        int32_t sgrid[STRUCT_NODES];
+        if (caps.allow_struct && !is_self && nown == STRUCT_OWNED && (int32_t)elems.size() == STRUCT_OWNED &&
+            extras.empty() && (int32_t)halo.size() == STRUCT_HALO && npub == STRUCT_HALO) {
+            std::vector<int32_t> byc0(elems);
+            std::sort(byc0.begin(), byc0.end(), [&](int32_t x, int32_t y) { return lnid[8 * (size_t)x] < lnid[8 * (size_t)y]; });
+            std::fill(sgrid, sgrid + STRUCT_NODES, -1);
+            is_struct = true;
+            for (int32_t k = 0; k < STRUCT_OWNED && is_struct; k++) {
+                const int32_t *ln = lnid + 8 * (size_t)byc0[k];
+                if (ln[0] != a + k) { is_struct = false; break; }
+                int x = 0, y = 0, z = 0;
+                for (int bt = 0; bt < 3; bt++) { x |= ((k >> (3 * bt)) & 1) << bt; y |= ((k >> (3 * bt + 1)) & 1) << bt; z |= ((k >> (3 * bt + 2)) & 1) << bt; }
+                for (int j = 0; j < 8; j++) {
+                    int32_t &g = sgrid[((z + (j >> 2)) * 9 + (y + ((j >> 1) & 1))) * 9 + (x + (j & 1))];
+                    if (g == -1) g = ln[j]; else if (g != ln[j]) { is_struct = false; break; }
+                }
+            }
+            for (int z = 0; z < 9 && is_struct; z++) for (int y = 0; y < 9 && is_struct; y++) for (int x = 0; x < 9; x++) {
+                const int32_t g = sgrid[(z * 9 + y) * 9 + x];
+                const bool inner = x < 8 && y < 8 && z < 8;
+                if (g < 0 || (inner ? g != a + struct_morton3(x, y, z) : (g >= a && g < b))) { is_struct = false; break; }
+            }
+            // 217 distinct gathered nodes = the halo list
+            if (is_struct) {
+                std::vector<int32_t> hs;
+                hs.reserve(STRUCT_HALO);
+                for (int z = 0; z < 9; z++) for (int y = 0; y < 9; y++) for (int x = 0; x < 9; x++)
+                    if (x == 8 || y == 8 || z == 8) hs.push_back(sgrid[(z * 9 + y) * 9 + x]);
+                std::sort(hs.begin(), hs.end());
+                if (!std::equal(hs.begin(), hs.end(), halo.begin())) is_struct = false;
+            }
+        }
         // Entry order.  Threads take consecutive entries, and a shared-memory access of 16 lanes
         // (one half-warp of 8-byte words) is conflict-free when the 16 slots differ modulo 16.
         // Core entries sorted by their corner-0 node are, in a uniform region, the tile's own
@@ -299,6 +334,16 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
                 return top;
             };
             const int32_t nrest = (int32_t)nhalo - npub;
+            if (is_struct) {
+                // canonical order of the three far faces (hgpu_internal.h)
+                for (int z = 0; z < 9; z++) for (int y = 0; y < 9; y++) for (int x = 0; x < 9; x++) {
+                    if (x < 8 && y < 8 && z < 8) continue;
+                    const int32_t h = -1 - slot_of[sgrid[(z * 9 + y) * 9 + x]];
+                    hslot[(size_t)h] = struct_slot(x, y, z);
+                }
+                npub_slots = STRUCT_HALO;
+                nslots = STRUCT_NODES;
+            } else {
             // slack of up to 31 slots for the residue choice, as far as the capacities and the
             // slots the other group still needs allow
             const int32_t hi_pub = std::min(std::min(max_acc, max_slots - nrest), (nown + npub + 31) & ~15);
@@ -309,6 +354,7 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
             const int32_t top_all = nrest > 0 ? assign(npub, (int32_t)nhalo, top_pub, hi_all) : top_pub;
             if (top_all < 0) { err = "internal: no free halo slot"; return false; }
             nslots = top_all;
+            }
             // halo list in slot order, -1 marks an unused slot
             // (each tile's range of halo_id -- hence of the partial-force array -- is padded to a
             // multiple of 16 entries = 384 bytes, so that no 128-byte line of partial forces is
@@ -332,6 +378,7 @@ bool build_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TileCaps &
         for (int32_t n = a; n < b; n++) tile_of[n] = tile;
         plan.node_off.push_back(b);
         plan.tile_self.push_back(is_self ? 1 : 0);
+        plan.tile_struct.push_back(is_struct ? 1 : 0);
         plan.elem_off.push_back((int32_t)plan.elem_id.size());
         plan.elem_core.push_back(ncore);
         plan.halo_off.push_back((int32_t)plan.halo_id.size());
@@ -454,6 +501,16 @@ bool validate_tile_plan(int32_t E, int32_t N, const int32_t *lnid, const TilePla
                 }
             }
             if (core && (lnid[8 * (size_t)e] < a || lnid[8 * (size_t)e] >= b)) { err = "core element whose corner 0 is not owned"; return false; }
+            if (!pl.tile_struct.empty() && pl.tile_struct[t]) {
+                // canonical layout: entry k is the element at de-interleave(k), corner j in slot struct_slot(...)
+                if (nown != STRUCT_OWNED || ne != STRUCT_OWNED || npub != STRUCT_HALO || nh < STRUCT_HALO) { err = "structured tile with the wrong counts"; return false; }
+                int x = 0, y = 0, z = 0;
+                for (int bt = 0; bt < 3; bt++) { x |= ((k >> (3 * bt)) & 1) << bt; y |= ((k >> (3 * bt + 1)) & 1) << bt; z |= ((k >> (3 * bt + 2)) & 1) << bt; }
+                for (int j = 0; j < 8; j++)
+                    if (pl.elem_slot[8 * (size_t)(eb + k) + j] != struct_slot(x + (j & 1), y + ((j >> 1) & 1), z + (j >> 2))) {
+                        err = "structured tile whose slots are not canonical"; return false;
+                    }
+            }
             if (!core && !touches) { err = "tile evaluates an extra element that touches none of its nodes"; return false; }
         }
     }

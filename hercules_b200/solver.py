@@ -33,6 +33,7 @@ FLAG_TIMERS = 2
 FLAG_NO_OVERLAP = 4
 FLAG_TAIL_OVERLAP = 8
 FLAG_WPASS = 16
+FLAG_NO_STRUCT = 32
 
 
 class HerculesGpuError(RuntimeError):

@@ -109,6 +109,9 @@ typedef struct hgpu_params {
 #define HGPU_FLAG_WPASS 16       /* opt-in step-kernel variant (Rayleigh + effective, fused): on tiles of one material
                                    the damped displacement is formed once per staged node, not per element corner */
 
+#define HGPU_FLAG_NO_STRUCT 32   /* do not use the structured-tile path of the step kernel (aligned uniform 8x8x8 cells
+                                   of one material evaluated as z pairs from a per-node damped displacement) */
+
 typedef struct hgpu_solver hgpu_solver_t;
 
 /* Named per-phase device times in seconds, accumulated with CUDA events under the reference's
@@ -247,7 +250,7 @@ typedef struct hgpu_layout {
     double est_gather_wavefronts, est_scatter_wavefronts;
     int32_t max_tile_acc;             /* owned + published nodes of the largest tile (shared-memory accumulator) */
     int32_t max_tile_recs, max_tile_srcs;
-    int32_t pad_;
+    int32_t struct_tiles;             /* tiles that take the structured path (aligned uniform 8x8x8 cells of one material) */
     int64_t partial_slots;            /* (tile, node) partial forces exchanged between tiles per pass */
     int64_t deps_total;               /* sum over tiles of the lower tiles they wait for */
 } hgpu_layout_t;

@@ -428,3 +428,47 @@ def test_basin_workload_matches_oracle(hb, oracle):
         want[sel] += got[d[sel, 2 + j]] / deps[sel, None]
     assert np.array_equal(got[d[:, 0]], want)
     s.close()
+
+
+@pytest.mark.parametrize("damping", ["rayleigh", "none"])
+def test_structured_tiles_match_oracle(hb, oracle, damping):
+    """The structured-tile path of the step kernel (aligned 8x8x8 cells of one material evaluated as z
+    pairs from a per-node damped displacement, hgpu_kernels.cuh): a 32 x 32 x 24 two-layer mesh whose
+    interface is cell-aligned -- 18 of its 48 cells take the path, the far-face cells and (second case)
+    the cells that straddle an unaligned interface take the generic one -- stepped with a source against
+    the oracle (compute_addforce_effective + damping_addforce + solver_compute_displacement,
+    stiffness.c:180-237, damping.c:29-103, psolve.c:4072-4114), and against the same library with the
+    path switched off.  MODE 1 (Rayleigh) and MODE 0 (no damping)."""
+    from hercules_b200 import meshgen
+    dmp = hb.RAYLEIGH if damping == "rayleigh" else hb.NONE
+    odmp = oracle.RAYLEIGH if damping == "rayleigh" else oracle.NONE
+    for ztop in (200.0, 300.0):                # 200 m = 8 elements: aligned; 300 m = 12 elements: inside a cell
+        mesh, info = meshgen.uniform_halfspace(32, 32, 24, h=25.0, dt=0.002, damping=dmp,
+                                               layers=((0.0, 4000.0, 2000.0, 2600.0), (ztop, 6000.0, 3464.0, 2700.0)))
+        ce = meshgen.element_index(info, 13, 11, 9)
+        loaded = np.sort(mesh.elem_lnid[ce]).astype(np.int32)
+        steps = 10
+        rng = np.random.default_rng(8)
+        F = 1e9 * rng.standard_normal((steps, 8, 3))
+        u0 = 1e-3 * rng.standard_normal((info["N"], 3)); v0 = 1e-3 * rng.standard_normal((info["N"], 3))
+        m = oracle.Mesh(mesh.elem_lnid, mesh.eTable, mesh.nTable, mesh.dnode, mesh.edata, mesh.K1, mesh.K2)
+        st = oracle.State(m)
+        st.tm1[:], st.tm2[:] = u0, v0
+        for k in range(steps):
+            oracle.step(m, st, odmp, oracle.EFFECTIVE, 1.0, 0.002, loaded, F[k])
+        out = []
+        for flags in (0, hb.FLAG_NO_STRUCT):
+            s = hb.Solver(mesh, dt=0.002, damping=dmp, stiffness=hb.EFFECTIVE, freq=1.0, loaded_lnid=loaded, flags=flags)
+            nstruct = s.layout()["struct_tiles"]
+            assert (nstruct == 0) if flags else (nstruct == (18 if ztop == 200.0 else 9)), nstruct
+            s.store_all(hb.TM1, u0); s.store_all(hb.TM2, v0)
+            s.run(0, steps, F)
+            out.append(s.fetch_all(hb.TM2))
+            # the step-by-step entry points take the same path
+            s.store_all(hb.TM1, u0); s.store_all(hb.TM2, v0)
+            for k in range(steps):
+                s.step(k, F[k])
+            assert np.array_equal(s.fetch_all(hb.TM2), out[-1])
+            s.close()
+        assert rel_l2(out[0], st.tm2) < REL_TOL_RUN and rel_l2(out[1], st.tm2) < REL_TOL_RUN
+        assert rel_l2(out[0], out[1]) < 1e-13
