@@ -1181,6 +1181,25 @@ extern "C" int hgpu_source_preload(hgpu_solver_t *s, int32_t step0, int32_t nste
     return HGPU_OK;
 }
 
+extern "C" int hgpu_force_source_resident(hgpu_solver_t *s, int32_t step)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    const int n = s->P.nloaded;
+    if (n == 0) return HGPU_OK;
+    if (s->fstate != F_CLEAN)
+        return fail(HGPU_ESTATE, "hgpu_force_source_resident must precede the element forces (assignment, psolve.c:5921)");
+    if (step < s->Fall_step0 || (size_t)(step - s->Fall_step0) >= s->Fall_loaded)
+        return fail(HGPU_EINVAL, "hgpu_force_source_resident: step %d is not covered by the preloaded source history [%d, %d)",
+                    step, s->Fall_step0, s->Fall_step0 + (int32_t)s->Fall_loaded);
+    CK(cudaSetDevice(s->dev));
+    PhaseTimer pt(s, PH_ADDFORCE_S);
+    source_kernel<<<grid_for(3LL * n, 128), 128, 0, s->stream>>>(
+        n, s->d_loaded, s->d_Fall + 3 * (size_t)n * (size_t)(step - s->Fall_step0), s->P.dt2, s->force);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    return HGPU_OK;
+}
+
 extern "C" int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all)
 {
     if (!s) return fail(HGPU_EINVAL, "null solver");

@@ -191,6 +191,10 @@ class Solver:
             raise ValueError("F must be [nloaded][3]")
         _chk(self._L.hgpu_force_source(self._h, F.ctypes.data))
 
+    def compute_force_source_resident(self, step: int) -> None:
+        """compute_addforce_s from the rows source_preload left in HBM (no per-step host traffic)."""
+        _chk(self._L.hgpu_force_source_resident(self._h, step))
+
     def compute_force_stiffness(self) -> None:
         _chk(self._L.hgpu_force_stiffness(self._h))
 

@@ -186,6 +186,9 @@ int hgpu_step(hgpu_solver_t *s, int32_t step, const double *F);
 /* Source streaming (read_myForces does fseeko+fread per step, psolve.c:3651-3667):
  * copy F_all = [nsteps][nloaded][3] host doubles (rows step0.. of force_process.<rank>) to HBM once. */
 int hgpu_source_preload(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const double *F_all);
+/* compute_addforce_s (psolve.c:5912) for one step from the rows hgpu_source_preload left in HBM: what
+ * hgpu_force_source does, without the per-step host read (read_myForces) and host->device copy. */
+int hgpu_force_source_resident(hgpu_solver_t *s, int32_t step);
 /* nsteps steps starting at step0 with the source history resident in HBM.  F_all non-NULL =
  * preload rows for [step0, step0+nsteps) first; NULL = use what hgpu_source_preload left
  * resident (it must cover those steps). */

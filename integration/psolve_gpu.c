@@ -258,6 +258,25 @@ static void gpu_solver_run(void)
     }
     const int32_t saved_nstations = Param.theNumberOfStations;
 
+    /* Source streaming: read_myForces does one fseeko + fread of this rank's row of
+     * force_process.<rank> per step (psolve.c:3651-3667).  Here the rows of the next SRC_WIN steps are read
+     * with ONE fread into a page-locked buffer and copied to HBM (hgpu_source_preload); each step then
+     * applies its row on the device (hgpu_force_source_resident).  The window keeps the host buffer below
+     * 256 MB for extended sources with many loaded nodes.  PSOLVE_GPU_HOST_SOURCE=1 keeps the per-step
+     * read_myForces + hgpu_force_source pair. */
+    const int host_source = getenv("PSOLVE_GPU_HOST_SOURCE") ? atoi(getenv("PSOLVE_GPU_HOST_SOURCE")) : 0;
+    int32_t src_win = 0, src_have0 = 0, src_have = 0;
+    double *src_rows = NULL;
+    if (Global.theNodesLoaded > 0 && !host_source) {
+        const size_t row = sizeof(double) * 3 * (size_t)Global.theNodesLoaded;
+        size_t w = ((size_t)256 << 20) / row;
+        if (w < 1) w = 1;
+        if (w > (size_t)(Param.theTotalSteps - startingStep)) w = (size_t)(Param.theTotalSteps - startingStep);
+        src_win = (int32_t)(w > 0 ? w : 1);
+        src_rows = hgpu_host_alloc(row * (size_t)src_win);
+        if (!src_rows) solver_abort("gpu_solver_run", NULL, "hgpu_host_alloc: %s\n", hgpu_last_error());
+    }
+
     MPI_Barrier(comm_solver);
     double loop_t0 = MPI_Wtime();
     double host_io = 0, host_tap = 0, host_gpu = 0, tmark;      /* where the host spends the loop */
@@ -314,7 +333,20 @@ static void gpu_solver_run(void)
         if (dev_stations) Param.theNumberOfStations = 0;       /* rows are written by write_station_rows */
         solver_output_stations(step);
         Param.theNumberOfStations = saved_nstations;
-        solver_read_source_forces(step);                        /* read_myForces, psolve.c:3651 */
+        if (src_rows == NULL) {
+            solver_read_source_forces(step);                    /* read_myForces, psolve.c:3651 */
+        } else if (step >= src_have0 + src_have) {
+            /* next window of rows: same file, same offsets as read_myForces, one read */
+            const int32_t nrows = (Param.theTotalSteps - step) < src_win ? (Param.theTotalSteps - step) : src_win;
+            const off_t where = ((off_t)sizeof(int32_t)) + Global.theNodesLoaded * sizeof(int32_t)
+                              + (off_t)Global.theNodesLoaded * step * sizeof(double) * 3;
+            Timer_Start("Read My Forces");
+            hu_fseeko(Global.fpsource, where, SEEK_SET);
+            hu_fread(src_rows, sizeof(double), (size_t)Global.theNodesLoaded * 3 * (size_t)nrows, Global.fpsource);
+            Timer_Stop("Read My Forces");
+            GPU(hgpu_source_preload(theGpu, step, nrows, src_rows));
+            src_have0 = step; src_have = nrows;
+        }
         Timer_Stop("Solver I/O");
         host_io += MPI_Wtime() - tmark; tmark = MPI_Wtime();
 
@@ -324,7 +356,10 @@ static void gpu_solver_run(void)
          * hgpu_get_timers below. */
         Timer_Start("Compute Physics");
         Timer_Start("Compute addforces s");
-        if (Global.theNodesLoaded > 0) GPU(hgpu_force_source(theGpu, (const double *)Global.myForces));
+        if (Global.theNodesLoaded > 0) {
+            if (src_rows) GPU(hgpu_force_source_resident(theGpu, step));
+            else GPU(hgpu_force_source(theGpu, (const double *)Global.myForces));
+        }
         Timer_Stop("Compute addforces s");
         Timer_Start("Compute addforces e");
         GPU(hgpu_force_stiffness(theGpu));
@@ -387,6 +422,7 @@ static void gpu_solver_run(void)
     theGpu = NULL;
     free(st_ids); free(st_tmp); free(st_steps);
     hgpu_host_free(st_rows);
+    hgpu_host_free(src_rows);
 }
 
 void hgpu_hook_Timer_Start(char *name)
