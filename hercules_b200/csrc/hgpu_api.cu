@@ -146,6 +146,11 @@ struct hgpu_solver {
     double *t_beta = nullptr;            // per tile (processing order): the entries' common beta, or NaN
     double *t_coef = nullptr;            // per tile (processing order): {c1, c2, beta, -} of a structured tile
     int32_t n_struct = 0;                // structured tiles of one material (take the STRUCT path of the step kernel)
+    int4 *t_meta_s = nullptr;            // tiles in the order of the STRUCT launches: slot-table tiles, then structured ones
+    int32_t n_generic = 0;               // slot-table tiles (= index of the first structured tile in t_meta_s)
+    int64_t struct_entries = 0, generic_entries = 0;   // elements evaluated by structured / by late slot-table tiles
+    double generic_cost = 1.6;           // cost of a slot-table element relative to a structured one (CTA split)
+    std::vector<int64_t> ent_prefix_s;   // [ntiles + 1] prefix sum of entries over t_meta_s
     uint2 *t_rec = nullptr;              // finish records
     int32_t *t_src = nullptr, *t_dep = nullptr;
     double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
@@ -597,23 +602,48 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 tbeta[i] = b;
             }
             TRY(upload(s, &s->t_beta, tbeta.data(), tbeta.size()));
-            // structured tiles of ONE material (c1, c2, c3/c1 equal bit for bit over the cell): coefficients per tile
-            std::vector<double> tcoef(4 * (size_t)pl.ntiles, 0.0);
+            TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
+            // Structured tiles of ONE material (c1, c2, c3/c1 equal bit for bit over the cell) get their
+            // coefficients per tile and a second processing order for the STRUCT launches, in which they come
+            // LAST: [self tiles | other slot-table tiles, ascending | structured tiles, ascending].  A STRUCT
+            // launch walks the last part with one set of CTAs and the rest with another (step_kernel).
+            std::vector<uint8_t> sok((size_t)pl.ntiles, 0);
             s->n_struct = 0;
-            for (int32_t i = 0; i < pl.ntiles; i++) {
-                const int32_t t = order[i];
-                if (pl.tile_struct.empty() || !pl.tile_struct[t]) continue;
+            for (int32_t t = 0; t < pl.ntiles; t++) {
+                if (pl.tile_struct.empty() || !pl.tile_struct[t] || pl.tile_self[t]) continue;
                 const int32_t e0 = pl.elem_off[t], e1 = pl.elem_off[(size_t)t + 1];
                 bool same = e1 > e0;
                 for (int32_t k = e0 + 1; k < e1 && same; k++)
                     same = memcmp(&coef[3 * (size_t)k], &coef[3 * (size_t)e0], 3 * sizeof(double)) == 0;
-                if (!same) continue;
-                for (int c = 0; c < 3; c++) tcoef[4 * (size_t)i + c] = coef[3 * (size_t)e0 + c];
-                meta[(size_t)META_INTS * (size_t)i + 15] = 1;
-                s->n_struct++;
+                if (same) { sok[t] = 1; s->n_struct++; }
             }
-            TRY(upload(s, &s->t_coef, tcoef.data(), tcoef.size()));
-            TRY(upload(s, (int32_t **)&s->t_meta, meta.data(), meta.size()));
+            if (s->n_struct > 0) {
+                std::vector<int32_t> order_s;
+                order_s.reserve((size_t)pl.ntiles);
+                std::vector<int32_t> pos((size_t)pl.ntiles, 0);
+                for (int32_t i = 0; i < pl.ntiles; i++) pos[order[i]] = i;
+                for (int32_t i = 0; i < pl.ntiles; i++) if (!sok[order[i]]) order_s.push_back(order[i]);
+                s->n_generic = (int32_t)order_s.size();
+                for (int32_t i = 0; i < pl.ntiles; i++) if (sok[order[i]]) order_s.push_back(order[i]);
+                std::vector<int32_t> meta_s(meta.size());
+                std::vector<double> tcoef(4 * (size_t)pl.ntiles, 0.0);
+                s->struct_entries = 0; s->generic_entries = 0;
+                s->ent_prefix_s.assign((size_t)pl.ntiles + 1, 0);
+                { const char *cenv = getenv("HGPU_GENERIC_COST"); if (cenv && atof(cenv) > 0) s->generic_cost = atof(cenv); }
+                for (int32_t i = 0; i < pl.ntiles; i++) {
+                    const int32_t t = order_s[i];
+                    s->ent_prefix_s[(size_t)i + 1] = s->ent_prefix_s[i] + (pl.elem_off[(size_t)t + 1] - pl.elem_off[t]);
+                    memcpy(&meta_s[(size_t)META_INTS * (size_t)i], &meta[(size_t)META_INTS * (size_t)pos[t]], META_INTS * sizeof(int32_t));
+                    const int64_t ne = pl.elem_off[(size_t)t + 1] - pl.elem_off[t];
+                    if (sok[t]) {
+                        meta_s[(size_t)META_INTS * (size_t)i + 15] = 1;
+                        for (int c = 0; c < 3; c++) tcoef[4 * (size_t)i + c] = coef[3 * (size_t)pl.elem_off[t] + c];
+                        s->struct_entries += ne;
+                    } else if (!pl.tile_self[t]) s->generic_entries += ne;
+                }
+                TRY(upload(s, &s->t_coef, tcoef.data(), tcoef.size()));
+                TRY(upload(s, (int32_t **)&s->t_meta_s, meta_s.data(), meta_s.size()));
+            }
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
         TRY(upload(s, &s->t_ent_coef, coef.data(), coef.size()));
@@ -742,7 +772,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     if (s->h_err) cudaFreeHost(s->h_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta); dfree(s->t_coef);
+    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta); dfree(s->t_coef); dfree(s->t_meta_s);
     dfree(s->conv); dfree(s->t_ent_bkt); dfree(s->entry_of_elem); dfree(s->conv_scratch);
     dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
@@ -803,8 +833,31 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
-    const int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin), B = s->block;
+    int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin);
+    const int B = s->block;
     if (begin == 0) A.epoch = ++s->epoch;       // a new pass over the tiles (a split pass shares one epoch)
+    // STRUCT launch: the range is taken from the second processing order (structured tiles last); its
+    // structured part goes to CTAs [0, grid_struct), the slot-table part to the others, in proportion to
+    // the elements of either kind weighted by their relative cost
+    bool use_struct = fuse && !dense && (mode == 0 || mode == 1) && B == 256 && s->n_struct > 0 &&
+                      !(s->P.flags & HGPU_FLAG_WPASS) && end > s->n_generic;
+    if (use_struct) {
+        const int32_t gb = std::min(begin, s->n_generic), ge = s->n_generic, sb = std::max(begin, s->n_generic), se = end;
+        const int32_t ng = ge - gb, ns = se - sb;
+        const double wg = s->generic_cost * (double)(s->ent_prefix_s[ge] - s->ent_prefix_s[gb]);
+        const double ws = (double)(s->ent_prefix_s[se] - s->ent_prefix_s[sb]);
+        const int Gmax = max_grid > 0 ? std::min(max_grid, s->grid) : s->grid;
+        int Gs, Gg;
+        if (ng == 0) { Gs = std::min(Gmax, ns); Gg = 0; }
+        else {
+            Gs = (int)std::lround((double)Gmax * ws / (ws + wg));
+            Gs = std::max(1, std::min(Gs, std::min(ns, Gmax - 1)));
+            Gg = std::min(Gmax - Gs, ng);
+        }
+        G = Gs + Gg;
+        A.tile_meta = s->t_meta_s;
+        A.tile_begin = gb; A.ntiles = ge; A.struct_begin = sb; A.struct_end = se; A.grid_struct = Gs;
+    }
     // Cooperative launch: a tile's finish spins on flags raised by other CTAs of the same launch, so
     // every CTA must be resident -- the driver then either co-schedules the whole grid or fails the launch
     // (it never starts a part of it), whatever else shares the device.
@@ -826,8 +879,8 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     } while (0)
     if (fuse && !dense && mode == 1 && B == 256 && (s->P.flags & HGPU_FLAG_WPASS))
         fn = (const void *)step_kernel<1, false, 256, true>;       // opt-in variant, see hgpu_kernels.cuh
-    else if (fuse && !dense && (mode == 0 || mode == 1) && B == 256 && s->n_struct > 0) {
-        // structured tiles of the plan take the z-pair path, the others the generic one, in one launch
+    else if (use_struct) {
+        // structured tiles take their own path on their own CTAs, the others the slot-table path, in one launch
         if (mode == 0) { fn = (const void *)step_kernel<0, false, 256, false, true>; smem = (size_t)s->smem_nou2; }
         else fn = (const void *)step_kernel<1, false, 256, false, true>;
     }

@@ -153,7 +153,9 @@ struct StepArgs {
     double *partial;                    // [halo slots][3] published partial forces
     unsigned int *flag;                 // [ntiles] epoch of the tile's last publish
     unsigned int epoch;
-    int32_t tile_begin, ntiles;         // this launch processes tile_meta[tile_begin .. ntiles)
+    int32_t tile_begin, ntiles;         // this launch processes tile_meta[tile_begin .. ntiles) (slot-table tiles)
+    int32_t struct_begin, struct_end;   // ... and tile_meta[struct_begin .. struct_end) (structured tiles, STRUCT launches)
+    int32_t grid_struct;                // STRUCT launches: CTAs [0, grid_struct) walk the structured tiles
     int32_t cap_slots;                  // staged nodes per stage
     int32_t cap_acc;                    // accumulator nodes (owned + published)
     int32_t cap_owned;                  // owned nodes (pending buffer)
@@ -566,18 +568,18 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
 // ------------------------------------------------------------------------------------------
 // STRUCTURED tiles (hgpu_internal.h): one aligned 8x8x8 cell of equal elements of one material.
 // No slot table is needed: thread (x, y, zq) evaluates the two elements (x, y, 2 zq) and
-// (x, y, 2 zq + 1) of the cell -- a z pair -- from a copy of the damped displacement
+// (x, y, 2 zq + 1) of the cell, one after the other, from a copy of the damped displacement
 // w = u1 + beta (u1 - u2) that is formed ONCE PER NODE (729 nodes) right after the tile has landed,
 // in a padded structure-of-arrays layout [component][z][y][x] with row stride 12 and plane stride
 // 108: lanes = (x & 3, y), so the 16 lanes of a half-warp (4 x values, 4 consecutive rows) always hit
 // 16 different 8-byte banks (12 y mod 16 = 0, 12, 8, 4) -- gathers and accumulator updates are
-// conflict-free.  What the two elements add to the 4 nodes they share (the middle level) is summed
-// in registers before the last two butterfly stages of the inverse transform, so a z pair makes
-// 36 gathers and 36 accumulator updates where two single elements make 96 and 48.
-// Accumulator updates are ordered by (dx, level class): within a warp by __syncwarp (the y
-// neighbours are lanes of the same warp), between warps by four barriers per tile:
-//   A: lower level, dx = 0   B: lower level, dx = 1   C: middle + upper level, dx = 0   D: ..., dx = 1
-// (warps = (x >> 2, zq): the x = 4 column and the even levels are shared between warps).
+// conflict-free, and an element costs 24 gathers instead of 48.
+// Accumulator updates are ordered by dx: within a warp by __syncwarp (the y neighbours are lanes of the
+// same warp), between warps by two barriers per round = four per tile where the slot-table path needs
+// sixteen (warps = (x >> 2, zq): in one round the warps touch disjoint level pairs, so only the x = 4
+// column is shared between warps, and only between the dx = 0 and dx = 1 passes).
+// (A variant that summed the two elements' shares of their common level in registers before the last
+// butterfly stages -- 36 gathers and 36 updates per pair -- was correct but spilled: r02 call 2.)
 // ------------------------------------------------------------------------------------------
 constexpr int SP_ROW = 12, SP_Z = 108, SP_C = 972, SP_TOTAL = 3 * SP_C;     // doubles
 
@@ -599,38 +601,10 @@ HGPU_HD int sp_of_slot(int s)
     return z * SP_Z + y * SP_ROW + x;
 }
 
-// z stage of wht_inverse taken apart: lo = what goes to the element's lower face, hi = to its upper
-// face; the y and x stages (face_inverse) are linear, so the contributions of two stacked elements
-// to the level they share are added BEFORE them.
-HGPU_HD void zsplit(const double (&v)[8], double (&lo)[4], double (&hi)[4])
-{
-    lo[0] = v[0] - v[1]; hi[0] = v[0] + v[1];
-    lo[1] = v[2] - v[4]; hi[1] = v[2] + v[4];
-    lo[2] = v[3] - v[5]; hi[2] = v[3] + v[5];
-    lo[3] = v[6] - v[7]; hi[3] = v[6] + v[7];
-}
-HGPU_HD void face_inverse(const double (&m)[4], double (&f)[4])      // f[jx + 2 jy]
-{
-    const double p0 = m[0] - m[1], p1 = m[0] + m[1], q0 = m[2] - m[3], q1 = m[2] + m[3];
-    f[0] = p0 - q0; f[1] = p0 + q0; f[2] = p1 - q1; f[3] = p1 + q1;
-}
-
 // the four nodes (x + dx, y + dy) of one level of a thread's column, one component plane
 HGPU_HD void gather_face(const double *plane, int o, double &w0, double &w1, double &w2, double &w3)
 {
     w0 = plane[o]; w1 = plane[o + 1]; w2 = plane[o + SP_ROW]; w3 = plane[o + SP_ROW + 1];
-}
-
-// One element of a structured tile: w = corner values (j = jx + 2 jy + 4 jz) per component ->
-// scaled modes split by face.
-HGPU_HD void struct_element(const double (&wx)[8], const double (&wy)[8], const double (&wz)[8],
-                                               double a, double c, double b,
-                                               double (&lo)[3][4], double (&hi)[3][4])
-{
-    double tx[8], ty[8], tz[8], vx[8], vy[8], vz[8];
-    wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
-    scale_modes(tx, ty, tz, a, c, b, vx, vy, vz);
-    zsplit(vx, lo[0], hi[0]); zsplit(vy, lo[1], hi[1]); zsplit(vz, lo[2], hi[2]);
 }
 
 // accumulator update of one (dx, dy) node of one level: f = per component value
@@ -646,9 +620,14 @@ HGPU_HD void acc_add3(double *acc, int o, double fx, double fy, double fz)
 // nodes, which needs u1 and u2, is put into the accumulator in the same pass (the forces are then
 // added on top of it and the sum is scaled by 1/mass where the default path adds the inertia term
 // last): m2, m1 of a tile's nodes are therefore prefetched one tile ahead.
-template <int MODE, bool DENSE, int THREADS, bool WPASS = false, bool STRUCT = false>
-__global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
+// tile_loop: one CTA walks tiles t0, t0 + G, t0 + 2 G, ... (< tend) of the processing order.
+//   KIND 0: slot-table tiles (any shape)      KIND 1: structured tiles (fused update, MODE 0 or 1)
+// A STRUCT launch runs both loops, on different CTAs (step_kernel below): each loop then carries only its
+// own registers between tiles -- the two paths in ONE loop spilled (r02 call 2).
+template <int MODE, bool DENSE, int THREADS, bool WPASS, int KIND>
+__device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const int G, const int tend)
 {
+    constexpr bool STRUCT = KIND == 1;
     static_assert(!WPASS || (MODE == 1 && !DENSE), "WPASS is a variant of the Rayleigh + effective kernel");
     static_assert(!STRUCT || ((MODE == 0 || MODE == 1) && !DENSE && !WPASS && THREADS == 256),
                   "STRUCT: effective stiffness with or without Rayleigh damping, 256 threads");
@@ -683,13 +662,12 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
     //                   for the tile that is staged at the top of the next iteration
     //   node tables   : registers; requested before the accumulation passes of the last round
     __shared__ __align__(16) int smeta[META_RING][META_INTS];
-    const int G = gridDim.x;
-    int t = A.tile_begin + blockIdx.x;
-    if (t >= A.ntiles) return;
+    int t = t0;
+    if (t >= tend) return;
     for (int k = tid; k < A3; k += nthr) acc[k] = 0.0;
     fetch_meta_async(A, t, smeta[0], tid);
-    if (t + G < A.ntiles) fetch_meta_async(A, t + G, smeta[1], tid);
-    if (t + 2 * G < A.ntiles) fetch_meta_async(A, t + 2 * G, smeta[2], tid);
+    if (t + G < tend) fetch_meta_async(A, t + G, smeta[1], tid);
+    if (t + 2 * G < tend) fetch_meta_async(A, t + 2 * G, smeta[2], tid);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
@@ -700,11 +678,11 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         if (U2E || fuse) stage_tile<true, U2E>(A, ma, smem, smem + S3, tid, nthr, hid);
         else             stage_tile<false, false>(A, ma, smem, smem + S3, tid, nthr, hid);
         cp_async_commit();
-        if (t + G < A.ntiles) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
+        if (t + G < tend) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
     }
     Entry ecur, enext;
     enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
-    {
+    if (!STRUCT) {
         const int4 mb = meta_group(smeta[0], 1);
         if (tid < mb.y - mb.x) enext = load_entry<MODE>(A, mb.x + tid);
     }
@@ -726,30 +704,39 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         beta_pref = ldg_f64_pinned(A.tile_beta + t);
     }
 
+    double spre[2][3], cpre[3];          // STRUCT: node-table rows and coefficients of the NEXT structured tile
+    bool pre_ok = false;
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
         double *su2 = su1 + S3;
         const int tn = t + G;
-        const bool has_next = tn < A.ntiles;
-        const bool has_nn = tn + G < A.ntiles;
+        const bool has_next = tn < tend;
+        const bool has_nn = tn + G < tend;
         const int *m_cur = smeta[it & (META_RING - 1)], *m_nxt = smeta[(it + 1) & (META_RING - 1)];
         const int *m_nn = smeta[(it + 2) & (META_RING - 1)], *m_prv = smeta[(it - 1) & (META_RING - 1)];
         const char *fb_prv = fbuf + ((it - 1) & 1) * fbuf_bytes;
         char *fb_cur = fbuf + (it & 1) * fbuf_bytes;
-        // STRUCT: node-table rows of this thread's two owned nodes and the tile's coefficients, requested
-        // before the landing wait so that the pre-pass finds them (no register is carried between tiles)
-        const bool st = STRUCT && fuse && m_cur[15] != 0;
+        // STRUCT: node-table rows of this thread's two owned nodes and the tile's coefficients travel in
+        // registers from the previous structured tile's second round (spre / cpre); a structured tile that
+        // follows a slot-table tile (or is the CTA's first) requests them here, before the landing wait
+        constexpr bool st = STRUCT;           // every tile of this loop is a structured one (host-side lists)
         double snt[2][3], scf[3];
         if (STRUCT && st) {
-            const int n0e = meta_group(m_cur, 0).x;
+            if (!pre_ok) {
+                const int n0e = meta_group(m_cur, 0).x;
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const double *nt = A.nt3 + 3 * (size_t)(n0e + tid + 256 * q);
-                snt[q][0] = ldg_f64_pinned(nt); snt[q][1] = ldg_f64_pinned(nt + 1); snt[q][2] = ldg_f64_pinned(nt + 2);
+                for (int q = 0; q < 2; q++) {
+                    const double *nt = A.nt3 + 3 * (size_t)(n0e + tid + 256 * q);
+                    spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
+                }
+                const double *tc = A.tile_coef + 4 * (size_t)t;
+                cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
             }
-            const double *tc = A.tile_coef + 4 * (size_t)t;
-            scf[0] = ldg_f64_pinned(tc); scf[1] = ldg_f64_pinned(tc + 1); scf[2] = ldg_f64_pinned(tc + 2);
+#pragma unroll
+            for (int q = 0; q < 2; q++) { snt[q][0] = spre[q][0]; snt[q][1] = spre[q][1]; snt[q][2] = spre[q][2]; }
+            scf[0] = cpre[0]; scf[1] = cpre[1]; scf[2] = cpre[2];
         }
+        pre_ok = false;
         cp_async_wait_all();
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1's stage
         if (it > 0 && tid == 0) publish_flag(A.flag + meta_group(m_prv, 3).z, A.epoch);
@@ -759,7 +746,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             const int4 nxt = meta_group(m_nxt, 0);
             if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
-            if (tn + 2 * G < A.ntiles) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & (META_RING - 1)], tid);
+            if (tn + 2 * G < tend) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & (META_RING - 1)], tid);
         }
         cp_async_commit();
         // what the element phase needs of this tile's offsets
@@ -773,7 +760,6 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
         // the previous tile is finished during this one: its publishers' flags are polled and its
         // partial forces requested between the accumulation passes of the last round
         const bool prv_pending = it > 0;
-        double ntv[NT_PRE][3];
         unsigned int flag_value = A.epoch;
         if (STRUCT && st) {
             // ---- structured tile (see the comment above sp_of_slot) ------------------------------------
@@ -818,68 +804,59 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             __syncthreads();
             const double ca = -0.5625 * (scf[1] + 2.0 * scf[0]), cc = -0.5625 * scf[1], cb = -0.5625 * scf[0];
             const int o0 = (2 * zq) * SP_Z + y * SP_ROW + x;
-            double wx[8], wy[8], wz[8], mid[3][4];
-            // ---- lower element of the pair: levels 2 zq, 2 zq + 1 ----
-            gather_face(W, o0, wx[0], wx[1], wx[2], wx[3]);
-            gather_face(W + SP_C, o0, wy[0], wy[1], wy[2], wy[3]);
-            gather_face(W + 2 * SP_C, o0, wz[0], wz[1], wz[2], wz[3]);
-            gather_face(W, o0 + SP_Z, wx[4], wx[5], wx[6], wx[7]);
-            gather_face(W + SP_C, o0 + SP_Z, wy[4], wy[5], wy[6], wy[7]);
-            gather_face(W + 2 * SP_C, o0 + SP_Z, wz[4], wz[5], wz[6], wz[7]);
-            {
-                double lo[3][4], fl[3][4];
-                struct_element(wx, wy, wz, ca, cc, cb, lo, mid);
+            // two rounds: element (x, y, 2 zq), then (x, y, 2 zq + 1).  Each is gathered, evaluated and added to
+            // the accumulator on its own (carrying anything from the first to the second costs the registers
+            // the operator itself needs: measured, r02 call 2 -- 600 bytes of spills per thread and tile).
+#pragma unroll 1
+            for (int r = 0; r < 2; r++) {
+                const int o = o0 + r * SP_Z;
+                double fx[8], fy[8], fz[8];
+                {
+                    double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8];
+                    gather_face(W, o, wx[0], wx[1], wx[2], wx[3]);
+                    gather_face(W + SP_C, o, wy[0], wy[1], wy[2], wy[3]);
+                    gather_face(W + 2 * SP_C, o, wz[0], wz[1], wz[2], wz[3]);
+                    gather_face(W, o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
+                    gather_face(W + SP_C, o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
+                    gather_face(W + 2 * SP_C, o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
+                    wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+                    scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);        // w* reused as the scaled modes
+                    wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
+                }
+                if (r == 1) {                   // what the next tile needs in registers
+                    if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
+                    if (has_next) {
+                        const int n0n = meta_group(m_nxt, 0).x;
 #pragma unroll
-                for (int c = 0; c < 3; c++) face_inverse(lo[c], fl[c]);
-                // pass A: lower level, dx = 0
-                acc_add3(acc, o0, fl[0][0], fl[1][0], fl[2][0]);
+                        for (int q = 0; q < 2; q++) {
+                            const double *nt = A.nt3 + 3 * (size_t)(n0n + tid + 256 * q);
+                            spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
+                        }
+                        const double *tc = A.tile_coef + 4 * (size_t)tn;
+                        cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
+                        pre_ok = true;
+                    }
+                }
+                // pass dx = 0: corners (0, dy, dz); the y neighbours are lanes of this warp
+                acc_add3(acc, o, fx[0], fy[0], fz[0]);
+                acc_add3(acc, o + SP_Z, fx[4], fy[4], fz[4]);
                 __syncwarp();
-                acc_add3(acc, o0 + SP_ROW, fl[0][2], fl[1][2], fl[2][2]);
-                if (prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
+                acc_add3(acc, o + SP_ROW, fx[2], fy[2], fz[2]);
+                acc_add3(acc, o + SP_Z + SP_ROW, fx[6], fy[6], fz[6]);
+                if (r == 0 && prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
                 __syncthreads();
-                if (prv_pending) {
+                if (r == 0 && prv_pending) {
                     request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
                     cp_async_commit();
                 }
-                // pass B: lower level, dx = 1
-                acc_add3(acc, o0 + 1, fl[0][1], fl[1][1], fl[2][1]);
+                // pass dx = 1
+                acc_add3(acc, o + 1, fx[1], fy[1], fz[1]);
+                acc_add3(acc, o + SP_Z + 1, fx[5], fy[5], fz[5]);
                 __syncwarp();
-                acc_add3(acc, o0 + SP_ROW + 1, fl[0][3], fl[1][3], fl[2][3]);
-            }
-            // ---- upper element: levels 2 zq + 1 (kept in registers), 2 zq + 2 ----
-#pragma unroll
-            for (int j = 0; j < 4; j++) { wx[j] = wx[4 + j]; wy[j] = wy[4 + j]; wz[j] = wz[4 + j]; }
-            gather_face(W, o0 + 2 * SP_Z, wx[4], wx[5], wx[6], wx[7]);
-            gather_face(W + SP_C, o0 + 2 * SP_Z, wy[4], wy[5], wy[6], wy[7]);
-            gather_face(W + 2 * SP_C, o0 + 2 * SP_Z, wz[4], wz[5], wz[6], wz[7]);
-            __syncthreads();                    // pass B is complete before anybody starts pass C
-            {
-                double lo[3][4], top[3][4], fm[3][4], ft[3][4];
-                struct_element(wx, wy, wz, ca, cc, cb, lo, top);
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) mid[c][k] += lo[c][k];      // the shared level, complete in z
-                    face_inverse(mid[c], fm[c]); face_inverse(top[c], ft[c]);
-                }
-                // what the next tile needs in registers
-                if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
-                if (has_next && m_nxt[15] == 0 && tid < nxt_ne) enext = load_entry<MODE>(A, nxt_eb + tid);
-                // pass C: middle and upper level, dx = 0
-                acc_add3(acc, o0 + SP_Z, fm[0][0], fm[1][0], fm[2][0]);
-                acc_add3(acc, o0 + 2 * SP_Z, ft[0][0], ft[1][0], ft[2][0]);
-                __syncwarp();
-                acc_add3(acc, o0 + SP_Z + SP_ROW, fm[0][2], fm[1][2], fm[2][2]);
-                acc_add3(acc, o0 + 2 * SP_Z + SP_ROW, ft[0][2], ft[1][2], ft[2][2]);
+                acc_add3(acc, o + SP_ROW + 1, fx[3], fy[3], fz[3]);
+                acc_add3(acc, o + SP_Z + SP_ROW + 1, fx[7], fy[7], fz[7]);
                 __syncthreads();
-                // pass D: dx = 1
-                acc_add3(acc, o0 + SP_Z + 1, fm[0][1], fm[1][1], fm[2][1]);
-                acc_add3(acc, o0 + 2 * SP_Z + 1, ft[0][1], ft[1][1], ft[2][1]);
-                __syncwarp();
-                acc_add3(acc, o0 + SP_Z + SP_ROW + 1, fm[0][3], fm[1][3], fm[2][3]);
-                acc_add3(acc, o0 + 2 * SP_Z + SP_ROW + 1, ft[0][3], ft[1][3], ft[2][3]);
             }
-            __syncthreads();
             // ---- publish the three far faces (slots 512 + h = partial force h of this tile) ----
             if (tid < 217) {
                 double *dst = A.partial + 3 * ((size_t)meta_group(m_cur, 0).z + tid);
@@ -902,6 +879,7 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
                 }
             }
         } else {
+        double ntv[NT_PRE][3];
         bool uni = false;                     // WPASS: this tile's entries share one beta
         if (WPASS) {
             const double beta_t = beta_pref;
@@ -1218,6 +1196,23 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
             break;
         }
         t = tn;
+    }
+}
+
+// step_kernel: a launch over tiles [tile_begin, ntiles) of the slot-table list and, with STRUCT, over
+// [struct_begin, struct_end) of the structured list.  STRUCT: CTAs [0, grid_struct) walk the structured
+// tiles, the others the slot-table tiles.  Every CTA of the launch is resident (cooperative launch) and
+// each walks ITS tiles in ascending order, so the lowest tile whose flag is not raised yet never waits:
+// the argument that makes the single loop deadlock-free holds for any such split.
+template <int MODE, bool DENSE, int THREADS, bool WPASS = false, bool STRUCT = false>
+__global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
+{
+    if (STRUCT) {
+        const int gs = A.grid_struct;
+        if ((int)blockIdx.x < gs) tile_loop<MODE, DENSE, THREADS, false, STRUCT ? 1 : 0>(A, A.struct_begin + blockIdx.x, gs, A.struct_end);
+        else tile_loop<MODE, DENSE, THREADS, false, 0>(A, A.tile_begin + (blockIdx.x - gs), gridDim.x - gs, A.ntiles);
+    } else {
+        tile_loop<MODE, DENSE, THREADS, WPASS, 0>(A, A.tile_begin + blockIdx.x, gridDim.x, A.ntiles);
     }
 }
 

@@ -1,9 +1,9 @@
 // struct_check.cu -- HOST emulation of the structured-tile path of step_kernel (hgpu_kernels.cuh),
 // compiled by nvcc for the CPU and run by tests/test_struct_host.py (no GPU needed).
 //
-// It uses the kernel's own helpers (sp_of_slot, struct_element, zsplit, face_inverse, wht_*,
-// scale_modes) and mirrors the kernel's thread mapping and pass order (A, B, C, D with a __syncwarp
-// between the dy = 0 and dy = 1 halves) to check, for one aligned 8x8x8 cell:
+// It uses the kernel's own helpers (sp_of_slot, gather_face, acc_add3, wht_forward, scale_modes,
+// wht_inverse) and mirrors the kernel's thread mapping and pass order (two rounds of a dx = 0 and a dx = 1
+// pass, a __syncwarp between the dy = 0 and dy = 1 halves of a pass) to check, for one aligned 8x8x8 cell:
 //   1. the padded layout: 729 slots map to 729 different offsets inside a plane of SP_C doubles;
 //   2. bank conflicts: every gather / accumulator access of a warp is conflict-free (16 lanes of a
 //      half-warp hit 16 different 8-byte banks);
@@ -77,80 +77,59 @@ int main()
             for (int c = 0; c < 3; c++) ref[3 * (((z + (j >> 2)) * 9 + y + ((j >> 1) & 1)) * 9 + x + (j & 1)) + c] += f[c][j];
     }
 
-    // ---- the kernel's schedule, 256 threads ----------------------------------------------------------
-    struct Regs { double wk[3][4], mid[3][4], fl[3][4], fm[3][4], ft[3][4]; int o0; };
+    // ---- the kernel's schedule, 256 threads: two rounds (element z = 2 zq, then 2 zq + 1), each with a
+    //      dx = 0 pass and a dx = 1 pass (barrier between them), each pass with a dy = 0 and a dy = 1 half
+    //      (__syncwarp between them), each half touching the element's lower and upper level ------------
+    struct Regs { double f[3][8]; int o; };
     std::vector<Regs> R(256);
-    // lower element + gathers
     std::vector<Access> g;
-    for (int lvl = 0; lvl < 3; lvl++) for (int k = 0; k < 4; k++) {       // one gather instruction = (level, face corner)
-        g.clear();
+    for (int r = 0; r < 2; r++) {
+        for (int lvl = 0; lvl < 2; lvl++) for (int k = 0; k < 4; k++) {       // one gather instruction = (level, face corner)
+            g.clear();
+            for (int tid = 0; tid < 256; tid++) {
+                const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
+                const int o = (2 * zq + r) * SP_Z + y * SP_ROW + x;
+                g.push_back({tid, o + lvl * SP_Z + (k & 1) + SP_ROW * (k >> 1)});
+            }
+            check_banks(g, "gather");
+        }
         for (int tid = 0; tid < 256; tid++) {
             const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-            const int o0 = (2 * zq) * SP_Z + y * SP_ROW + x;
-            g.push_back({tid, o0 + lvl * SP_Z + (k & 1) + SP_ROW * (k >> 1)});
+            Regs &q = R[tid];
+            q.o = (2 * zq + r) * SP_Z + y * SP_ROW + x;
+            double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8];
+            gather_face(W.data(), q.o, wx[0], wx[1], wx[2], wx[3]);
+            gather_face(W.data() + SP_C, q.o, wy[0], wy[1], wy[2], wy[3]);
+            gather_face(W.data() + 2 * SP_C, q.o, wz[0], wz[1], wz[2], wz[3]);
+            gather_face(W.data(), q.o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
+            gather_face(W.data() + SP_C, q.o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
+            gather_face(W.data() + 2 * SP_C, q.o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
+            wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+            scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);
+            wht_inverse(wx, q.f[0]); wht_inverse(wy, q.f[1]); wht_inverse(wz, q.f[2]);
         }
-        check_banks(g, "gather");
-    }
-    for (int tid = 0; tid < 256; tid++) {
-        const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-        Regs &r = R[tid];
-        r.o0 = (2 * zq) * SP_Z + y * SP_ROW + x;
-        double wx[8], wy[8], wz[8], lo[3][4];
-        gather_face(W.data(), r.o0, wx[0], wx[1], wx[2], wx[3]);
-        gather_face(W.data() + SP_C, r.o0, wy[0], wy[1], wy[2], wy[3]);
-        gather_face(W.data() + 2 * SP_C, r.o0, wz[0], wz[1], wz[2], wz[3]);
-        gather_face(W.data(), r.o0 + SP_Z, wx[4], wx[5], wx[6], wx[7]);
-        gather_face(W.data() + SP_C, r.o0 + SP_Z, wy[4], wy[5], wy[6], wy[7]);
-        gather_face(W.data() + 2 * SP_C, r.o0 + SP_Z, wz[4], wz[5], wz[6], wz[7]);
-        struct_element(wx, wy, wz, ca, cc, cb, lo, r.mid);
-        for (int c = 0; c < 3; c++) face_inverse(lo[c], r.fl[c]);
-        for (int j = 0; j < 4; j++) { r.wk[0][j] = wx[4 + j]; r.wk[1][j] = wy[4 + j]; r.wk[2][j] = wz[4 + j]; }
-    }
-    // passes: (name, per half: list of (level offset, which array, k))
-    auto run_pass = [&](const char *name, int dx, bool upper) {
-        std::map<int, int> warp_of;                     // offset -> warp that touched it in this pass
-        for (int half = 0; half < 2; half++) {
-            const int k = dx + 2 * half, d = dx + SP_ROW * half;
-            std::map<int, int> lane_of;                 // offset -> tid within this half
-            std::vector<Access> a1, a2;
-            for (int tid = 0; tid < 256; tid++) {
-                Regs &r = R[tid];
-                std::vector<std::pair<int, const double (*)[4]>> tg;
-                if (!upper) tg.push_back({r.o0 + d, r.fl});
-                else { tg.push_back({r.o0 + SP_Z + d, r.fm}); tg.push_back({r.o0 + 2 * SP_Z + d, r.ft}); }
-                for (size_t i = 0; i < tg.size(); i++) {
-                    const int o = tg[i].first;
-                    CHECK(lane_of.insert({o, tid}).second, "%s half %d: threads %d and %d update the same accumulator", name, half, lane_of[o], tid);
-                    auto w = warp_of.find(o);
-                    CHECK(w == warp_of.end() || w->second == tid / 32, "%s: warps %d and %d update the same accumulator inside one pass",
-                          name, w == warp_of.end() ? -1 : w->second, tid / 32);
-                    warp_of[o] = tid / 32;
-                    acc_add3(acc.data(), o, tg[i].second[0][k], tg[i].second[1][k], tg[i].second[2][k]);
-                    (i == 0 ? a1 : a2).push_back({tid, o});
+        for (int dx = 0; dx < 2; dx++) {                    // one pass = the code between two barriers
+            std::map<int, int> warp_of;                     // offset -> warp that touched it in this pass
+            for (int half = 0; half < 2; half++) {          // dy; a __syncwarp separates the halves
+                std::map<int, int> lane_of;
+                std::vector<Access> a1, a2;
+                for (int tid = 0; tid < 256; tid++) {
+                    Regs &q = R[tid];
+                    for (int lvl = 0; lvl < 2; lvl++) {
+                        const int o = q.o + lvl * SP_Z + dx + SP_ROW * half, j = dx + 2 * half + 4 * lvl;
+                        CHECK(lane_of.insert({o, tid}).second, "round %d dx %d half %d: threads %d and %d update the same accumulator", r, dx, half, lane_of[o], tid);
+                        auto w = warp_of.find(o);
+                        CHECK(w == warp_of.end() || w->second == tid / 32, "round %d dx %d: warps %d and %d update the same accumulator inside one pass",
+                              r, dx, w == warp_of.end() ? -1 : w->second, tid / 32);
+                        warp_of[o] = tid / 32;
+                        acc_add3(acc.data(), o, q.f[0][j], q.f[1][j], q.f[2][j]);
+                        (lvl == 0 ? a1 : a2).push_back({tid, o});
+                    }
                 }
+                check_banks(a1, "accumulate"); check_banks(a2, "accumulate");
             }
-            check_banks(a1, name);
-            if (!a2.empty()) check_banks(a2, name);
-        }
-    };
-    run_pass("pass A", 0, false);
-    run_pass("pass B", 1, false);
-    // upper element
-    for (int tid = 0; tid < 256; tid++) {
-        Regs &r = R[tid];
-        double wx[8], wy[8], wz[8], lo[3][4], top[3][4];
-        for (int j = 0; j < 4; j++) { wx[j] = r.wk[0][j]; wy[j] = r.wk[1][j]; wz[j] = r.wk[2][j]; }
-        gather_face(W.data(), r.o0 + 2 * SP_Z, wx[4], wx[5], wx[6], wx[7]);
-        gather_face(W.data() + SP_C, r.o0 + 2 * SP_Z, wy[4], wy[5], wy[6], wy[7]);
-        gather_face(W.data() + 2 * SP_C, r.o0 + 2 * SP_Z, wz[4], wz[5], wz[6], wz[7]);
-        struct_element(wx, wy, wz, ca, cc, cb, lo, top);
-        for (int c = 0; c < 3; c++) {
-            for (int k = 0; k < 4; k++) r.mid[c][k] += lo[c][k];
-            face_inverse(r.mid[c], r.fm[c]); face_inverse(top[c], r.ft[c]);
         }
     }
-    run_pass("pass C", 0, true);
-    run_pass("pass D", 1, true);
 
     // ---- 4. numerics ---------------------------------------------------------------------------------
     double worst = 0.0, scale = 0.0;
