@@ -149,8 +149,10 @@ struct hgpu_solver {
     int4 *t_meta_s = nullptr;            // tiles in the order of the STRUCT launches: slot-table tiles, then structured ones
     int32_t n_generic = 0;               // slot-table tiles (= index of the first structured tile in t_meta_s)
     int64_t struct_entries = 0, generic_entries = 0;   // elements evaluated by structured / by late slot-table tiles
-    double generic_cost = 1.6;           // cost of a slot-table element relative to a structured one (CTA split)
+    double generic_cost = 2.2;           // cost of a slot-table element relative to a structured one (CTA split)
     std::vector<int64_t> ent_prefix_s;   // [ntiles + 1] prefix sum of entries over t_meta_s
+    int *d_queue = nullptr;              // {next slot-table tile, next structured tile} of a STRUCT launch (HGPU_DYNAMIC=0: unused)
+    bool dynamic_tiles = true;
     uint2 *t_rec = nullptr;              // finish records
     int32_t *t_src = nullptr, *t_dep = nullptr;
     double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
@@ -643,6 +645,8 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 }
                 TRY(upload(s, &s->t_coef, tcoef.data(), tcoef.size()));
                 TRY(upload(s, (int32_t **)&s->t_meta_s, meta_s.data(), meta_s.size()));
+                TRY(dalloc(s, &s->d_queue, 2));
+                { const char *denv = getenv("HGPU_DYNAMIC"); s->dynamic_tiles = !(denv && atoi(denv) == 0); }
             }
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
@@ -694,7 +698,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // share so that solvers with different plans can coexist in one process
         const int smem_cap = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
         if (s->smem_u2 > smem_cap) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan needs %d bytes of shared memory (> %d)", s->smem_u2, smem_cap); }
-        if (s->n_struct > 0 && 3 * s->cap_slots + 3 * s->cap_owned < SP_TOTAL + STRUCT_OWNED) {
+        if (s->n_struct > 0 && 3 * s->cap_slots + 3 * s->cap_owned < SP_TOTAL + STRUCT_OWNED + SX4_TOTAL) {
             hgpu_finalize(s); return fail(HGPU_EINVAL, "internal: stage too small for the structured path");
         }
 #define SETUP(T)                                                                                             \
@@ -772,7 +776,7 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
     if (s->h_err) cudaFreeHost(s->h_err);
     for (int b = 0; b < 3; b++) dfree(s->u[b]);
     dfree(s->force); dfree(s->mass); dfree(s->m2); dfree(s->m1); dfree(s->nt3); dfree(s->etab); dfree(s->Kd);
-    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta); dfree(s->t_coef); dfree(s->t_meta_s);
+    dfree(s->t_meta); dfree(s->t_ent_slot); dfree(s->t_ent_coef); dfree(s->t_halo_id); dfree(s->t_beta); dfree(s->t_coef); dfree(s->t_meta_s); dfree(s->d_queue);
     dfree(s->conv); dfree(s->t_ent_bkt); dfree(s->entry_of_elem); dfree(s->conv_scratch);
     dfree(s->t_rec); dfree(s->t_src); dfree(s->t_dep); dfree(s->t_partial); dfree(s->t_flag);
     dfree(s->d_slist); dfree(s->d_loaded); dfree(s->d_F); dfree(s->d_Fall); dfree(s->d_dnode);
@@ -855,6 +859,14 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
             Gg = std::min(Gmax - Gs, ng);
         }
         G = Gs + Gg;
+        if (s->dynamic_tiles && ng > 0) {
+            // tiles handed out from two counters: every CTA the device holds takes part, the split only says
+            // which list a CTA starts on
+            G = std::min(Gmax, ng + ns);
+            Gs = std::max(1, std::min(G - 1, (int)std::lround((double)G * ws / (ws + wg))));
+            CK(cudaMemsetAsync(s->d_queue, 0, 2 * sizeof(int), s->stream));
+            A.queue = s->d_queue;
+        }
         A.tile_meta = s->t_meta_s;
         A.tile_begin = gb; A.ntiles = ge; A.struct_begin = sb; A.struct_end = se; A.grid_struct = Gs;
     }

@@ -156,6 +156,7 @@ struct StepArgs {
     int32_t tile_begin, ntiles;         // this launch processes tile_meta[tile_begin .. ntiles) (slot-table tiles)
     int32_t struct_begin, struct_end;   // ... and tile_meta[struct_begin .. struct_end) (structured tiles, STRUCT launches)
     int32_t grid_struct;                // STRUCT launches: CTAs [0, grid_struct) walk the structured tiles
+    int *queue;                         // STRUCT launches: {next slot-table tile, next structured tile} handed out dynamically, or null
     int32_t cap_slots;                  // staged nodes per stage
     int32_t cap_acc;                    // accumulator nodes (owned + published)
     int32_t cap_owned;                  // owned nodes (pending buffer)
@@ -612,6 +613,16 @@ HGPU_HD void acc_add3(double *acc, int o, double fx, double fy, double fz)
 {
     acc[o] += fx; acc[o + SP_C] += fy; acc[o + 2 * SP_C] += fz;
 }
+// the same with the component stride given (the x = 4 side array, see SX4_*)
+HGPU_HD void acc_add3s(double *a, int o, int sc, double fx, double fy, double fz)
+{
+    a[o] += fx; a[o + sc] += fy; a[o + 2 * sc] += fz;
+}
+// What the x < 4 warps add to the nodes of the x = 4 column (their dx = 1 corners at x = 3) goes to a side
+// array [component][z][y] of 3 x 81 doubles instead of the accumulator, where the x >= 4 warps add their
+// dx = 0 corners to the same nodes: with that, no two warps touch one address inside a round, and the
+// dx = 0 and dx = 1 passes need no barrier between them.  The side array is added when the tile is drained.
+constexpr int SX4_C = 81, SX4_TOTAL = 243;
 
 // WPASS (MODE 1, fused update; opt-in, HGPU_FLAG_WPASS): on a tile whose entries share one beta, the
 // damped displacement w = u1 + beta (u1 - u2) is formed ONCE PER STAGED NODE right after the tile has
@@ -624,8 +635,11 @@ HGPU_HD void acc_add3(double *acc, int o, double fx, double fy, double fz)
 //   KIND 0: slot-table tiles (any shape)      KIND 1: structured tiles (fused update, MODE 0 or 1)
 // A STRUCT launch runs both loops, on different CTAs (step_kernel below): each loop then carries only its
 // own registers between tiles -- the two paths in ONE loop spilled (r02 call 2).
+// Tiles are handed out either statically (t0, t0 + G, ...; queue == nullptr) or from a counter shared by
+// the CTAs of the launch (queue: next tile = t0 + atomicAdd(queue, 1); G unused): in both cases a CTA's tiles
+// ascend, which is all the deadlock argument needs.
 template <int MODE, bool DENSE, int THREADS, bool WPASS, int KIND>
-__device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const int G, const int tend)
+__device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const int G, const int tend, int *queue)
 {
     constexpr bool STRUCT = KIND == 1;
     static_assert(!WPASS || (MODE == 1 && !DENSE), "WPASS is a variant of the Rayleigh + effective kernel");
@@ -662,12 +676,20 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
     //                   for the tile that is staged at the top of the next iteration
     //   node tables   : registers; requested before the accumulation passes of the last round
     __shared__ __align__(16) int smeta[META_RING][META_INTS];
-    int t = t0;
+    // ids of this CTA's tiles, position p in slot p & (META_RING - 1); >= tend = none.  Positions 0..3 now,
+    // position it + 4 during iteration it (the offsets of position it + 3 are requested at its top).
+    __shared__ int stile[META_RING];
+    if (tid == 0) {
+#pragma unroll
+        for (int p = 0; p < 4; p++) stile[p] = queue ? t0 + atomicAdd(queue, 1) : t0 + p * G;
+    }
+    __syncthreads();
+    int t = stile[0];
     if (t >= tend) return;
     for (int k = tid; k < A3; k += nthr) acc[k] = 0.0;
     fetch_meta_async(A, t, smeta[0], tid);
-    if (t + G < tend) fetch_meta_async(A, t + G, smeta[1], tid);
-    if (t + 2 * G < tend) fetch_meta_async(A, t + 2 * G, smeta[2], tid);
+    if (stile[1] < tend) fetch_meta_async(A, stile[1], smeta[1], tid);
+    if (stile[2] < tend) fetch_meta_async(A, stile[2], smeta[2], tid);
     cp_async_commit();
     cp_async_wait_all();
     __syncthreads();
@@ -678,7 +700,7 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         if (U2E || fuse) stage_tile<true, U2E>(A, ma, smem, smem + S3, tid, nthr, hid);
         else             stage_tile<false, false>(A, ma, smem, smem + S3, tid, nthr, hid);
         cp_async_commit();
-        if (t + G < tend) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
+        if (stile[1] < tend) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
     }
     Entry ecur, enext;
     enext.s = make_uint4(0, 0, 0, 0); enext.c1 = enext.c2 = enext.beta = 0.0;
@@ -709,9 +731,10 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
         double *su2 = su1 + S3;
-        const int tn = t + G;
+        const int tn = stile[(it + 1) & (META_RING - 1)];
+        int popped = 0;
         const bool has_next = tn < tend;
-        const bool has_nn = tn + G < tend;
+        const bool has_nn = stile[(it + 2) & (META_RING - 1)] < tend;
         const int *m_cur = smeta[it & (META_RING - 1)], *m_nxt = smeta[(it + 1) & (META_RING - 1)];
         const int *m_nn = smeta[(it + 2) & (META_RING - 1)], *m_prv = smeta[(it - 1) & (META_RING - 1)];
         const char *fb_prv = fbuf + ((it - 1) & 1) * fbuf_bytes;
@@ -746,7 +769,11 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             const int4 nxt = meta_group(m_nxt, 0);
             if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
-            if (tn + 2 * G < tend) fetch_meta_async(A, tn + 2 * G, smeta[(it + 3) & (META_RING - 1)], tid);
+            const int t3 = stile[(it + 3) & (META_RING - 1)];
+            if (t3 < tend) fetch_meta_async(A, t3, smeta[(it + 3) & (META_RING - 1)], tid);
+            // position it + 4: requested here, stored before the first barrier of the tail (so that thread 0
+            // does not wait for the atomic), read from the top of iteration it + 1 on
+            if (tid == 0) popped = queue ? t0 + atomicAdd(queue, 1) : t0 + (it + 4) * G;
         }
         cp_async_commit();
         // what the element phase needs of this tile's offsets
@@ -784,6 +811,8 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             __syncthreads();                    // the raw stage has been read by everybody
             double *W = su1;                    // three padded planes over the raw stage ...
             double *srm_own = su1 + SP_TOTAL;   // ... and 1/mass of the owned nodes behind them
+            double *accx = srm_own + 512;       // ... and the side array of the x = 4 column (SX4_*)
+            if (tid < SX4_TOTAL) accx[tid] = 0.0;
 #pragma unroll
             for (int q = 0; q < 3; q++) {
                 if (q < 2 || tid < 217) {
@@ -807,6 +836,10 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             // two rounds: element (x, y, 2 zq), then (x, y, 2 zq + 1).  Each is gathered, evaluated and added to
             // the accumulator on its own (carrying anything from the first to the second costs the registers
             // the operator itself needs: measured, r02 call 2 -- 600 bytes of spills per thread and tile).
+            // Inside a round the warps touch disjoint addresses (levels by zq, the x = 4 column through the side
+            // array), so lanes are ordered by __syncwarp only; the ONE barrier between the rounds sits behind the
+            // second element's arithmetic, where nobody waits for it.
+            const bool redir = x == 3;          // dx = 1 corners of this thread land on the x = 4 column
 #pragma unroll 1
             for (int r = 0; r < 2; r++) {
                 const int o = o0 + r * SP_Z;
@@ -823,46 +856,60 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
                     scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);        // w* reused as the scaled modes
                     wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
                 }
-                if (r == 1) {                   // what the next tile needs in registers
-                    if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
-                    if (has_next) {
-                        const int n0n = meta_group(m_nxt, 0).x;
-#pragma unroll
-                        for (int q = 0; q < 2; q++) {
-                            const double *nt = A.nt3 + 3 * (size_t)(n0n + tid + 256 * q);
-                            spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
-                        }
-                        const double *tc = A.tile_coef + 4 * (size_t)tn;
-                        cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
-                        pre_ok = true;
+                if (r == 1) {
+                    // every warp is done with the first round's updates before anybody starts the second's
+                    if (prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
+                    __syncthreads();
+                    if (prv_pending) {
+                        request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
+                        cp_async_commit();
                     }
                 }
-                // pass dx = 0: corners (0, dy, dz); the y neighbours are lanes of this warp
+                // dx = 0: corners (0, dy, dz); the y and x neighbours are lanes of this warp
                 acc_add3(acc, o, fx[0], fy[0], fz[0]);
                 acc_add3(acc, o + SP_Z, fx[4], fy[4], fz[4]);
                 __syncwarp();
                 acc_add3(acc, o + SP_ROW, fx[2], fy[2], fz[2]);
                 acc_add3(acc, o + SP_Z + SP_ROW, fx[6], fy[6], fz[6]);
-                if (r == 0 && prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
-                __syncthreads();
-                if (r == 0 && prv_pending) {
-                    request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
-                    cp_async_commit();
-                }
-                // pass dx = 1
-                acc_add3(acc, o + 1, fx[1], fy[1], fz[1]);
-                acc_add3(acc, o + SP_Z + 1, fx[5], fy[5], fz[5]);
                 __syncwarp();
-                acc_add3(acc, o + SP_ROW + 1, fx[3], fy[3], fz[3]);
-                acc_add3(acc, o + SP_Z + SP_ROW + 1, fx[7], fy[7], fz[7]);
-                __syncthreads();
+                // dx = 1 (addresses formed here rather than kept: the forces fill the register file)
+                {
+                    double *pa1 = redir ? accx : acc;
+                    const int sc1 = redir ? SX4_C : SP_C, sy1 = redir ? 1 : SP_ROW, sz1 = redir ? 9 : SP_Z;
+                    const int o1 = redir ? (2 * zq + r) * 9 + y : o + 1;
+                    acc_add3s(pa1, o1, sc1, fx[1], fy[1], fz[1]);
+                    acc_add3s(pa1, o1 + sz1, sc1, fx[5], fy[5], fz[5]);
+                    __syncwarp();
+                    acc_add3s(pa1, o1 + sy1, sc1, fx[3], fy[3], fz[3]);
+                    acc_add3s(pa1, o1 + sz1 + sy1, sc1, fx[7], fy[7], fz[7]);
+                }
             }
+            // what the next tile needs in registers, requested now that this tile's forces have left them
+            if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
+            if (has_next) {
+                const int n0n = meta_group(m_nxt, 0).x;
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const double *nt = A.nt3 + 3 * (size_t)(n0n + tid + 256 * q);
+                    spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
+                }
+                const double *tc = A.tile_coef + 4 * (size_t)tn;
+                cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
+                pre_ok = true;
+            }
+            __syncthreads();
             // ---- publish the three far faces (slots 512 + h = partial force h of this tile) ----
             if (tid < 217) {
                 double *dst = A.partial + 3 * ((size_t)meta_group(m_cur, 0).z + tid);
                 const int sp = sp_of_slot(512 + tid);
+                const bool x4 = sp % SP_ROW == 4;
+                const int ox = (sp / SP_Z) * 9 + (sp / SP_ROW) % 9;
 #pragma unroll
-                for (int c = 0; c < 3; c++) { __stcg(dst + c, acc[sp + c * SP_C]); acc[sp + c * SP_C] = 0.0; }
+                for (int c = 0; c < 3; c++) {
+                    double v = acc[sp + c * SP_C];
+                    if (x4) v += accx[ox + c * SX4_C];
+                    __stcg(dst + c, v); acc[sp + c * SP_C] = 0.0;
+                }
             }
             // ---- this tile's own share of the update: scale by 1/mass (REGULAR nodes), hand it on ----
 #pragma unroll
@@ -870,9 +917,12 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
                 const int sl = tid + 256 * q, sp = sp_of_slot(sl);
                 const double rm = srm_own[sl];
                 double *o = A.unext + 3 * (size_t)(n0 + sl);
+                const bool x4 = sp % SP_ROW == 4;
+                const int ox = (sp / SP_Z) * 9 + (sp / SP_ROW) % 9;
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     double v = acc[sp + c * SP_C];
+                    if (x4) v += accx[ox + c * SX4_C];
                     if (rm > 0.0) v *= rm;
                     acc[sp + c * SP_C] = v;         // record nodes take it from here (pend)
                     o[c] = v;
@@ -1125,6 +1175,7 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             }
         }
         }
+        if (has_next && tid == 0) stile[(it + 4) & (META_RING - 1)] = popped;
         cp_async_wait_all();                    // partial forces of the previous tile, this tile's finish data
         __syncthreads();                        // ... and every thread's published partial forces are written
         // (the flag is raised at the top of the next iteration: by then the stores have long been
@@ -1209,10 +1260,24 @@ __global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
 {
     if (STRUCT) {
         const int gs = A.grid_struct;
-        if ((int)blockIdx.x < gs) tile_loop<MODE, DENSE, THREADS, false, STRUCT ? 1 : 0>(A, A.struct_begin + blockIdx.x, gs, A.struct_end);
-        else tile_loop<MODE, DENSE, THREADS, false, 0>(A, A.tile_begin + (blockIdx.x - gs), gridDim.x - gs, A.ntiles);
+        const bool sfirst = (int)blockIdx.x < gs;
+        // static split: one pass (a CTA walks the list it was started on).  Dynamic (A.queue): two shared
+        // counters; a CTA drains the list it was started on, then helps with the other one.  The loop keeps
+        // ONE inlined copy of either tile_loop in the kernel.
+        if (A.queue) {
+            if (sfirst) {
+                tile_loop<MODE, DENSE, THREADS, false, STRUCT ? 1 : 0>(A, A.struct_begin, 0, A.struct_end, A.queue + 1);
+                __syncthreads();
+                tile_loop<MODE, DENSE, THREADS, false, 0>(A, A.tile_begin, 0, A.ntiles, A.queue);
+            } else {
+                tile_loop<MODE, DENSE, THREADS, false, 0>(A, A.tile_begin, 0, A.ntiles, A.queue);
+                __syncthreads();
+                tile_loop<MODE, DENSE, THREADS, false, STRUCT ? 1 : 0>(A, A.struct_begin, 0, A.struct_end, A.queue + 1);
+            }
+        } else if (sfirst) tile_loop<MODE, DENSE, THREADS, false, STRUCT ? 1 : 0>(A, A.struct_begin + (int)blockIdx.x, gs, A.struct_end, nullptr);
+        else tile_loop<MODE, DENSE, THREADS, false, 0>(A, A.tile_begin + ((int)blockIdx.x - gs), (int)gridDim.x - gs, A.ntiles, nullptr);
     } else {
-        tile_loop<MODE, DENSE, THREADS, WPASS, 0>(A, A.tile_begin + blockIdx.x, gridDim.x, A.ntiles);
+        tile_loop<MODE, DENSE, THREADS, WPASS, 0>(A, A.tile_begin + blockIdx.x, gridDim.x, A.ntiles, nullptr);
     }
 }
 

@@ -7,8 +7,8 @@
 //   1. the padded layout: 729 slots map to 729 different offsets inside a plane of SP_C doubles;
 //   2. bank conflicts: every gather / accumulator access of a warp is conflict-free (16 lanes of a
 //      half-warp hit 16 different 8-byte banks);
-//   3. races: inside one pass half, no two threads touch the same accumulator; inside one pass, threads
-//      of DIFFERENT warps never touch the same accumulator (only __syncwarp orders the halves);
+//   3. races: inside one half of a pass no two threads touch the same accumulator; inside one ROUND (the
+//      code between two barriers) threads of DIFFERENT warps never do (only __syncwarp orders the halves);
 //   4. numerics: the accumulated forces equal those of 512 single-element evaluations
 //      (wht_forward, scale_modes, wht_inverse, scatter) to rounding.
 #include <cmath>
@@ -55,7 +55,7 @@ int main()
             CHECK(sp_of_slot(struct_slot(x, y, z)) == z * SP_Z + y * SP_ROW + x, "slot of (%d,%d,%d)", x, y, z);
     }
     // ---- random w on the 729 nodes, padded planes -------------------------------------------------
-    std::vector<double> W(SP_TOTAL, 0.0), acc(SP_TOTAL, 0.0), ref(3 * STRUCT_NODES, 0.0);
+    std::vector<double> W(SP_TOTAL, 0.0), acc(SP_TOTAL, 0.0), accx(SX4_TOTAL, 0.0), ref(3 * STRUCT_NODES, 0.0);
     srand(12345);
     auto rnd = []() { return (double)rand() / RAND_MAX - 0.5; };
     std::vector<double> wnode(3 * STRUCT_NODES);
@@ -108,28 +108,37 @@ int main()
             scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);
             wht_inverse(wx, q.f[0]); wht_inverse(wy, q.f[1]); wht_inverse(wz, q.f[2]);
         }
-        for (int dx = 0; dx < 2; dx++) {                    // one pass = the code between two barriers
-            std::map<int, int> warp_of;                     // offset -> warp that touched it in this pass
-            for (int half = 0; half < 2; half++) {          // dy; a __syncwarp separates the halves
-                std::map<int, int> lane_of;
-                std::vector<Access> a1, a2;
-                for (int tid = 0; tid < 256; tid++) {
-                    Regs &q = R[tid];
-                    for (int lvl = 0; lvl < 2; lvl++) {
-                        const int o = q.o + lvl * SP_Z + dx + SP_ROW * half, j = dx + 2 * half + 4 * lvl;
-                        CHECK(lane_of.insert({o, tid}).second, "round %d dx %d half %d: threads %d and %d update the same accumulator", r, dx, half, lane_of[o], tid);
-                        auto w = warp_of.find(o);
-                        CHECK(w == warp_of.end() || w->second == tid / 32, "round %d dx %d: warps %d and %d update the same accumulator inside one pass",
-                              r, dx, w == warp_of.end() ? -1 : w->second, tid / 32);
-                        warp_of[o] = tid / 32;
-                        acc_add3(acc.data(), o, q.f[0][j], q.f[1][j], q.f[2][j]);
-                        (lvl == 0 ? a1 : a2).push_back({tid, o});
-                    }
+        // one ROUND = the code between two barriers: four halves (dx = 0 / 1 x dy = 0 / 1) separated by
+        // __syncwarp only, so no two DIFFERENT warps may touch one address anywhere inside the round; the
+        // dx = 1 corners of the x = 3 threads go to the side array of the x = 4 column
+        std::map<long, int> warp_of;                        // address -> warp that touched it in this round
+        for (int dx = 0; dx < 2; dx++) for (int half = 0; half < 2; half++) {
+            std::map<long, int> lane_of;
+            std::vector<Access> a1, a2;
+            for (int tid = 0; tid < 256; tid++) {
+                Regs &q = R[tid];
+                const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
+                const bool redir = dx == 1 && x == 3;
+                for (int lvl = 0; lvl < 2; lvl++) {
+                    const int j = dx + 2 * half + 4 * lvl;
+                    int o; long key;
+                    if (redir) { o = (2 * zq + r + lvl) * 9 + y + half; key = 1000000L + o; }
+                    else { o = q.o + lvl * SP_Z + dx + SP_ROW * half; key = o; }
+                    CHECK(lane_of.insert({key, tid}).second, "round %d dx %d half %d: threads %d and %d update the same accumulator", r, dx, half, lane_of[key], tid);
+                    auto w = warp_of.find(key);
+                    CHECK(w == warp_of.end() || w->second == tid / 32, "round %d: warps %d and %d update the same accumulator inside one round",
+                          r, w == warp_of.end() ? -1 : w->second, tid / 32);
+                    warp_of[key] = tid / 32;
+                    if (redir) acc_add3s(accx.data(), o, SX4_C, q.f[0][j], q.f[1][j], q.f[2][j]);
+                    else { acc_add3(acc.data(), o, q.f[0][j], q.f[1][j], q.f[2][j]); (lvl == 0 ? a1 : a2).push_back({tid, o}); }
                 }
-                check_banks(a1, "accumulate"); check_banks(a2, "accumulate");
             }
+            if (dx == 0) { check_banks(a1, "accumulate"); check_banks(a2, "accumulate"); }   // dx = 1: the redirected lanes may collide
         }
     }
+    // drain: the side array belongs to the x = 4 column
+    for (int z = 0; z < 9; z++) for (int y = 0; y < 9; y++) for (int c = 0; c < 3; c++)
+        acc[c * SP_C + z * SP_Z + y * SP_ROW + 4] += accx[c * SX4_C + z * 9 + y];
 
     // ---- 4. numerics ---------------------------------------------------------------------------------
     double worst = 0.0, scale = 0.0;
