@@ -568,6 +568,21 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             for (int32_t t = 0; t < pl.ntiles; t++) if (pl.tile_self[t]) order.push_back(t);
             s->n_early = s->n_self = (int32_t)order.size();
             for (int32_t t = 0; t < pl.ntiles; t++) if (!pl.tile_self[t]) order.push_back(t);
+            // HGPU_ORDER=level: the rest by dependency LEVEL (0 = reads nobody's partial forces, else 1 + the
+            // highest level among the tiles it reads), ascending ids inside a level -- still a topological order
+            // of the dependencies, but the tiles that run at the same time no longer wait for one another
+            // (in Z-order a tile's lower neighbours are its immediate predecessors, i.e. run concurrently with it)
+            {
+                const char *oenv = getenv("HGPU_ORDER");
+                if (oenv && strcmp(oenv, "level") == 0) {
+                    std::vector<int32_t> lvl((size_t)pl.ntiles, 0);
+                    for (int32_t t = 0; t < pl.ntiles; t++)
+                        for (int32_t k = pl.dep_off[t]; k < pl.dep_off[(size_t)t + 1]; k++)
+                            lvl[t] = std::max(lvl[t], lvl[pl.dep[(size_t)k]] + 1);
+                    std::stable_sort(order.begin() + s->n_self, order.end(),
+                                     [&](int32_t a, int32_t b) { return lvl[a] < lvl[b]; });
+                }
+            }
             // SPECIAL nodes owned by self tiles first (ascending within each part)
             if (fused) {
                 std::vector<int32_t> early_part, late_part;
