@@ -149,10 +149,10 @@ struct hgpu_solver {
     int4 *t_meta_s = nullptr;            // tiles in the order of the STRUCT launches: slot-table tiles, then structured ones
     int32_t n_generic = 0;               // slot-table tiles (= index of the first structured tile in t_meta_s)
     int64_t struct_entries = 0, generic_entries = 0;   // elements evaluated by structured / by late slot-table tiles
-    double generic_cost = 2.2;           // cost of a slot-table element relative to a structured one (CTA split)
+    double generic_cost = 2.6;           // cost of a slot-table element relative to a structured one (CTA split)
     std::vector<int64_t> ent_prefix_s;   // [ntiles + 1] prefix sum of entries over t_meta_s
     int *d_queue = nullptr;              // {next slot-table tile, next structured tile} of a STRUCT launch (HGPU_DYNAMIC=0: unused)
-    bool dynamic_tiles = true;
+    bool dynamic_tiles = false;          // HGPU_DYNAMIC=1: tiles from two shared counters (measured slower: consecutive tiles on one CTA wait for each other)
     uint2 *t_rec = nullptr;              // finish records
     int32_t *t_src = nullptr, *t_dep = nullptr;
     double *t_partial = nullptr;         // [halo slots][3] partial forces published by lower tiles
@@ -529,7 +529,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // structured tiles (aligned uniform 8x8x8 cells): the fused effective-stiffness kernels only
         bool want_struct = fused && !bkt && params->stiffness == HGPU_STIFFNESS_EFFECTIVE &&
                            !(params->flags & (HGPU_FLAG_WPASS | HGPU_FLAG_NO_STRUCT));
-        { const char *senv = getenv("HGPU_STRUCT"); if (senv && atoi(senv) == 0) want_struct = false; }
+        {   // opt-in while it does not beat the slot-table path on the bench (profiles/README.md): HGPU_STRUCT=1
+            const char *senv = getenv("HGPU_STRUCT");
+            if (!(senv && atoi(senv) == 1) && !(params->flags & HGPU_FLAG_STRUCT)) want_struct = false;
+        }
         const int smem_cap0 = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
         TileCaps caps = tile_caps(max_smem, params->tile_nodes, want_struct);
         for (;;) {
@@ -661,7 +664,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 TRY(upload(s, &s->t_coef, tcoef.data(), tcoef.size()));
                 TRY(upload(s, (int32_t **)&s->t_meta_s, meta_s.data(), meta_s.size()));
                 TRY(dalloc(s, &s->d_queue, 2));
-                { const char *denv = getenv("HGPU_DYNAMIC"); s->dynamic_tiles = !(denv && atoi(denv) == 0); }
+                { const char *denv = getenv("HGPU_DYNAMIC"); s->dynamic_tiles = denv && atoi(denv) == 1; }
             }
         }
         TRY(upload(s, (uint16_t **)&s->t_ent_slot, pl.elem_slot.data(), pl.elem_slot.size()));
@@ -1520,7 +1523,7 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     std::string err;
     // structured tiles recognised as hgpu_init does for the fused effective-stiffness kernels (HGPU_STRUCT=0: not)
     const char *senv = getenv("HGPU_STRUCT");
-    const TileCaps caps = tile_caps(232448, tile_nodes, !(senv && atoi(senv) == 0));
+    const TileCaps caps = tile_caps(232448, tile_nodes, senv && atoi(senv) == 1);
     // nodes of the halo schedules and the hanging-node lists (when given) make their tiles "self"
     // tiles, as hgpu_init does on a multi-rank mesh
     std::vector<uint8_t> self_node;

@@ -34,6 +34,7 @@ FLAG_NO_OVERLAP = 4
 FLAG_TAIL_OVERLAP = 8
 FLAG_WPASS = 16
 FLAG_NO_STRUCT = 32
+FLAG_STRUCT = 64
 
 
 class HerculesGpuError(RuntimeError):

@@ -109,8 +109,10 @@ typedef struct hgpu_params {
 #define HGPU_FLAG_WPASS 16       /* opt-in step-kernel variant (Rayleigh + effective, fused): on tiles of one material
                                    the damped displacement is formed once per staged node, not per element corner */
 
-#define HGPU_FLAG_NO_STRUCT 32   /* do not use the structured-tile path of the step kernel (aligned uniform 8x8x8 cells
-                                   of one material evaluated as z pairs from a per-node damped displacement) */
+#define HGPU_FLAG_NO_STRUCT 32   /* never use the structured-tile path of the step kernel */
+#define HGPU_FLAG_STRUCT 64      /* opt-in: aligned uniform 8x8x8 cells of one material are evaluated without a slot table,
+                                   from a per-node damped displacement in padded conflict-free planes, on their own CTAs
+                                   (also HGPU_STRUCT=1 in the environment) */
 
 typedef struct hgpu_solver hgpu_solver_t;
 

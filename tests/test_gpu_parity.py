@@ -457,10 +457,10 @@ def test_structured_tiles_match_oracle(hb, oracle, damping):
         for k in range(steps):
             oracle.step(m, st, odmp, oracle.EFFECTIVE, 1.0, 0.002, loaded, F[k])
         out = []
-        for flags in (0, hb.FLAG_NO_STRUCT):
+        for flags in (hb.FLAG_STRUCT, hb.FLAG_NO_STRUCT):
             s = hb.Solver(mesh, dt=0.002, damping=dmp, stiffness=hb.EFFECTIVE, freq=1.0, loaded_lnid=loaded, flags=flags)
             nstruct = s.layout()["struct_tiles"]
-            assert (nstruct == 0) if flags else (nstruct == (18 if ztop == 200.0 else 9)), nstruct
+            assert (nstruct == 0) if flags == hb.FLAG_NO_STRUCT else (nstruct == (18 if ztop == 200.0 else 9)), nstruct
             s.store_all(hb.TM1, u0); s.store_all(hb.TM2, v0)
             s.run(0, steps, F)
             out.append(s.fetch_all(hb.TM2))

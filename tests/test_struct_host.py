@@ -22,10 +22,11 @@ def test_structured_tile_schedule_on_host(tmp_path):
     assert p.returncode == 0 and "struct_check: ok" in p.stdout, p.stdout[-3000:]
 
 
-def test_structured_tiles_recognised():
+def test_structured_tiles_recognised(monkeypatch):
     """The planner marks exactly the aligned uniform cells that do not touch a far face of the domain, gives
     them the canonical slot order (re-checked inside hgpu_plan_build), and leaves everything else alone."""
     from hercules_b200 import meshgen, solver
+    monkeypatch.setenv("HGPU_STRUCT", "1")
     mesh, info = meshgen.uniform_halfspace(32, 32, 24, h=25.0, dt=0.002)
     r = solver.plan_build(mesh.elem_lnid, info["N"])
     assert r["ntiles"] == 48 and r["struct_tiles"] == 3 * 3 * 2
