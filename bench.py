@@ -48,6 +48,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+T_START = time.time()
 METRIC = "element-updates/sec"
 UNIT = "element-updates/s"
 LAYERS = ((0.0, 4000.0, 2000.0, 2600.0), (1000.0, 6000.0, 3464.0, 2700.0))   # ztop, Vp, Vs, rho
@@ -341,7 +342,7 @@ def adaptive_layers(n: int):
 
 def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayleigh", info: dict | None = None) -> dict:
     if info is not None and "bands" in info:
-        cx, cy = column_grid(8 if info.get("strong") else world)
+        cx, cy = column_grid(info.get("columns", world))
         return {"workload": f"configs[{3 if world > 1 or info.get('strong') else 2}]: adaptive octree mesh, 3 refinement levels (element edge "
                             f"{H_M:g}/{2*H_M:g}/{4*H_M:g} m by depth band, "
                             f"{'Vs 1000/2000/3464 m/s' if damping == 'rayleigh' else 'soft sedimentary column Vs 500-1500 m/s (configs[4] damping model)'}"
@@ -352,7 +353,7 @@ def workload_config(world: int, n: int, halo: str = "p2p", damping: str = "rayle
                             "tests/golden/graded{2,3}_*.npz)",
                 "elements_per_gpu": info["E"], "global_elements": info["etotal"], "hanging_nodes": info["D"],
                 "global_grid": [n * cx, n * cy, n], "bands": [list(b) for b in info["bands"]], "dt": DT,
-                "partition": ((f"{world} columns" if not info.get("strong") else f"8 columns cut into {world} blocks") +
+                "partition": ((f"{world} columns" if not info.get("strong") else f"{info.get('columns')} columns cut into {world} blocks") +
                               f" of {n}^3 h-cells = octor's equal blocks of the Morton-ordered leaf list, halo "
                               f"exchange over {halo} overlapped with interior tiles" if world > 1 else "single rank"),
                 "l2": "inputs larger than L2; no explicit flush"}
@@ -520,6 +521,9 @@ def main() -> None:
     ap.add_argument("--strong", action="store_true",
                     help="--workload adaptive: cut ONE mesh of 8 columns (4 x 2; --edge 384: 326 M elements, configs[3]'s ~400 M) "
                          "over the GPUs instead of one column per GPU")
+    ap.add_argument("--columns", type=int, default=8, choices=[2, 4, 8],
+                    help="--strong: columns of the one mesh (--edge 512: 4 columns = 386 M elements, configs[3]'s ~400 M; "
+                         "8 columns = 773 M); must be a multiple of --gpus")
     ap.add_argument("--wpass", action="store_true",
                     help="opt-in step-kernel variant (HGPU_FLAG_WPASS): damped displacement formed once per staged node")
     ap.add_argument("--tile-nodes", type=int, default=0)
@@ -551,6 +555,14 @@ def main() -> None:
     import hercules_b200 as hb
     from hercules_b200 import meshgen
 
+    wd = float(os.environ.get("BENCH_WATCHDOG_S", "0"))
+    if wd > 0:                                  # a hung run says where it hangs, then ends
+        import faulthandler
+        faulthandler.dump_traceback_later(wd, exit=True, file=sys.stderr)
+
+    def note(msg: str) -> None:
+        print(f"[bench rank {os.environ.get('RANK', '0')} +{time.time() - T_START:.1f}s] {msg}", file=sys.stderr, flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -570,7 +582,9 @@ def main() -> None:
         hb.build()
     run_flags = (hb.FLAG_NO_OVERLAP if args.no_overlap else 0) | (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0) | \
                 (hb.FLAG_WPASS if args.wpass else 0)
+    note("process group up")
     parity = parity_check(hb, dist, rank, world, local, args.halo, run_flags) if world > 1 and not args.no_parity_check else None
+    note(f"parity check done: {parity and parity['rel_l2']}")
 
     # ---- workload -------------------------------------------------------------------------------
     n = args.n
@@ -587,12 +601,13 @@ def main() -> None:
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")
         bands = adaptive_bands(n)
-        if args.strong and world not in (1, 2, 4, 8):
-            raise SystemExit("--strong cuts 8 columns: 1, 2, 4 or 8 GPUs")
-        cols = column_grid(8 if args.strong else world)
+        if args.strong and (args.columns % world or n & (n - 1)):
+            raise SystemExit("--strong: --columns must be a multiple of --gpus and --edge a power of two (octor's Morton "
+                             "blocks are whole columns only then)")
+        cols = column_grid(args.columns if args.strong else world)
         try:                                        # host side: ~350 B per element while the mesh tables and the
             import psutil                           # tile plan are built, on every rank of this box at once
-            need = 350 * sum(nl * (n // sz) ** 2 for nl, sz in bands) * (8 if args.strong else world)
+            need = 350 * sum(nl * (n // sz) ** 2 for nl, sz in bands) * (args.columns if args.strong else world)
             if psutil.virtual_memory().available < need:
                 raise SystemExit(f"--workload adaptive --edge {n} --gpus {world}: needs ~{need >> 30} GiB of host memory for "
                                  f"the mesh tables of {world} rank(s); use a smaller --edge")
@@ -604,6 +619,7 @@ def main() -> None:
         mesh, info = meshgen.graded_halfspace(n * cols[0], n * cols[1], bands, h=H_M, dt=DT, freq=FREQ, layers=layers,
                                               damping=damp, part=(rank, world) if world > 1 else None)
         info["strong"] = bool(args.strong)
+        info["columns"] = args.columns if args.strong else world
     elif world == 1:
         mesh, info = meshgen.uniform_halfspace(n, n, n, h=H_M, dt=DT, freq=FREQ, layers=layers, damping=damp)
     else:
@@ -652,6 +668,7 @@ def main() -> None:
             dist.all_gather_object(blobs, s.p2p_export())
             s.p2p_connect(blobs)
     t_init = time.time() - t0
+    note(f"solver ready: mesh {t_mesh:.1f} s, init {t_init:.1f} s")
     layout = s.layout()
     stream = torch.cuda.ExternalStream(s.stream, device=torch.device("cuda", local))
 
@@ -671,7 +688,9 @@ def main() -> None:
     # ---- device-resident run: `value` ------------------------------------------------------------
     s.source_preload(0, F_all[:steps_hist])
     s.run(0, args.warmup)
+    note("warm-up enqueued")
     barrier()
+    note("warm-up done")
     tm0 = s.timers()
     clk = ClockSampler(local)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -682,6 +701,7 @@ def main() -> None:
     ev1.record(stream)
     clk.sample_now()                       # the steps are still in flight here
     barrier()
+    note("timed run done")
     dev_s = max_over_ranks(ev0.elapsed_time(ev1) * 1e-3)
     clocks = clk.result()
     tm1 = s.timers()

@@ -74,6 +74,8 @@ SYMBOLS = {
     "hgpu_step": (C.c_int, [_H, i32, C.c_void_p]),
     "hgpu_source_preload": (C.c_int, [_H, i32, i32, C.c_void_p]),
     "hgpu_force_source_resident": (C.c_int, [_H, i32]),
+    "hgpu_fetch_all_async": (C.c_int, [_H, i32, C.c_void_p]),
+    "hgpu_fetch_wait": (C.c_int, [_H]),
     "hgpu_run": (C.c_int, [_H, i32, i32, C.c_void_p]),
     "hgpu_fetch_nodes": (C.c_int, [_H, i32, C.c_void_p, i32, C.c_void_p]),
     "hgpu_fetch_all": (C.c_int, [_H, i32, C.c_void_p]),

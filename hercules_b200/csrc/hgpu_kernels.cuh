@@ -216,6 +216,36 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA, 1-D) with mbarrier completion: the contiguous owned range of a
+//      structured tile (2 x 12 288 bytes) is ONE instruction per array instead of 48 cp.async per warp ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred P1;\n"
+                 "LAB_WAIT:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                 "@P1 bra DONE;\n"
+                 "bra LAB_WAIT;\n"
+                 "DONE:\n"
+                 "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// generic-proxy accesses to shared memory (ld/st.shared) before, async-proxy accesses (bulk copies) after
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct Entry { uint4 s; double c1, c2, beta; };
 
 // Loads that must be ISSUED where they are written (register prefetch one round / one phase ahead
@@ -336,6 +366,26 @@ __device__ __forceinline__ void stage_tile(const StepArgs &A, const int4 m, doub
         if (id < 0) continue;
         const size_t g = 3 * (size_t)id;
         double *d1 = su1 + nd + 3 * h, *d2 = su2 + nd + 3 * h;
+        cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
+        if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
+    }
+}
+
+// The same for a STRUCTURED tile: its 512 owned nodes are one bulk copy per array (thread 0, completion
+// counted on `bar`), its 217 far-face nodes one thread each as above.
+template <bool U2_HALO>
+__device__ __forceinline__ void stage_tile_struct(const StepArgs &A, const int4 m, double *su1, double *su2,
+                                                  unsigned long long *bar, int tid, const int (&hid)[HALO_PRE])
+{
+    constexpr unsigned OWNED_BYTES = 512 * 3 * sizeof(double);
+    if (tid == 0) {
+        mbar_expect_tx(bar, 2 * OWNED_BYTES);
+        bulk_g2s(su1, A.u1 + 3 * (size_t)m.x, OWNED_BYTES, bar);
+        bulk_g2s(su2, A.u2 + 3 * (size_t)m.x, OWNED_BYTES, bar);
+    }
+    if (tid < 217 && hid[0] >= 0) {
+        const size_t g = 3 * (size_t)hid[0];
+        double *d1 = su1 + 1536 + 3 * tid, *d2 = su2 + 1536 + 3 * tid;
         cp_async8(d1, A.u1 + g); cp_async8(d1 + 1, A.u1 + g + 1); cp_async8(d1 + 2, A.u1 + g + 2);
         if (U2_HALO) { cp_async8(d2, A.u2 + g); cp_async8(d2 + 1, A.u2 + g + 1); cp_async8(d2 + 2, A.u2 + g + 2); }
     }
@@ -679,10 +729,13 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
     // ids of this CTA's tiles, position p in slot p & (META_RING - 1); >= tend = none.  Positions 0..3 now,
     // position it + 4 during iteration it (the offsets of position it + 3 are requested at its top).
     __shared__ int stile[META_RING];
+    __shared__ __align__(8) unsigned long long sbar[2];      // STRUCT: completion of the bulk copies into either stage
     if (tid == 0) {
 #pragma unroll
         for (int p = 0; p < 4; p++) stile[p] = queue ? t0 + atomicAdd(queue, 1) : t0 + p * G;
+        if (STRUCT) { mbar_init(&sbar[0], 1); mbar_init(&sbar[1], 1); }
     }
+    if (STRUCT) fence_proxy_async();
     __syncthreads();
     int t = stile[0];
     if (t >= tend) return;
@@ -697,8 +750,9 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
     {
         const int4 ma = meta_group(smeta[0], 0);
         load_halo_ids(A, ma, tid, nthr, hid);
-        if (U2E || fuse) stage_tile<true, U2E>(A, ma, smem, smem + S3, tid, nthr, hid);
-        else             stage_tile<false, false>(A, ma, smem, smem + S3, tid, nthr, hid);
+        if (STRUCT)           stage_tile_struct<U2E>(A, ma, smem, smem + S3, &sbar[0], tid, hid);
+        else if (U2E || fuse) stage_tile<true, U2E>(A, ma, smem, smem + S3, tid, nthr, hid);
+        else                  stage_tile<false, false>(A, ma, smem, smem + S3, tid, nthr, hid);
         cp_async_commit();
         if (stile[1] < tend) load_halo_ids(A, meta_group(smeta[1], 0), tid, nthr, hid);
     }
@@ -761,14 +815,19 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         }
         pre_ok = false;
         cp_async_wait_all();
+        if (STRUCT) {
+            mbar_wait(&sbar[it & 1], (unsigned)(it >> 1) & 1u);     // the bulk part of tile `it`
+            fence_proxy_async();              // this thread's ld/st.shared of the other stage, before its next bulk copy
+        }
         __syncthreads();                      // tile `it` has landed; everyone is done with tile it-1's stage
         if (it > 0 && tid == 0) publish_flag(A.flag + meta_group(m_prv, 3).z, A.epoch);
         stage_finish(A, meta_group(m_cur, 2), meta_group(m_cur, 3), fb_cur, tid, nthr);
         if (has_next) {
             double *n1 = smem + ((it + 1) & 1) * stage_doubles;
             const int4 nxt = meta_group(m_nxt, 0);
-            if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
-            else             stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
+            if (STRUCT)           stage_tile_struct<U2E>(A, nxt, n1, n1 + S3, &sbar[(it + 1) & 1], tid, hid);
+            else if (U2E || fuse) stage_tile<true, U2E>(A, nxt, n1, n1 + S3, tid, nthr, hid);
+            else                  stage_tile<false, false>(A, nxt, n1, n1 + S3, tid, nthr, hid);
             const int t3 = stile[(it + 3) & (META_RING - 1)];
             if (t3 < tend) fetch_meta_async(A, t3, smeta[(it + 3) & (META_RING - 1)], tid);
             // position it + 4: requested here, stored before the first barrier of the tail (so that thread 0
@@ -837,9 +896,9 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             // the accumulator on its own (carrying anything from the first to the second costs the registers
             // the operator itself needs: measured, r02 call 2 -- 600 bytes of spills per thread and tile).
             // Inside a round the warps touch disjoint addresses (levels by zq, the x = 4 column through the side
-            // array), so lanes are ordered by __syncwarp only; the ONE barrier between the rounds sits behind the
-            // second element's arithmetic, where nobody waits for it.
-            const bool redir = x == 3;          // dx = 1 corners of this thread land on the x = 4 column
+            // array); the ONE barrier between the rounds sits behind the second element's arithmetic, where nobody
+            // waits for it.
+            const bool xlo = (tid & 3) != 0, xhi = (tid & 3) == 3, ylo = y != 0, yhi = y == 7;
 #pragma unroll 1
             for (int r = 0; r < 2; r++) {
                 const int o = o0 + r * SP_Z;
@@ -865,23 +924,37 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
                         cp_async_commit();
                     }
                 }
-                // dx = 0: corners (0, dy, dz); the y and x neighbours are lanes of this warp
-                acc_add3(acc, o, fx[0], fy[0], fz[0]);
-                acc_add3(acc, o + SP_Z, fx[4], fy[4], fz[4]);
-                __syncwarp();
-                acc_add3(acc, o + SP_ROW, fx[2], fy[2], fz[2]);
-                acc_add3(acc, o + SP_Z + SP_ROW, fx[6], fy[6], fz[6]);
-                __syncwarp();
-                // dx = 1 (addresses formed here rather than kept: the forces fill the register file)
-                {
-                    double *pa1 = redir ? accx : acc;
-                    const int sc1 = redir ? SX4_C : SP_C, sy1 = redir ? 1 : SP_ROW, sz1 = redir ? 9 : SP_Z;
-                    const int o1 = redir ? (2 * zq + r) * 9 + y : o + 1;
-                    acc_add3s(pa1, o1, sc1, fx[1], fy[1], fz[1]);
-                    acc_add3s(pa1, o1 + sz1, sc1, fx[5], fy[5], fz[5]);
-                    __syncwarp();
-                    acc_add3s(pa1, o1 + sy1, sc1, fx[3], fy[3], fz[3]);
-                    acc_add3s(pa1, o1 + sz1 + sy1, sc1, fx[7], fy[7], fz[7]);
+                // Shuffle-combined update.  Within the warp's 4 x 8 patch of one level the four elements around a
+                // node are lanes (xl, y), (xl - 1, y), (xl, y - 1), (xl - 1, y - 1): their shares are summed with
+                // shuffles and the lane that has the node as its corner (0, 0) makes ONE accumulator update per level
+                // and component; lanes on the patch's +x / +y edges also update the nodes beyond them (x = 4 column
+                // of the lower x half: side array).  All updates of a round touch different addresses, so nothing
+                // orders them: one shared-memory round trip where four dependent passes used to be.
+#pragma unroll
+                for (int dz = 0; dz < 2; dz++) {
+                    const int ol = o + dz * SP_Z, lx = (2 * zq + r + dz) * 9 + y;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        const double F0 = c == 0 ? fx[4 * dz] : c == 1 ? fy[4 * dz] : fz[4 * dz];
+                        const double F1 = c == 0 ? fx[4 * dz + 1] : c == 1 ? fy[4 * dz + 1] : fz[4 * dz + 1];
+                        const double F2 = c == 0 ? fx[4 * dz + 2] : c == 1 ? fy[4 * dz + 2] : fz[4 * dz + 2];
+                        const double F3 = c == 0 ? fx[4 * dz + 3] : c == 1 ? fy[4 * dz + 3] : fz[4 * dz + 3];
+                        const double u3 = __shfl_up_sync(0xffffffffu, F3, 4);       // element (x, y - 1), corner (1, 1)
+                        const double u2 = __shfl_up_sync(0xffffffffu, F2, 4);       // element (x, y - 1), corner (0, 1)
+                        const double a = ylo ? F1 + u3 : F1;                        // node (x + 1, y), this column pair
+                        const double ua = __shfl_up_sync(0xffffffffu, a, 1);        // node (x, y) from the x - 1 pair
+                        const double u3x = __shfl_up_sync(0xffffffffu, F3, 1);      // element (x - 1, y), corner (1, 1)
+                        double own = ylo ? F0 + u2 : F0;
+                        if (xlo) own += ua;
+                        acc[ol + c * SP_C] += own;
+                        if (xhi) {
+                            if (x == 3) accx[lx + c * SX4_C] += a; else acc[ol + 1 + c * SP_C] += a;
+                        }
+                        if (yhi) acc[ol + SP_ROW + c * SP_C] += xlo ? F2 + u3x : F2;
+                        if (xhi && yhi) {
+                            if (x == 3) accx[lx + 1 + c * SX4_C] += F3; else acc[ol + SP_ROW + 1 + c * SP_C] += F3;
+                        }
+                    }
                 }
             }
             // what the next tile needs in registers, requested now that this tile's forces have left them

@@ -246,6 +246,15 @@ class Solver:
         _chk(self._L.hgpu_fetch_all(self._h, which, out.ctypes.data))
         return out
 
+    def fetch_all_async(self, which: int, out: np.ndarray) -> None:
+        """Snapshot now (stream order), copy to `out` (ideally a PinnedArray's .a) in the background."""
+        if out.shape != (self._rows(which), 3) or out.dtype != np.float64 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 [rows][3] array")
+        _chk(self._L.hgpu_fetch_all_async(self._h, which, out.ctypes.data))
+
+    def fetch_wait(self) -> None:
+        _chk(self._L.hgpu_fetch_wait(self._h))
+
     def store_all(self, which: int, a) -> None:
         a = np.ascontiguousarray(a, np.float64)
         if a.size != 3 * self._rows(which):

@@ -203,6 +203,12 @@ int hgpu_fetch_nodes(hgpu_solver_t *s, int32_t which, const int32_t *lnid, int32
 /* Full read for 4D output and checkpoints (output.c:1233, io_checkpoint.c:29): [nharbored][3]
  * (conv arrays: [8*lenum][3]). */
 int hgpu_fetch_all(hgpu_solver_t *s, int32_t which, double *out);
+/* The same without stopping the time loop (checkpoints and 4D frames): the array (HGPU_TM1..3) is
+ * snapshotted on the device in stream order and copied to `out` (page-locked memory from hgpu_host_alloc for a
+ * truly asynchronous copy) on a separate stream; the call returns at once.  hgpu_fetch_wait blocks until every
+ * such read has landed; it only waits on events and may be called from a writer thread. */
+int hgpu_fetch_all_async(hgpu_solver_t *s, int32_t which, double *out);
+int hgpu_fetch_wait(hgpu_solver_t *s);
 /* Restart after checkpoint_read (psolve.c:4249), and test set-up: overwrite a device array. */
 int hgpu_store_all(hgpu_solver_t *s, int32_t which, const double *in);
 

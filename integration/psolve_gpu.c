@@ -42,6 +42,10 @@ void Timer_Stop(char *name);
 
 #include "hercules_gpu.h"
 
+int64_t hgpu_planes_node_list(int theNumberOfPlanes, int32_t *out);      /* io_planes_gpu.c */
+
+#include <pthread.h>
+
 static hgpu_solver_t *theGpu;
 static int32_t        theSavedTotalSteps = -1;
 
@@ -53,6 +57,79 @@ static int32_t        theSavedTotalSteps = -1;
             exit(1);                                                                       \
         }                                                                                  \
     } while (0)
+
+/* ---- asynchronous checkpoints ------------------------------------------------------------
+ * checkpoint_write (io_checkpoint.c:29-117) stops the reference for as long as two whole fields take to
+ * reach the disk.  Here the fields are snapshotted on the device (hgpu_fetch_all_async), travel to two
+ * page-locked shadow buffers while the time loop goes on, and a writer thread puts them into the file in the
+ * reference's layout: header {group size, step, nharboredmax} written by rank 0, then for rank r at byte
+ * 12 + 2 r nharboredmax sizeof(fvector_t): the tm2 array followed by the tm1 array (io_checkpoint.c:93-112),
+ * files checkpoint.out0 / checkpoint.out1 in turn.  The main thread only creates the file (rank 0) and meets
+ * the other ranks at a barrier, as checkpoint_write does, so that every writer finds the header in place. */
+typedef struct ckpt_job {
+    char      filename[256];
+    off_t     offset;
+    size_t    rows;
+    double   *tm1, *tm2;             /* shadow buffers (page-locked) */
+    pthread_t thread;
+    int       running, failed;
+} ckpt_job_t;
+static ckpt_job_t theCkpt;
+static int        theCkptNumber = 0;     /* io_checkpoint.c:38 CheckpointNumber */
+
+static void *ckpt_writer(void *arg)
+{
+    ckpt_job_t *j = arg;
+    if (hgpu_fetch_wait(theGpu) != 0) { j->failed = 1; return NULL; }
+    FILE *fp = fopen(j->filename, "rb+");
+    if (!fp) { j->failed = 1; return NULL; }
+    const size_t row = 3 * sizeof(double);
+    if (fseeko(fp, j->offset, SEEK_SET) != 0 || fwrite(j->tm2, row, j->rows, fp) != j->rows ||
+        fseeko(fp, j->offset + (off_t)(j->rows * row), SEEK_SET) != 0 || fwrite(j->tm1, row, j->rows, fp) != j->rows)
+        j->failed = 1;
+    if (fclose(fp) != 0) j->failed = 1;
+    return NULL;
+}
+
+static void ckpt_join(void)
+{
+    if (!theCkpt.running) return;
+    pthread_join(theCkpt.thread, NULL);
+    theCkpt.running = 0;
+    if (theCkpt.failed) solver_abort("gpu_solver_run", NULL, "asynchronous checkpoint to %s failed: %s\n",
+                                     theCkpt.filename, hgpu_last_error());
+}
+
+/* checkpoint_write's job for `step`, without stopping the loop */
+static void ckpt_write_async(int32_t step, int nharboredmax)
+{
+    ckpt_join();                                            /* the previous checkpoint is on disk first */
+    const size_t rows = (size_t)Global.myMesh->nharbored;
+    if (!theCkpt.tm1) {
+        theCkpt.tm1 = hgpu_host_alloc(sizeof(double) * 3 * (rows + 1));
+        theCkpt.tm2 = hgpu_host_alloc(sizeof(double) * 3 * (rows + 1));
+        if (!theCkpt.tm1 || !theCkpt.tm2) solver_abort("gpu_solver_run", NULL, "hgpu_host_alloc: %s\n", hgpu_last_error());
+    }
+    GPU(hgpu_fetch_all_async(theGpu, HGPU_TM1, theCkpt.tm1));
+    GPU(hgpu_fetch_all_async(theGpu, HGPU_TM2, theCkpt.tm2));
+    sprintf(theCkpt.filename, "%s%s%d", Param.theCheckPointingDirOut, "/checkpoint.out", theCkptNumber);
+    if (Global.myID == 0) {
+        FILE *fp = fopen(theCkpt.filename, "wb");
+        if (!fp) solver_abort("gpu_solver_run", NULL, "cannot create %s\n", theCkpt.filename);
+        int hdr[3] = {Global.theGroupSize, step, nharboredmax};
+        fwrite(hdr, sizeof(int), 3, fp);
+        fclose(fp);
+    }
+    MPI_Barrier(comm_solver);
+    theCkpt.offset = (off_t)(3 * sizeof(int)) + (off_t)2 * Global.myID * nharboredmax * (off_t)sizeof(fvector_t);
+    theCkpt.rows = rows;
+    theCkpt.failed = 0;
+    if (pthread_create(&theCkpt.thread, NULL, ckpt_writer, &theCkpt) != 0)
+        solver_abort("gpu_solver_run", NULL, "pthread_create failed\n");
+    theCkpt.running = 1;
+    theCkptNumber = theCkptNumber ? 0 : 1;
+}
+
 
 /* messenger_t list (psolve.h:235-272) -> flat arrays; list order = the reference's unpack order */
 static void flatten_messengers(messenger_t *first, hgpu_msglist_t *out)
@@ -258,6 +335,37 @@ static void gpu_solver_run(void)
     }
     const int32_t saved_nstations = Param.theNumberOfStations;
 
+    /* checkpoints: asynchronous by default (PSOLVE_GPU_ASYNC_CKPT=0: the reference's checkpoint_write on
+     * fields fetched synchronously) */
+    const int async_ckpt = Param.theCheckPointingRate != 0 &&
+                           !(getenv("PSOLVE_GPU_ASYNC_CKPT") && atoi(getenv("PSOLVE_GPU_ASYNC_CKPT")) == 0);
+    int nharboredmax = Global.myMesh->nharbored;
+    if (async_ckpt) {
+        int mine = Global.myMesh->nharbored;
+        MPI_Allreduce(&mine, &nharboredmax, 1, MPI_INT, MPI_MAX, comm_solver);       /* io_checkpoint.c:44-48 */
+    }
+    const int32_t saved_ckpt_rate = Param.theCheckPointingRate;
+
+    /* Planes: planes_print reads tm1 at the 8 nodes of every plane point (io_planes.c:151-250).
+     * Their sorted, duplicate-free list is fetched on a plane step instead of the whole field
+     * (PSOLVE_GPU_PLANES_FULL=1 keeps the whole-field copy). */
+    int32_t npl = 0, *pl_ids = NULL;
+    double *pl_tmp = NULL;
+    if (Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 &&
+        !(getenv("PSOLVE_GPU_PLANES_FULL") && atoi(getenv("PSOLVE_GPU_PLANES_FULL")))) {
+        const int64_t nraw = hgpu_planes_node_list(Param.theNumberOfPlanes, NULL);
+        int32_t *raw = malloc(sizeof(int32_t) * (size_t)(nraw + 1));
+        unsigned char *seen = calloc((size_t)Global.myMesh->nharbored + 1, 1);
+        hgpu_planes_node_list(Param.theNumberOfPlanes, raw);
+        for (int64_t i = 0; i < nraw; i++) seen[raw[i]] = 1;
+        for (int32_t n = 0; n < Global.myMesh->nharbored; n++) npl += seen[n];
+        pl_ids = malloc(sizeof(int32_t) * (size_t)(npl + 1));
+        pl_tmp = hgpu_host_alloc(sizeof(double) * 3 * (size_t)(npl + 1));
+        npl = 0;
+        for (int32_t n = 0; n < Global.myMesh->nharbored; n++) if (seen[n]) pl_ids[npl++] = n;
+        free(raw); free(seen);
+    }
+
     /* Source streaming: read_myForces does one fseeko + fread of this rank's row of
      * force_process.<rank> per step (psolve.c:3651-3667).  Here the rows of the next SRC_WIN steps are read
      * with ONE fread into a page-locked buffer and copied to HBM (hgpu_source_preload); each step then
@@ -307,9 +415,15 @@ static void gpu_solver_run(void)
         const int wave = DO_OUTPUT && (step % Param.theRate == 0);
         const int plane = (Param.theNumberOfPlanes != 0) && (step % Param.thePlanePrintRate == 0);
         const int stat = (Param.theNumberOfStations != 0) && (step % Param.theStationsPrintRate == 0);
-        if (ckpt || wave || plane) {
+        const int plane_sparse = plane && pl_ids != NULL;
+        const int ckpt_sync = ckpt && !async_ckpt;
+        if (ckpt && async_ckpt) ckpt_write_async(step, nharboredmax);
+        if (ckpt_sync || wave || (plane && !plane_sparse)) {
             GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
-            if (ckpt || wave) GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
+            if (ckpt_sync || wave) GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
+        } else if (plane_sparse) {
+            fetch_station_rows(HGPU_TM1, sv->tm1, pl_ids, npl, pl_tmp);       /* rows of tm1 planes_print reads */
+            if (stat && !dev_stations) fetch_station_rows(HGPU_TM1, sv->tm1, st_ids, nst, st_tmp);
         } else if (stat && !dev_stations) {
             fetch_station_rows(HGPU_TM1, sv->tm1, st_ids, nst, st_tmp);
         }
@@ -326,7 +440,9 @@ static void gpu_solver_run(void)
         }
         host_tap += MPI_Wtime() - tmark; tmark = MPI_Wtime();
         Timer_Start("Solver I/O");
+        if (async_ckpt) Param.theCheckPointingRate = 0;        /* written by ckpt_write_async above */
         solver_write_checkpoint(step, startingStep);
+        Param.theCheckPointingRate = saved_ckpt_rate;
         solver_update_status(step, startingStep);
         solver_output_wavefield(step);
         solver_output_planes(Global.mySolver, Global.myID, step);
@@ -397,6 +513,7 @@ static void gpu_solver_run(void)
         GPU(hgpu_stations_drain(theGpu, st_rows, st_steps, ST_RING, &nr));
         write_station_rows(st_rows, st_steps, nr, vel, acc);
     }
+    ckpt_join();
     const double loop_wall = MPI_Wtime() - loop_t0;
     /* leave the host arrays as the reference's loop would: tm1 = u(t_last), tm2 = u(t_last + dt) */
     GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
@@ -423,6 +540,9 @@ static void gpu_solver_run(void)
     free(st_ids); free(st_tmp); free(st_steps);
     hgpu_host_free(st_rows);
     hgpu_host_free(src_rows);
+    free(pl_ids); hgpu_host_free(pl_tmp);
+    hgpu_host_free(theCkpt.tm1); hgpu_host_free(theCkpt.tm2);
+    theCkpt.tm1 = theCkpt.tm2 = NULL;
 }
 
 void hgpu_hook_Timer_Start(char *name)

@@ -7,8 +7,8 @@
 //   1. the padded layout: 729 slots map to 729 different offsets inside a plane of SP_C doubles;
 //   2. bank conflicts: every gather / accumulator access of a warp is conflict-free (16 lanes of a
 //      half-warp hit 16 different 8-byte banks);
-//   3. races: inside one half of a pass no two threads touch the same accumulator; inside one ROUND (the
-//      code between two barriers) threads of DIFFERENT warps never do (only __syncwarp orders the halves);
+//   3. races: inside one ROUND (the code between two barriers) every accumulator address is updated by
+//      exactly one thread of the CTA (the shares of neighbouring elements are combined with shuffles first);
 //   4. numerics: the accumulated forces equal those of 512 single-element evaluations
 //      (wht_forward, scale_modes, wht_inverse, scatter) to rounding.
 #include <cmath>
@@ -39,6 +39,13 @@ static void check_banks(const std::vector<Access> &acc, const char *what)
         CHECK(banks.size() == kv.second.size(), "%s: bank conflict in half-warp %d (%zu lanes, %zu banks)", what, kv.first,
               kv.second.size(), banks.size());
     }
+}
+
+static void check_banks_rebased(const std::vector<Access> &acc, int base, const char *what)
+{
+    std::vector<Access> b;
+    for (const Access &a : acc) b.push_back({a.tid - base, a.off});
+    check_banks(b, what);
 }
 
 int main()
@@ -108,32 +115,35 @@ int main()
             scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);
             wht_inverse(wx, q.f[0]); wht_inverse(wy, q.f[1]); wht_inverse(wz, q.f[2]);
         }
-        // one ROUND = the code between two barriers: four halves (dx = 0 / 1 x dy = 0 / 1) separated by
-        // __syncwarp only, so no two DIFFERENT warps may touch one address anywhere inside the round; the
-        // dx = 1 corners of the x = 3 threads go to the side array of the x = 4 column
-        std::map<long, int> warp_of;                        // address -> warp that touched it in this round
-        for (int dx = 0; dx < 2; dx++) for (int half = 0; half < 2; half++) {
-            std::map<long, int> lane_of;
-            std::vector<Access> a1, a2;
-            for (int tid = 0; tid < 256; tid++) {
-                Regs &q = R[tid];
+        // one ROUND = the code between two barriers.  The accumulator update is shuffle-combined: per level and
+        // component the lanes exchange shares with __shfl_up (by 4 = y - 1, by 1 = x - 1) and every address is
+        // updated by exactly ONE thread of the CTA in the round -- checked here over all 256 threads.
+        std::map<long, int> owner;                          // address -> thread that updated it in this round
+        auto upd = [&](int tid, bool side, int o, int c, double v, std::vector<Access> *rec) {
+            const long key = (side ? 1000000L : 0L) + o + (side ? c * SX4_C : c * SP_C);
+            CHECK(owner.insert({key, tid}).second, "round %d: threads %d and %d update the same accumulator", r, owner[key], tid);
+            if (side) accx[o + c * SX4_C] += v; else { acc[o + c * SP_C] += v; if (rec) rec->push_back({tid, o}); }
+        };
+        for (int w = 0; w < 8; w++) for (int dz = 0; dz < 2; dz++) for (int c = 0; c < 3; c++) {
+            double F0[32], F1[32], F2[32], F3[32], u3[32], u2[32], a[32], ua[32], u3x[32];
+            for (int l = 0; l < 32; l++) { const Regs &q = R[32 * w + l]; F0[l] = q.f[c][4 * dz]; F1[l] = q.f[c][4 * dz + 1]; F2[l] = q.f[c][4 * dz + 2]; F3[l] = q.f[c][4 * dz + 3]; }
+            for (int l = 0; l < 32; l++) { u3[l] = l >= 4 ? F3[l - 4] : F3[l]; u2[l] = l >= 4 ? F2[l - 4] : F2[l]; u3x[l] = l >= 1 ? F3[l - 1] : F3[l]; }
+            for (int l = 0; l < 32; l++) a[l] = ((l >> 2) & 7) != 0 ? F1[l] + u3[l] : F1[l];
+            for (int l = 0; l < 32; l++) ua[l] = l >= 1 ? a[l - 1] : a[l];
+            std::vector<Access> a_own, a_x, a_y;
+            for (int l = 0; l < 32; l++) {
+                const int tid = 32 * w + l;
                 const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-                const bool redir = dx == 1 && x == 3;
-                for (int lvl = 0; lvl < 2; lvl++) {
-                    const int j = dx + 2 * half + 4 * lvl;
-                    int o; long key;
-                    if (redir) { o = (2 * zq + r + lvl) * 9 + y + half; key = 1000000L + o; }
-                    else { o = q.o + lvl * SP_Z + dx + SP_ROW * half; key = o; }
-                    CHECK(lane_of.insert({key, tid}).second, "round %d dx %d half %d: threads %d and %d update the same accumulator", r, dx, half, lane_of[key], tid);
-                    auto w = warp_of.find(key);
-                    CHECK(w == warp_of.end() || w->second == tid / 32, "round %d: warps %d and %d update the same accumulator inside one round",
-                          r, w == warp_of.end() ? -1 : w->second, tid / 32);
-                    warp_of[key] = tid / 32;
-                    if (redir) acc_add3s(accx.data(), o, SX4_C, q.f[0][j], q.f[1][j], q.f[2][j]);
-                    else { acc_add3(acc.data(), o, q.f[0][j], q.f[1][j], q.f[2][j]); (lvl == 0 ? a1 : a2).push_back({tid, o}); }
-                }
+                const bool xlo = (tid & 3) != 0, xhi = (tid & 3) == 3, ylo = y != 0, yhi = y == 7;
+                const int ol = R[tid].o + dz * SP_Z, lx = (2 * zq + r + dz) * 9 + y;
+                double own = ylo ? F0[l] + u2[l] : F0[l];
+                if (xlo) own += ua[l];
+                upd(tid, false, ol, c, own, &a_own);
+                if (xhi) { if (x == 3) upd(tid, true, lx, c, a[l], nullptr); else upd(tid, false, ol + 1, c, a[l], &a_x); }
+                if (yhi) upd(tid, false, ol + SP_ROW, c, xlo ? F2[l] + u3x[l] : F2[l], &a_y);
+                if (xhi && yhi) { if (x == 3) upd(tid, true, lx + 1, c, F3[l], nullptr); else upd(tid, false, ol + SP_ROW + 1, c, F3[l], nullptr); }
             }
-            if (dx == 0) { check_banks(a1, "accumulate"); check_banks(a2, "accumulate"); }   // dx = 1: the redirected lanes may collide
+            check_banks_rebased(a_own, 32 * w, "own update"); check_banks_rebased(a_x, 32 * w, "+x edge update"); check_banks_rebased(a_y, 32 * w, "+y edge update");
         }
     }
     // drain: the side array belongs to the x = 4 column

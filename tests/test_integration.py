@@ -152,3 +152,72 @@ def test_device_stations_write_the_same_files():
             files[host] = [(d / "out" / "stations" / f"station.{i}").read_bytes() for i in range(len(c.stations))]
     assert files["0"] == files["1"]
     assert all(len(f.splitlines()) > 10 for f in files["0"])
+
+
+PLANES = [(100.0, 150.0, 0.0, 50.0, 15, 50.0, 12, 0.0, 0.0), (200.0, 300.0, 20.0, 40.0, 10, 30.0, 8, 30.0, 60.0)]
+
+
+def _run_gpu(case, env_extra=None, nranks=1, keep=()):
+    import os, subprocess
+    with tempfile.TemporaryDirectory() as td:
+        d = refcase.write_case(case, td)
+        env = dict(os.environ, HMPI_NP=str(nranks), **(env_extra or {}))
+        p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=env, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-4000:]
+        return {k: (d / k).read_bytes() for k in keep}, p.stdout
+
+
+def test_planes_sparse_fetch_writes_the_same_files():
+    """Output planes (io_planes.c:151-250): psolve_gpu fetches only the rows of tm1 the reference's own
+    planes_print interpolates from (node list from the reference's plane tables, integration/io_planes_gpu.c)
+    instead of the whole field.  planedisplacements.N must be byte-identical to the whole-field variant
+    (PSOLVE_GPU_PLANES_FULL=1) and agree with the CPU reference's files to 1e-10 relative L2 (north_star)."""
+    if not (refcase.have_ref("psolve_ref_O2") and refcase.have_ref("mkcvm") and GPU_BIN.exists()):
+        pytest.skip("reference binaries / integration/_bin/psolve_gpu not built")
+    c = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.06, planes=PLANES, plane_rate=5)
+    keep = [f"out/planes/planedisplacements.{i}" for i in range(len(PLANES))]
+    sparse, _ = _run_gpu(c, keep=keep)
+    full, _ = _run_gpu(c, {"PSOLVE_GPU_PLANES_FULL": "1"}, keep=keep)
+    assert sparse == full
+    with tempfile.TemporaryDirectory() as td:
+        d = refcase.write_case(c, td)
+        refcase.run("psolve_ref_O2", d, nranks=1, timeout=300)
+        for k in keep:
+            ref = np.frombuffer((d / k).read_bytes(), np.float64)
+            got = np.frombuffer(sparse[k], np.float64)
+            assert ref.shape == got.shape and ref.size == 3 * (c.steps // 5 + (1 if c.steps % 5 else 0)) * (15 * 12 if k.endswith("0") else 10 * 8)
+            assert np.abs(ref).max() > 0
+            assert np.linalg.norm(got - ref) <= 1e-10 * np.linalg.norm(ref)
+
+
+def test_async_checkpoint_same_bytes_and_restart():
+    """Checkpoints (io_checkpoint.c:29-117): psolve_gpu snapshots tm1 / tm2 on the device, lets the time loop
+    run on and writes the reference's file layout from a writer thread (hgpu_fetch_all_async).  The files
+    must be byte-identical to those of the reference's own checkpoint_write on synchronously fetched fields
+    (PSOLVE_GPU_ASYNC_CKPT=0), and a run restarted from one (checkpoint_read, use_checkpoint = 1) must
+    continue exactly as the uninterrupted run."""
+    import os, shutil, subprocess
+    if not (refcase.have_ref("mkcvm") and GPU_BIN.exists()):
+        pytest.skip("integration/_bin/psolve_gpu not built")
+    c = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.06, checkpoint_rate=20)
+    keep = ["out/checkpoints/checkpoint.out0", "out/checkpoints/checkpoint.out1"] + [f"out/stations/station.{i}" for i in range(3)]
+    a, _ = _run_gpu(c, keep=keep)
+    b, _ = _run_gpu(c, {"PSOLVE_GPU_ASYNC_CKPT": "0"}, keep=keep)
+    for k in keep:
+        assert a[k] == b[k], k
+    hdr = np.frombuffer(a[keep[1]][:12], np.int32)
+    assert hdr[0] == 1 and hdr[1] == 40 and len(a[keep[1]]) == 12 + 2 * 24 * hdr[2]
+    assert np.abs(np.frombuffer(a[keep[1]][12:], np.float64)).max() > 0
+    # restart from the step-40 checkpoint
+    c2 = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.06, use_checkpoint=1)
+    with tempfile.TemporaryDirectory() as td:
+        d = refcase.write_case(c2, td)
+        (d / "out" / "checkpoints" / "checkpoint.in").write_bytes(a[keep[1]])
+        p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=dict(os.environ, HMPI_NP="1"), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert p.returncode == 0, p.stdout[-4000:]
+        for i in range(3):
+            rows_full = [ln for ln in a[f"out/stations/station.{i}"].decode().splitlines() if ln.strip() and not ln.lstrip().startswith("#")]
+            rows_re = [ln for ln in (d / "out" / "stations" / f"station.{i}").read_text().splitlines() if ln.strip() and not ln.lstrip().startswith("#")]
+            assert len(rows_full) == c.steps and rows_re == rows_full[40:], i
