@@ -866,6 +866,8 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping
     PhaseTimer pt(s, fuse ? PH_FUSED_STEP : (tm.stiff ? PH_ADDFORCE_E : PH_DAMPING));
+    // multi-rank: never ask for every CTA slot of the device (see the launch below)
+    if (s->P.nranks > 1) max_grid = max_grid > 0 ? std::min(max_grid, s->grid_late) : s->grid_late;
     int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin);
     const int B = s->block;
     if (begin == 0) A.epoch = ++s->epoch;       // a new pass over the tiles (a split pass shares one epoch)
@@ -899,9 +901,16 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
         A.tile_meta = s->t_meta_s;
         A.tile_begin = gb; A.ntiles = ge; A.struct_begin = sb; A.struct_end = se; A.grid_struct = Gs;
     }
-    // Cooperative launch: a tile's finish spins on flags raised by other CTAs of the same launch, so
-    // every CTA must be resident -- the driver then either co-schedules the whole grid or fails the launch
+    // Cooperative launch (single rank): a tile's finish spins on flags raised by other CTAs of the same launch,
+    // so every CTA must be resident -- the driver then either co-schedules the whole grid or fails the launch
     // (it never starts a part of it), whatever else shares the device.
+    // NOT with several ranks: a cooperative grid that needs every slot of the device cannot start while ANY
+    // other kernel is resident, and a kernel of another library that spins for its peer -- the NCCL kernel of a
+    // host-side barrier -- closes a cycle: this rank's steps wait for that kernel, the peer's steps wait for this
+    // rank's halo, the peer's host (launch queue full) never reaches its barrier (found at 120+ queued steps on
+    // 2 GPUs, r02 call 5c).  Multi-rank launches are ordinary ones that leave the communication SM free, so
+    // the grid fits beside the halo kernels and a foreign kernel or two; the bounded wait in wait_deps reports
+    // the case where it still does not.
     const void *fn = nullptr;
     size_t smem = (size_t)s->smem_u2;
 #define PICK(T)                                                                                   \
@@ -934,7 +943,7 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
         cfg.dynamicSmemBytes = smem; cfg.stream = s->stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeCooperative; at[0].val.cooperative = 1;
-        cfg.attrs = at; cfg.numAttrs = s->cooperative ? 1 : 0;
+        cfg.attrs = at; cfg.numAttrs = (s->cooperative && s->P.nranks == 1) ? 1 : 0;
         CK(cudaLaunchKernelExC(&cfg, fn, kargs));
     }
     CK(cudaGetLastError());

@@ -18,3 +18,5 @@ try:
 except Exception as e: print("$f", "ERR", e); print(open("$O/$f.err").read()[-800:])
 PY
 done
+unset HGPU_STRUCT
+timeout 600 python -m pytest tests/test_integration.py -x -q > $O/pytest_integration.log 2>&1; echo "rc=$?" >> $O/pytest_integration.log; tail -n 5 $O/pytest_integration.log
