@@ -163,6 +163,7 @@ struct hgpu_solver {
     double *conv = nullptr; double *t_ent_bkt = nullptr; int32_t *entry_of_elem = nullptr;
     double *conv_scratch = nullptr;      // [8 E][3] staging for hgpu_fetch_all / hgpu_store_all of a conv array
     double *nt3 = nullptr;               // [N][3] {+-1/mass, m2, m1} for the fused update
+    int smem_struct = 0, cap_acc_struct = 0, grid_struct_max = 0;   // STRUCT launches: one CTA of 512 threads per SM
     int smem_u2 = 0, smem_nou2 = 0, block = 256, grid = 0, grid_late = 0, cap_slots = 0, cap_acc = 0, cap_owned = 0,
         cap_recs = 0, cap_srcs = 0, ctas_per_sm = 0;
     // special-node path
@@ -342,13 +343,9 @@ static TileCaps tile_caps(int max_smem, int32_t tile_nodes, bool allow_struct = 
     c.elem_block = 512;
     const char *eenv = getenv("HGPU_ELEM_BLOCK");
     if (eenv && atoi(eenv) > 0) c.elem_block = atoi(eenv);
-    // with structured tiles the accumulator holds three padded planes (SP_TOTAL doubles > 3 x 9^3): a little
-    // less is left for the stages and the finish buffers (224 / 272 cover the far-face tiles of a uniform mesh)
-    if (allow_struct) { c.max_recs = 224; c.max_srcs = 272; }
     const int budget = (per_cta - finish_smem_bytes(c.max_recs, c.max_srcs)) / 8;     // doubles
     // an interior tile of a uniform region stages and accumulates 9^3 nodes and owns 8^3 of them
-    const int32_t rest = allow_struct ? (budget - SP_TOTAL) / 12      // 12 S + the padded planes
-                                      : budget / 15;                  // 12 S + 3 A with S = A
+    const int32_t rest = budget / 15;                      // 12 S + 3 A with S = A
     c.max_owned = cap_owned;
     c.max_acc = std::max(16, std::min(rest, 65535 / 3) & ~15);
     c.max_slots = c.max_acc;
@@ -537,7 +534,6 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             const char *senv = getenv("HGPU_STRUCT");
             if (!(senv && atoi(senv) == 1) && !(params->flags & HGPU_FLAG_STRUCT)) want_struct = false;
         }
-        const int smem_cap0 = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
         TileCaps caps = tile_caps(max_smem, params->tile_nodes, want_struct);
         for (;;) {
             if (!build_tile_plan(E, N, mesh->elem_lnid, caps, (params->nranks > 1 && !bkt) ? early_node.data() : nullptr,
@@ -545,15 +541,16 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
                 hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan: %s", err.c_str());
             }
             if (!caps.allow_struct) break;
-            // the padded accumulator of the structured path (SP_TOTAL doubles) must fit beside the stages
+            // STRUCT launches run ONE CTA of 512 threads per SM: two stages + the planes and the element-force
+            // buffer (SP_TOTAL + SF_TOTAL doubles) + the finish buffers must fit the SM's shared memory
             const TilePlan &q = s->plan;
             bool any = false;
             for (uint8_t f : q.tile_struct) any = any || f;
-            const int need = step_smem_bytes(true, (q.max_tile_nodes + 15) & ~15, std::max((q.max_tile_acc + 15) & ~15, any ? SP_C : 0),
+            const int need = step_smem_bytes(true, (q.max_tile_nodes + 15) & ~15, (SP_TOTAL + SF_TOTAL + 2) / 3,
                                              (q.max_tile_owned + 15) & ~15, std::min(caps.max_recs, (q.max_tile_recs + 15) & ~15),
                                              std::min(caps.max_srcs, (q.max_tile_srcs + 15) & ~15));
-            if (!any || need <= smem_cap0) break;
-            caps.allow_struct = 0;              // does not fit next to this mesh's largest generic tile: plain plan
+            if (!any || need <= max_smem) break;
+            caps.allow_struct = 0;              // does not fit: plain plan
         }
         TilePlan &pl = s->plan;
         const size_t entries = pl.elem_id.size();
@@ -707,12 +704,13 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         TRYCU(cudaMemset(s->t_flag, 0, std::max<size_t>(1, (size_t)pl.ntiles) * sizeof(unsigned int)));
         // shared memory actually needed by this plan
         s->cap_slots = (pl.max_tile_nodes + 15) & ~15; s->cap_acc = (pl.max_tile_acc + 15) & ~15;
-        if (s->n_struct > 0) s->cap_acc = std::max(s->cap_acc, (int)SP_C);      // padded planes of the structured path
+        s->cap_acc_struct = ((SP_TOTAL + SF_TOTAL + 2) / 3 + 15) & ~15;         // planes + element forces (STRUCT launches)
         s->cap_owned = (pl.max_tile_owned + 15) & ~15;
         s->cap_recs = std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15);
         s->cap_srcs = std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15);
         s->smem_u2 = step_smem_bytes(true, s->cap_slots, s->cap_acc, s->cap_owned, s->cap_recs, s->cap_srcs);
         s->smem_nou2 = step_smem_bytes(false, s->cap_slots, s->cap_acc, s->cap_owned, s->cap_recs, s->cap_srcs);
+        s->smem_struct = step_smem_bytes(true, s->cap_slots, s->cap_acc_struct, s->cap_owned, s->cap_recs, s->cap_srcs);
         const char *benv = getenv("HGPU_BLOCK");
         if (benv && atoi(benv) == 384) s->block = 384;
         int occ = 0;
@@ -720,9 +718,7 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         // share so that solvers with different plans can coexist in one process
         const int smem_cap = std::min(max_smem, (max_smem + 1024) / 2 - 1024);
         if (s->smem_u2 > smem_cap) { hgpu_finalize(s); return fail(HGPU_EINVAL, "tile plan needs %d bytes of shared memory (> %d)", s->smem_u2, smem_cap); }
-        if (s->n_struct > 0 && 3 * s->cap_slots + 3 * s->cap_owned < SP_TOTAL + STRUCT_OWNED + SX4_TOTAL) {
-            hgpu_finalize(s); return fail(HGPU_EINVAL, "internal: stage too small for the structured path");
-        }
+        if (s->n_struct > 0 && s->smem_struct > max_smem) s->n_struct = 0;
 #define SETUP(T)                                                                                             \
         do {                                                                                                 \
             TRYCU(cudaFuncSetAttribute(step_kernel<0, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
@@ -733,8 +729,8 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<3, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
-            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<0, false, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
-            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
+            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<0, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
+            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
@@ -744,11 +740,12 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_w, step_kernel<1, false, 256, true>, 256, s->smem_u2));
             occ = std::min(occ, occ_w);
         }
-        if (s->block != 256) s->n_struct = 0;     // the structured path is written for 256 threads
+        if (s->block != 256) s->n_struct = 0;     // STRUCT launches replace the 256-thread ones only
         if (s->n_struct > 0) {
             int occ_s = 0;
-            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, false, 256, false, true>, 256, s->smem_u2));
-            occ = std::min(occ, occ_s);
+            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, false, 512, false, true>, 512, s->smem_struct));
+            if (occ_s < 1) s->n_struct = 0;
+            s->grid_struct_max = nsm * std::max(occ_s, 1);
         }
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
         {
@@ -869,19 +866,23 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     // multi-rank: never ask for every CTA slot of the device (see the launch below)
     if (s->P.nranks > 1) max_grid = max_grid > 0 ? std::min(max_grid, s->grid_late) : s->grid_late;
     int G = std::min(max_grid > 0 ? std::min(max_grid, s->grid) : s->grid, end - begin);
-    const int B = s->block;
     if (begin == 0) A.epoch = ++s->epoch;       // a new pass over the tiles (a split pass shares one epoch)
     // STRUCT launch: the range is taken from the second processing order (structured tiles last); its
     // structured part goes to CTAs [0, grid_struct), the slot-table part to the others, in proportion to
     // the elements of either kind weighted by their relative cost
-    bool use_struct = fuse && !dense && (mode == 0 || mode == 1) && B == 256 && s->n_struct > 0 &&
+    bool use_struct = fuse && !dense && (mode == 0 || mode == 1) && s->block == 256 && s->n_struct > 0 &&
                       !(s->P.flags & HGPU_FLAG_WPASS) && end > s->n_generic;
+    int B = s->block;
     if (use_struct) {
         const int32_t gb = std::min(begin, s->n_generic), ge = s->n_generic, sb = std::max(begin, s->n_generic), se = end;
         const int32_t ng = ge - gb, ns = se - sb;
         const double wg = s->generic_cost * (double)(s->ent_prefix_s[ge] - s->ent_prefix_s[gb]);
         const double ws = (double)(s->ent_prefix_s[se] - s->ent_prefix_s[sb]);
-        const int Gmax = max_grid > 0 ? std::min(max_grid, s->grid) : s->grid;
+        // one CTA of 512 threads per SM (multi-rank: the communication SMs stay free)
+        B = 512;
+        A.cap_acc = s->cap_acc_struct;
+        const int Gmax = s->P.nranks > 1 ? std::max(1, s->grid_struct_max - (s->grid - s->grid_late) / std::max(1, s->ctas_per_sm))
+                                         : s->grid_struct_max;
         int Gs, Gg;
         if (ng == 0) { Gs = std::min(Gmax, ns); Gg = 0; }
         else {
@@ -931,8 +932,9 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
         fn = (const void *)step_kernel<1, false, 256, true>;       // opt-in variant, see hgpu_kernels.cuh
     else if (use_struct) {
         // structured tiles take their own path on their own CTAs, the others the slot-table path, in one launch
-        if (mode == 0) { fn = (const void *)step_kernel<0, false, 256, false, true>; smem = (size_t)s->smem_nou2; }
-        else fn = (const void *)step_kernel<1, false, 256, false, true>;
+        smem = (size_t)s->smem_struct;
+        if (mode == 0) fn = (const void *)step_kernel<0, false, 512, false, true>;
+        else fn = (const void *)step_kernel<1, false, 512, false, true>;
     }
     else if (B == 384) PICK(384); else PICK(256);
 #undef PICK
@@ -1623,9 +1625,7 @@ extern "C" int hgpu_plan_build(const hgpu_mesh_t *mesh, int32_t tile_nodes, hgpu
     out->tile_elems_total = (int64_t)pl.elem_id.size();
     out->tile_halo_total = pl.halo_nodes_total;
     estimate_wavefronts(pl, &out->est_gather_wavefronts, &out->est_scatter_wavefronts);
-    bool any_struct = false;
-    for (uint8_t f : pl.tile_struct) any_struct = any_struct || f;
-    out->smem_bytes = step_smem_bytes(true, (pl.max_tile_nodes + 15) & ~15, std::max((pl.max_tile_acc + 15) & ~15, any_struct ? (int)SP_C : 0),
+    out->smem_bytes = step_smem_bytes(true, (pl.max_tile_nodes + 15) & ~15, (pl.max_tile_acc + 15) & ~15,
                                       (pl.max_tile_owned + 15) & ~15, std::min(caps.max_recs, (pl.max_tile_recs + 15) & ~15),
                                       std::min(caps.max_srcs, (pl.max_tile_srcs + 15) & ~15));
     out->block_threads = 256;

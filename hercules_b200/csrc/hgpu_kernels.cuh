@@ -633,6 +633,7 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
 // butterfly stages -- 36 gathers and 36 updates per pair -- was correct but spilled: r02 call 2.)
 // ------------------------------------------------------------------------------------------
 constexpr int SP_ROW = 12, SP_Z = 108, SP_C = 972, SP_TOTAL = 3 * SP_C;     // doubles
+constexpr int SF_TOTAL = 24 * 512;                                          // element forces of one structured tile
 
 // tile-local slot (Morton for the 512 owned nodes, canonical far-face order for the 217 others,
 // hgpu_internal.h) -> offset of the node inside one component plane
@@ -693,8 +694,8 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
 {
     constexpr bool STRUCT = KIND == 1;
     static_assert(!WPASS || (MODE == 1 && !DENSE), "WPASS is a variant of the Rayleigh + effective kernel");
-    static_assert(!STRUCT || ((MODE == 0 || MODE == 1) && !DENSE && !WPASS && THREADS == 256),
-                  "STRUCT: effective stiffness with or without Rayleigh damping, 256 threads");
+    static_assert(!STRUCT || ((MODE == 0 || MODE == 1) && !DENSE && !WPASS && THREADS == 512),
+                  "STRUCT: effective stiffness with or without Rayleigh damping, 512 threads");
     constexpr bool U2E = MODE != 0;          // elements read u2
     extern __shared__ double smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
@@ -780,7 +781,7 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         beta_pref = ldg_f64_pinned(A.tile_beta + t);
     }
 
-    double spre[2][3], cpre[3];          // STRUCT: node-table rows and coefficients of the NEXT structured tile
+    double spre[3], cpre[3];             // STRUCT: node-table row (slot tid) and coefficients of the NEXT structured tile
     bool pre_ok = false;
     for (int it = 0;; it++) {
         double *su1 = smem + (it & 1) * stage_doubles;
@@ -797,20 +798,15 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         // registers from the previous structured tile's second round (spre / cpre); a structured tile that
         // follows a slot-table tile (or is the CTA's first) requests them here, before the landing wait
         constexpr bool st = STRUCT;           // every tile of this loop is a structured one (host-side lists)
-        double snt[2][3], scf[3];
+        double snt[3], scf[3];
         if (STRUCT && st) {
             if (!pre_ok) {
-                const int n0e = meta_group(m_cur, 0).x;
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const double *nt = A.nt3 + 3 * (size_t)(n0e + tid + 256 * q);
-                    spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
-                }
+                const double *nt = A.nt3 + 3 * (size_t)(meta_group(m_cur, 0).x + tid);
+                spre[0] = ldg_f64_pinned(nt); spre[1] = ldg_f64_pinned(nt + 1); spre[2] = ldg_f64_pinned(nt + 2);
                 const double *tc = A.tile_coef + 4 * (size_t)t;
                 cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
             }
-#pragma unroll
-            for (int q = 0; q < 2; q++) { snt[q][0] = spre[q][0]; snt[q][1] = spre[q][1]; snt[q][2] = spre[q][2]; }
+            snt[0] = spre[0]; snt[1] = spre[1]; snt[2] = spre[2];
             scf[0] = cpre[0]; scf[1] = cpre[1]; scf[2] = cpre[2];
         }
         pre_ok = false;
@@ -848,156 +844,109 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         const bool prv_pending = it > 0;
         unsigned int flag_value = A.epoch;
         if (STRUCT && st) {
-            // ---- structured tile (see the comment above sp_of_slot) ------------------------------------
-            const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-            // pre-pass, read side: w of this thread's (up to) three staged nodes -- slots tid, tid + 256 and
-            // 512 + tid -- and the inertia term m2 u1 - m1 u2 of the two owned ones (0 for SPECIAL nodes)
-            double wv[3][3], iv[2][3];
+            // ---- structured tile, 512 threads (see the comment above sp_of_slot) -------------------------
+            // thread = element (x, y, z) of the cell in the element phase, = node (x, y, z) (and, tid < 217, far-
+            // face node tid) in the node phase, = staged slot tid (and 512 + tid) where data is in slot order
+            const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, z = tid >> 6;
+            double *W = acc;                    // padded planes of w; later the owned nodes' forces in slot order
+            double *F = acc + SP_TOTAL;         // element forces, F[(3 j + c) * 512 + element thread]
+            // pre-pass: w = u1 + beta (u1 - u2) of slot tid and of far-face slot 512 + tid, into the planes
+            // (the raw stage stays: the inertia term is taken from it when the tile is settled)
 #pragma unroll
-            for (int q = 0; q < 3; q++) {
-                const int k = 3 * (q < 2 ? tid + 256 * q : 512 + tid);
-                if (q < 2 || tid < 217) {
+            for (int q = 0; q < 2; q++) {
+                if (q == 0 || tid < 217) {
+                    const int sl = q == 0 ? tid : 512 + tid, k = 3 * sl, sp = sp_of_slot(sl);
 #pragma unroll
                     for (int c = 0; c < 3; c++) {
                         const double x1 = su1[k + c];
-                        double x2 = 0.0;
-                        if (MODE == 1 || q < 2) x2 = su2[k + c];
-                        wv[q][c] = MODE == 1 ? fma(scf[2], x1 - x2, x1) : x1;
-                        if (q < 2) iv[q][c] = snt[q][1] * x1 - snt[q][2] * x2;
+                        W[sp + c * SP_C] = MODE == 1 ? fma(scf[2], x1 - su2[k + c], x1) : x1;
                     }
                 }
             }
-            __syncthreads();                    // the raw stage has been read by everybody
-            double *W = su1;                    // three padded planes over the raw stage ...
-            double *srm_own = su1 + SP_TOTAL;   // ... and 1/mass of the owned nodes behind them
-            double *accx = srm_own + 512;       // ... and the side array of the x = 4 column (SX4_*)
-            if (tid < SX4_TOTAL) accx[tid] = 0.0;
-#pragma unroll
-            for (int q = 0; q < 3; q++) {
-                if (q < 2 || tid < 217) {
-                    const int sl = q < 2 ? tid + 256 * q : 512 + tid;
-                    const int sp = sp_of_slot(sl);
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        W[sp + c * SP_C] = wv[q][c];
-                        if (q < 2) acc[sp + c * SP_C] = iv[q][c];       // the accumulator starts from the inertia term
-                    }
-                    if (q < 2) srm_own[sl] = snt[q][0];
-                }
-            }
-            if (prv_pending) {                  // flags of the previous tile's publishers: checked after pass A
+            if (prv_pending) {                  // flags of the previous tile's publishers: checked before the node phase
                 const int4 md = meta_group(m_prv, 3);
                 if (tid < md.y - md.x) flag_value = ld_relaxed_u32(dep_flag(A, md, fb_prv, tid));
             }
             __syncthreads();
-            const double ca = -0.5625 * (scf[1] + 2.0 * scf[0]), cc = -0.5625 * scf[1], cb = -0.5625 * scf[0];
-            const int o0 = (2 * zq) * SP_Z + y * SP_ROW + x;
-            // two rounds: element (x, y, 2 zq), then (x, y, 2 zq + 1).  Each is gathered, evaluated and added to
-            // the accumulator on its own (carrying anything from the first to the second costs the registers
-            // the operator itself needs: measured, r02 call 2 -- 600 bytes of spills per thread and tile).
-            // Inside a round the warps touch disjoint addresses (levels by zq, the x = 4 column through the side
-            // array); the ONE barrier between the rounds sits behind the second element's arithmetic, where nobody
-            // waits for it.
-            const bool xlo = (tid & 3) != 0, xhi = (tid & 3) == 3, ylo = y != 0, yhi = y == 7;
-#pragma unroll 1
-            for (int r = 0; r < 2; r++) {
-                const int o = o0 + r * SP_Z;
-                double fx[8], fy[8], fz[8];
-                {
-                    double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8];
-                    gather_face(W, o, wx[0], wx[1], wx[2], wx[3]);
-                    gather_face(W + SP_C, o, wy[0], wy[1], wy[2], wy[3]);
-                    gather_face(W + 2 * SP_C, o, wz[0], wz[1], wz[2], wz[3]);
-                    gather_face(W, o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
-                    gather_face(W + SP_C, o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
-                    gather_face(W + 2 * SP_C, o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
-                    wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
-                    scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);        // w* reused as the scaled modes
-                    wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
-                }
-                if (r == 1) {
-                    // every warp is done with the first round's updates before anybody starts the second's
-                    if (prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
-                    __syncthreads();
-                    if (prv_pending) {
-                        request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
-                        cp_async_commit();
-                    }
-                }
-                // Shuffle-combined update.  Within the warp's 4 x 8 patch of one level the four elements around a
-                // node are lanes (xl, y), (xl - 1, y), (xl, y - 1), (xl - 1, y - 1): their shares are summed with
-                // shuffles and the lane that has the node as its corner (0, 0) makes ONE accumulator update per level
-                // and component; lanes on the patch's +x / +y edges also update the nodes beyond them (x = 4 column
-                // of the lower x half: side array).  All updates of a round touch different addresses, so nothing
-                // orders them: one shared-memory round trip where four dependent passes used to be.
+            // ---- element phase: gather 24, evaluate, store the 24 corner forces (no accumulator, no order) ----
+            {
+                const double ca = -0.5625 * (scf[1] + 2.0 * scf[0]), cc = -0.5625 * scf[1], cb = -0.5625 * scf[0];
+                const int o = z * SP_Z + y * SP_ROW + x;
+                double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8], fx[8], fy[8], fz[8];
+                gather_face(W, o, wx[0], wx[1], wx[2], wx[3]);
+                gather_face(W + SP_C, o, wy[0], wy[1], wy[2], wy[3]);
+                gather_face(W + 2 * SP_C, o, wz[0], wz[1], wz[2], wz[3]);
+                gather_face(W, o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
+                gather_face(W + SP_C, o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
+                gather_face(W + 2 * SP_C, o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
+                wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+                scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);            // w* reused as the scaled modes
+                wht_inverse(wx, fx); wht_inverse(wy, fy); wht_inverse(wz, fz);
 #pragma unroll
-                for (int dz = 0; dz < 2; dz++) {
-                    const int ol = o + dz * SP_Z, lx = (2 * zq + r + dz) * 9 + y;
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        const double F0 = c == 0 ? fx[4 * dz] : c == 1 ? fy[4 * dz] : fz[4 * dz];
-                        const double F1 = c == 0 ? fx[4 * dz + 1] : c == 1 ? fy[4 * dz + 1] : fz[4 * dz + 1];
-                        const double F2 = c == 0 ? fx[4 * dz + 2] : c == 1 ? fy[4 * dz + 2] : fz[4 * dz + 2];
-                        const double F3 = c == 0 ? fx[4 * dz + 3] : c == 1 ? fy[4 * dz + 3] : fz[4 * dz + 3];
-                        const double u3 = __shfl_up_sync(0xffffffffu, F3, 4);       // element (x, y - 1), corner (1, 1)
-                        const double u2 = __shfl_up_sync(0xffffffffu, F2, 4);       // element (x, y - 1), corner (0, 1)
-                        const double a = ylo ? F1 + u3 : F1;                        // node (x + 1, y), this column pair
-                        const double ua = __shfl_up_sync(0xffffffffu, a, 1);        // node (x, y) from the x - 1 pair
-                        const double u3x = __shfl_up_sync(0xffffffffu, F3, 1);      // element (x - 1, y), corner (1, 1)
-                        double own = ylo ? F0 + u2 : F0;
-                        if (xlo) own += ua;
-                        acc[ol + c * SP_C] += own;
-                        if (xhi) {
-                            if (x == 3) accx[lx + c * SX4_C] += a; else acc[ol + 1 + c * SP_C] += a;
-                        }
-                        if (yhi) acc[ol + SP_ROW + c * SP_C] += xlo ? F2 + u3x : F2;
-                        if (xhi && yhi) {
-                            if (x == 3) accx[lx + 1 + c * SX4_C] += F3; else acc[ol + SP_ROW + 1 + c * SP_C] += F3;
-                        }
-                    }
+                for (int j = 0; j < 8; j++) {
+                    F[(3 * j) * 512 + tid] = fx[j]; F[(3 * j + 1) * 512 + tid] = fy[j]; F[(3 * j + 2) * 512 + tid] = fz[j];
                 }
             }
-            // what the next tile needs in registers, requested now that this tile's forces have left them
+            // what the next tile needs in registers
             if (has_nn) load_halo_ids(A, meta_group(m_nn, 0), tid, nthr, hid);
             if (has_next) {
-                const int n0n = meta_group(m_nxt, 0).x;
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const double *nt = A.nt3 + 3 * (size_t)(n0n + tid + 256 * q);
-                    spre[q][0] = ldg_f64_pinned(nt); spre[q][1] = ldg_f64_pinned(nt + 1); spre[q][2] = ldg_f64_pinned(nt + 2);
-                }
+                const double *nt = A.nt3 + 3 * (size_t)(meta_group(m_nxt, 0).x + tid);
+                spre[0] = ldg_f64_pinned(nt); spre[1] = ldg_f64_pinned(nt + 1); spre[2] = ldg_f64_pinned(nt + 2);
                 const double *tc = A.tile_coef + 4 * (size_t)tn;
                 cpre[0] = ldg_f64_pinned(tc); cpre[1] = ldg_f64_pinned(tc + 1); cpre[2] = ldg_f64_pinned(tc + 2);
                 pre_ok = true;
             }
-            __syncthreads();
-            // ---- publish the three far faces (slots 512 + h = partial force h of this tile) ----
-            if (tid < 217) {
-                double *dst = A.partial + 3 * ((size_t)meta_group(m_cur, 0).z + tid);
-                const int sp = sp_of_slot(512 + tid);
-                const bool x4 = sp % SP_ROW == 4;
-                const int ox = (sp / SP_Z) * 9 + (sp / SP_ROW) % 9;
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    double v = acc[sp + c * SP_C];
-                    if (x4) v += accx[ox + c * SX4_C];
-                    __stcg(dst + c, v); acc[sp + c * SP_C] = 0.0;
-                }
+            if (prv_pending) wait_deps(A, meta_group(m_prv, 3), fb_prv, tid, nthr, flag_value);
+            __syncthreads();                    // every element's forces are in F; W is free
+            if (prv_pending) {
+                request_partials(A, meta_group(m_prv, 0).x, meta_group(m_prv, 2), fb_prv, fb, tid, nthr);
+                cp_async_commit();
             }
-            // ---- this tile's own share of the update: scale by 1/mass (REGULAR nodes), hand it on ----
+            // ---- node phase: every node sums the forces of its (up to) eight elements, in a fixed order ----
+            {
+                double T0 = 0.0, T1 = 0.0, T2 = 0.0;
 #pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const int sl = tid + 256 * q, sp = sp_of_slot(sl);
-                const double rm = srm_own[sl];
-                double *o = A.unext + 3 * (size_t)(n0 + sl);
-                const bool x4 = sp % SP_ROW == 4;
-                const int ox = (sp / SP_Z) * 9 + (sp / SP_ROW) % 9;
+                for (int j = 0; j < 8; j++) {
+                    const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+                    if (x >= dx && y >= dy && z >= dz) {
+                        const int ex = x - dx;
+                        const int te = (ex & 3) | ((ex & 4) << 3) | ((y - dy) << 2) | ((z - dz) << 6);
+                        T0 += F[(3 * j) * 512 + te]; T1 += F[(3 * j + 1) * 512 + te]; T2 += F[(3 * j + 2) * 512 + te];
+                    }
+                }
+                const int k = 3 * ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | ((x & 2) << 2) | ((y & 2) << 3) | ((z & 2) << 4) |
+                                   ((x & 4) << 4) | ((y & 4) << 5) | ((z & 4) << 6));          // Morton slot of node (x, y, z)
+                W[k] = T0; W[k + 1] = T1; W[k + 2] = T2;
+            }
+            if (tid < 217) {                    // far-face node tid (hgpu_internal.h): published as partial force tid
+                int X, Y, Z;
+                if (tid < 81)       { Z = 8; Y = tid / 9; X = tid - 9 * Y; }
+                else if (tid < 153) { const int q = tid - 81; Y = 8; Z = q / 9; X = q - 9 * Z; }
+                else                { const int q = tid - 153; X = 8; Z = q >> 3; Y = q & 7; }
+                double T0 = 0.0, T1 = 0.0, T2 = 0.0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int ex = X - (j & 1), ey = Y - ((j >> 1) & 1), ez = Z - (j >> 2);
+                    if (ex >= 0 && ex < 8 && ey >= 0 && ey < 8 && ez >= 0 && ez < 8) {
+                        const int te = (ex & 3) | ((ex & 4) << 3) | (ey << 2) | (ez << 6);
+                        T0 += F[(3 * j) * 512 + te]; T1 += F[(3 * j + 1) * 512 + te]; T2 += F[(3 * j + 2) * 512 + te];
+                    }
+                }
+                double *dst = A.partial + 3 * ((size_t)meta_group(m_cur, 0).z + tid);
+                __stcg(dst, T0); __stcg(dst + 1, T1); __stcg(dst + 2, T2);
+            }
+            if (has_next && tid == 0) stile[(it + 4) & (META_RING - 1)] = popped;
+            cp_async_wait_all();
+            __syncthreads();                    // the owned nodes' forces are in W, in slot order
+            // ---- settle slot tid: central difference of a REGULAR node, the plain force otherwise; hand it on ----
+            {
+                const int k = 3 * tid;
+                double *o = A.unext + 3 * (size_t)(n0 + tid);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
-                    double v = acc[sp + c * SP_C];
-                    if (x4) v += accx[ox + c * SX4_C];
-                    if (rm > 0.0) v *= rm;
-                    acc[sp + c * SP_C] = v;         // record nodes take it from here (pend)
+                    double v = W[k + c];
+                    if (snt[0] > 0.0) v = (v + (snt[1] * su1[k + c] - snt[2] * su2[k + c])) * snt[0];
+                    W[k + c] = v;               // record nodes take it from here (pend)
                     o[c] = v;
                 }
             }
@@ -1248,8 +1197,8 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
             }
         }
         }
-        if (has_next && tid == 0) stile[(it + 4) & (META_RING - 1)] = popped;
-        cp_async_wait_all();                    // partial forces of the previous tile, this tile's finish data
+        if (!(STRUCT && st) && has_next && tid == 0) stile[(it + 4) & (META_RING - 1)] = popped;
+        if (!(STRUCT && st)) cp_async_wait_all();   // partial forces of the previous tile, this tile's finish data
         __syncthreads();                        // ... and every thread's published partial forces are written
         // (the flag is raised at the top of the next iteration: by then the stores have long been
         // acknowledged and the fence in front of the flag costs thread 0 next to nothing)
@@ -1265,12 +1214,8 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
                 if (tid < nrec_prv) { own_prv[0] = fb.pend[3 * tid]; own_prv[1] = fb.pend[3 * tid + 1]; own_prv[2] = fb.pend[3 * tid + 2]; }
                 if (tid < nrec) {
                     const int slot3 = reinterpret_cast<const uint2 *>(fb_cur)[tid].x & 0xffff;
-                    if (STRUCT && st) {
-                        const int sp = sp_of_slot(slot3 / 3);
-                        fb.pend[3 * tid] = acc[sp]; fb.pend[3 * tid + 1] = acc[sp + SP_C]; fb.pend[3 * tid + 2] = acc[sp + 2 * SP_C];
-                    } else {
-                        fb.pend[3 * tid] = acc[slot3]; fb.pend[3 * tid + 1] = acc[slot3 + 1]; fb.pend[3 * tid + 2] = acc[slot3 + 2];
-                    }
+                    // (STRUCT: acc = the planes' region, which holds the settled owned nodes in slot order here)
+                    fb.pend[3 * tid] = acc[slot3]; fb.pend[3 * tid + 1] = acc[slot3 + 1]; fb.pend[3 * tid + 2] = acc[slot3 + 2];
                 }
             }
         }
@@ -1280,12 +1225,7 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
         {
             const size_t g0 = 3 * (size_t)n0;
             if (STRUCT && st) {
-                // handed on already; leave the accumulator clean for the next tile
-#pragma unroll
-                for (int q = 0; q < 2; q++) {
-                    const int sp = sp_of_slot(tid + 256 * q);
-                    acc[sp] = 0.0; acc[sp + SP_C] = 0.0; acc[sp + 2 * SP_C] = 0.0;
-                }
+                // handed on when it was settled; nothing accumulates in shared memory on this path
             } else if (fuse) {
                 double2 *dst = reinterpret_cast<double2 *>(A.unext + g0);         // g0 is even
                 for (int k = tid; k < (nown3 >> 1); k += nthr) {
@@ -1329,7 +1269,7 @@ __device__ __forceinline__ void tile_loop(const StepArgs &A, const int t0, const
 // each walks ITS tiles in ascending order, so the lowest tile whose flag is not raised yet never waits:
 // the argument that makes the single loop deadlock-free holds for any such split.
 template <int MODE, bool DENSE, int THREADS, bool WPASS = false, bool STRUCT = false>
-__global__ void __launch_bounds__(THREADS, 2) step_kernel(const StepArgs A)
+__global__ void __launch_bounds__(THREADS, THREADS >= 512 ? 1 : 2) step_kernel(const StepArgs A)
 {
     if (STRUCT) {
         const int gs = A.grid_struct;

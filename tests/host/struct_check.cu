@@ -7,8 +7,7 @@
 //   1. the padded layout: 729 slots map to 729 different offsets inside a plane of SP_C doubles;
 //   2. bank conflicts: every gather / accumulator access of a warp is conflict-free (16 lanes of a
 //      half-warp hit 16 different 8-byte banks);
-//   3. races: inside one ROUND (the code between two barriers) every accumulator address is updated by
-//      exactly one thread of the CTA (the shares of neighbouring elements are combined with shuffles first);
+//   3. no read-modify-write at all: every element force is stored once, every node sum is formed by one thread;
 //   4. numerics: the accumulated forces equal those of 512 single-element evaluations
 //      (wht_forward, scale_modes, wht_inverse, scatter) to rounding.
 #include <cmath>
@@ -62,7 +61,7 @@ int main()
             CHECK(sp_of_slot(struct_slot(x, y, z)) == z * SP_Z + y * SP_ROW + x, "slot of (%d,%d,%d)", x, y, z);
     }
     // ---- random w on the 729 nodes, padded planes -------------------------------------------------
-    std::vector<double> W(SP_TOTAL, 0.0), acc(SP_TOTAL, 0.0), accx(SX4_TOTAL, 0.0), ref(3 * STRUCT_NODES, 0.0);
+    std::vector<double> W(SP_TOTAL, 0.0), acc(SP_TOTAL, 0.0), ref(3 * STRUCT_NODES, 0.0);
     srand(12345);
     auto rnd = []() { return (double)rand() / RAND_MAX - 0.5; };
     std::vector<double> wnode(3 * STRUCT_NODES);
@@ -84,71 +83,85 @@ int main()
             for (int c = 0; c < 3; c++) ref[3 * (((z + (j >> 2)) * 9 + y + ((j >> 1) & 1)) * 9 + x + (j & 1)) + c] += f[c][j];
     }
 
-    // ---- the kernel's schedule, 256 threads: two rounds (element z = 2 zq, then 2 zq + 1), each with a
-    //      dx = 0 pass and a dx = 1 pass (barrier between them), each pass with a dy = 0 and a dy = 1 half
-    //      (__syncwarp between them), each half touching the element's lower and upper level ------------
-    struct Regs { double f[3][8]; int o; };
-    std::vector<Regs> R(256);
+    // ---- the kernel's schedule, 512 threads: thread = element (x, y, z) stores its 24 corner forces in
+    //      F[(3 j + c) * 512 + thread]; after a barrier thread = node (x, y, z) (and far-face node tid < 217) sums
+    //      the forces of its up to eight elements in a fixed order ------------------------------------------
+    std::vector<double> F(SF_TOTAL, 0.0), own(3 * 512, 0.0), pub(3 * 217, 0.0);
     std::vector<Access> g;
-    for (int r = 0; r < 2; r++) {
-        for (int lvl = 0; lvl < 2; lvl++) for (int k = 0; k < 4; k++) {       // one gather instruction = (level, face corner)
+    for (int lvl = 0; lvl < 2; lvl++) for (int k = 0; k < 4; k++) {           // one gather instruction = (level, face corner)
+        for (int w = 0; w < 16; w++) {
             g.clear();
-            for (int tid = 0; tid < 256; tid++) {
-                const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-                const int o = (2 * zq + r) * SP_Z + y * SP_ROW + x;
-                g.push_back({tid, o + lvl * SP_Z + (k & 1) + SP_ROW * (k >> 1)});
+            for (int l = 0; l < 32; l++) {
+                const int tid = 32 * w + l, x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, z = tid >> 6;
+                g.push_back({l, z * SP_Z + y * SP_ROW + x + lvl * SP_Z + (k & 1) + SP_ROW * (k >> 1)});
             }
             check_banks(g, "gather");
         }
-        for (int tid = 0; tid < 256; tid++) {
-            const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-            Regs &q = R[tid];
-            q.o = (2 * zq + r) * SP_Z + y * SP_ROW + x;
-            double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8];
-            gather_face(W.data(), q.o, wx[0], wx[1], wx[2], wx[3]);
-            gather_face(W.data() + SP_C, q.o, wy[0], wy[1], wy[2], wy[3]);
-            gather_face(W.data() + 2 * SP_C, q.o, wz[0], wz[1], wz[2], wz[3]);
-            gather_face(W.data(), q.o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
-            gather_face(W.data() + SP_C, q.o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
-            gather_face(W.data() + 2 * SP_C, q.o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
-            wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
-            scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);
-            wht_inverse(wx, q.f[0]); wht_inverse(wy, q.f[1]); wht_inverse(wz, q.f[2]);
-        }
-        // one ROUND = the code between two barriers.  The accumulator update is shuffle-combined: per level and
-        // component the lanes exchange shares with __shfl_up (by 4 = y - 1, by 1 = x - 1) and every address is
-        // updated by exactly ONE thread of the CTA in the round -- checked here over all 256 threads.
-        std::map<long, int> owner;                          // address -> thread that updated it in this round
-        auto upd = [&](int tid, bool side, int o, int c, double v, std::vector<Access> *rec) {
-            const long key = (side ? 1000000L : 0L) + o + (side ? c * SX4_C : c * SP_C);
-            CHECK(owner.insert({key, tid}).second, "round %d: threads %d and %d update the same accumulator", r, owner[key], tid);
-            if (side) accx[o + c * SX4_C] += v; else { acc[o + c * SP_C] += v; if (rec) rec->push_back({tid, o}); }
-        };
-        for (int w = 0; w < 8; w++) for (int dz = 0; dz < 2; dz++) for (int c = 0; c < 3; c++) {
-            double F0[32], F1[32], F2[32], F3[32], u3[32], u2[32], a[32], ua[32], u3x[32];
-            for (int l = 0; l < 32; l++) { const Regs &q = R[32 * w + l]; F0[l] = q.f[c][4 * dz]; F1[l] = q.f[c][4 * dz + 1]; F2[l] = q.f[c][4 * dz + 2]; F3[l] = q.f[c][4 * dz + 3]; }
-            for (int l = 0; l < 32; l++) { u3[l] = l >= 4 ? F3[l - 4] : F3[l]; u2[l] = l >= 4 ? F2[l - 4] : F2[l]; u3x[l] = l >= 1 ? F3[l - 1] : F3[l]; }
-            for (int l = 0; l < 32; l++) a[l] = ((l >> 2) & 7) != 0 ? F1[l] + u3[l] : F1[l];
-            for (int l = 0; l < 32; l++) ua[l] = l >= 1 ? a[l - 1] : a[l];
-            std::vector<Access> a_own, a_x, a_y;
-            for (int l = 0; l < 32; l++) {
-                const int tid = 32 * w + l;
-                const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, zq = tid >> 6;
-                const bool xlo = (tid & 3) != 0, xhi = (tid & 3) == 3, ylo = y != 0, yhi = y == 7;
-                const int ol = R[tid].o + dz * SP_Z, lx = (2 * zq + r + dz) * 9 + y;
-                double own = ylo ? F0[l] + u2[l] : F0[l];
-                if (xlo) own += ua[l];
-                upd(tid, false, ol, c, own, &a_own);
-                if (xhi) { if (x == 3) upd(tid, true, lx, c, a[l], nullptr); else upd(tid, false, ol + 1, c, a[l], &a_x); }
-                if (yhi) upd(tid, false, ol + SP_ROW, c, xlo ? F2[l] + u3x[l] : F2[l], &a_y);
-                if (xhi && yhi) { if (x == 3) upd(tid, true, lx + 1, c, F3[l], nullptr); else upd(tid, false, ol + SP_ROW + 1, c, F3[l], nullptr); }
-            }
-            check_banks_rebased(a_own, 32 * w, "own update"); check_banks_rebased(a_x, 32 * w, "+x edge update"); check_banks_rebased(a_y, 32 * w, "+y edge update");
-        }
     }
-    // drain: the side array belongs to the x = 4 column
-    for (int z = 0; z < 9; z++) for (int y = 0; y < 9; y++) for (int c = 0; c < 3; c++)
-        acc[c * SP_C + z * SP_Z + y * SP_ROW + 4] += accx[c * SX4_C + z * 9 + y];
+    for (int tid = 0; tid < 512; tid++) {
+        const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, z = tid >> 6;
+        const int o = z * SP_Z + y * SP_ROW + x;
+        double wx[8], wy[8], wz[8], tx[8], ty[8], tz[8], f[3][8];
+        gather_face(W.data(), o, wx[0], wx[1], wx[2], wx[3]);
+        gather_face(W.data() + SP_C, o, wy[0], wy[1], wy[2], wy[3]);
+        gather_face(W.data() + 2 * SP_C, o, wz[0], wz[1], wz[2], wz[3]);
+        gather_face(W.data(), o + SP_Z, wx[4], wx[5], wx[6], wx[7]);
+        gather_face(W.data() + SP_C, o + SP_Z, wy[4], wy[5], wy[6], wy[7]);
+        gather_face(W.data() + 2 * SP_C, o + SP_Z, wz[4], wz[5], wz[6], wz[7]);
+        wht_forward(wx, tx); wht_forward(wy, ty); wht_forward(wz, tz);
+        scale_modes(tx, ty, tz, ca, cc, cb, wx, wy, wz);
+        wht_inverse(wx, f[0]); wht_inverse(wy, f[1]); wht_inverse(wz, f[2]);
+        for (int j = 0; j < 8; j++) for (int c = 0; c < 3; c++) F[(3 * j + c) * 512 + tid] = f[c][j];
+    }
+    // node phase (barrier before): owned node (x, y, z) of thread tid -> Morton slot; far-face node tid -> partial force tid
+    for (int j = 0; j < 8; j++) for (int w = 0; w < 16; w++) {                // bank check of the F gather, instruction by instruction
+        g.clear();
+        for (int l = 0; l < 32; l++) {
+            const int tid = 32 * w + l, x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, z = tid >> 6;
+            const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+            if (x >= dx && y >= dy && z >= dz) {
+                const int ex = x - dx;
+                g.push_back({l, (ex & 3) | ((ex & 4) << 3) | ((y - dy) << 2) | ((z - dz) << 6)});
+            }
+        }
+        check_banks(g, "node gather");
+    }
+    for (int tid = 0; tid < 512; tid++) {
+        const int x = (tid & 3) | ((tid >> 3) & 4), y = (tid >> 2) & 7, z = tid >> 6;
+        double T[3] = {0, 0, 0};
+        for (int j = 0; j < 8; j++) {
+            const int dx = j & 1, dy = (j >> 1) & 1, dz = j >> 2;
+            if (x >= dx && y >= dy && z >= dz) {
+                const int ex = x - dx, te = (ex & 3) | ((ex & 4) << 3) | ((y - dy) << 2) | ((z - dz) << 6);
+                for (int c = 0; c < 3; c++) T[c] += F[(3 * j + c) * 512 + te];
+            }
+        }
+        const int k = 3 * ((x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | ((x & 2) << 2) | ((y & 2) << 3) | ((z & 2) << 4) |
+                           ((x & 4) << 4) | ((y & 4) << 5) | ((z & 4) << 6));
+        CHECK(k == 3 * struct_morton3(x, y, z), "Morton slot of node (%d,%d,%d)", x, y, z);
+        for (int c = 0; c < 3; c++) own[k + c] = T[c];
+    }
+    for (int tid = 0; tid < 217; tid++) {
+        int X, Y, Z;
+        if (tid < 81)       { Z = 8; Y = tid / 9; X = tid - 9 * Y; }
+        else if (tid < 153) { const int q = tid - 81; Y = 8; Z = q / 9; X = q - 9 * Z; }
+        else                { const int q = tid - 153; X = 8; Z = q >> 3; Y = q & 7; }
+        CHECK(struct_slot(X, Y, Z) == 512 + tid, "far-face node %d decodes to (%d,%d,%d)", tid, X, Y, Z);
+        double T[3] = {0, 0, 0};
+        for (int j = 0; j < 8; j++) {
+            const int ex = X - (j & 1), ey = Y - ((j >> 1) & 1), ez = Z - (j >> 2);
+            if (ex >= 0 && ex < 8 && ey >= 0 && ey < 8 && ez >= 0 && ez < 8) {
+                const int te = (ex & 3) | ((ex & 4) << 3) | (ey << 2) | (ez << 6);
+                for (int c = 0; c < 3; c++) T[c] += F[(3 * j + c) * 512 + te];
+            }
+        }
+        for (int c = 0; c < 3; c++) pub[3 * tid + c] = T[c];
+    }
+    // back into the padded planes for the comparison below
+    for (int z = 0; z < 9; z++) for (int y = 0; y < 9; y++) for (int x = 0; x < 9; x++) for (int c = 0; c < 3; c++) {
+        const int sl = struct_slot(x, y, z);
+        acc[c * SP_C + z * SP_Z + y * SP_ROW + x] = sl < 512 ? own[3 * sl + c] : pub[3 * (sl - 512) + c];
+    }
 
     // ---- 4. numerics ---------------------------------------------------------------------------------
     double worst = 0.0, scale = 0.0;
