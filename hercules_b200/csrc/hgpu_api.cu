@@ -729,8 +729,6 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             TRYCU(cudaFuncSetAttribute(step_kernel<2, true, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap));  \
             TRYCU(cudaFuncSetAttribute(step_kernel<3, false, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
             if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_cap)); \
-            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<0, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
-            if (T == 256) TRYCU(cudaFuncSetAttribute(step_kernel<1, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem)); \
             TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, step_kernel<1, false, T>, T, s->smem_u2));            \
         } while (0)
         if (s->block == 384) SETUP(384); else SETUP(256);
@@ -742,9 +740,19 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
         }
         if (s->block != 256) s->n_struct = 0;     // STRUCT launches replace the 256-thread ones only
         if (s->n_struct > 0) {
+            // STRUCT launches: one CTA per SM with (almost) the whole shared memory; the opt-in limit counts the
+            // kernel's static shared memory too.  Any failure here only switches the structured path off.
             int occ_s = 0;
-            TRYCU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, false, 512, false, true>, 512, s->smem_struct));
-            if (occ_s < 1) s->n_struct = 0;
+            cudaFuncAttributes fa0, fa1;
+            bool ok = cudaFuncGetAttributes(&fa0, step_kernel<0, false, 512, false, true>) == cudaSuccess &&
+                      cudaFuncGetAttributes(&fa1, step_kernel<1, false, 512, false, true>) == cudaSuccess;
+            const int dyn_max = ok ? max_smem - (int)std::max(fa0.sharedSizeBytes, fa1.sharedSizeBytes) : 0;
+            ok = ok && s->smem_struct <= dyn_max &&
+                 cudaFuncSetAttribute(step_kernel<0, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
+                 cudaFuncSetAttribute(step_kernel<1, false, 512, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_max) == cudaSuccess &&
+                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, false, 512, false, true>, 512, s->smem_struct) == cudaSuccess &&
+                 occ_s >= 1;
+            if (!ok) { cudaGetLastError(); s->n_struct = 0; }
             s->grid_struct_max = nsm * std::max(occ_s, 1);
         }
         if (occ < 1) { hgpu_finalize(s); return fail(HGPU_EINVAL, "step kernel does not fit on an SM"); }
