@@ -572,10 +572,10 @@ extern "C" int hgpu_init(hgpu_solver_t **out, const hgpu_mesh_t *mesh, const hgp
             for (int32_t t = 0; t < pl.ntiles; t++) if (pl.tile_self[t]) order.push_back(t);
             s->n_early = s->n_self = (int32_t)order.size();
             for (int32_t t = 0; t < pl.ntiles; t++) if (!pl.tile_self[t]) order.push_back(t);
-            // HGPU_ORDER=level: the rest by dependency LEVEL (0 = reads nobody's partial forces, else 1 + the
-            // highest level among the tiles it reads), ascending ids inside a level -- still a topological order
-            // of the dependencies, but the tiles that run at the same time no longer wait for one another
-            // (in Z-order a tile's lower neighbours are its immediate predecessors, i.e. run concurrently with it)
+            // HGPU_ORDER=level (experiment, measured SLOWER: profiles/README.md): the rest by dependency LEVEL
+            // (0 = reads nobody's partial forces, else 1 + the highest level among the tiles it reads), ascending
+            // ids inside a level -- still a topological order of the dependencies; Z-order keeps the halos and the
+            // partial forces of neighbouring tiles in L2, which is worth more than the waiting it causes
             {
                 const char *oenv = getenv("HGPU_ORDER");
                 if (oenv && strcmp(oenv, "level") == 0) {

@@ -617,20 +617,22 @@ __device__ __forceinline__ void bkt_family(double *conv, size_t entry, int fam, 
 
 
 // ------------------------------------------------------------------------------------------
-// STRUCTURED tiles (hgpu_internal.h): one aligned 8x8x8 cell of equal elements of one material.
-// No slot table is needed: thread (x, y, zq) evaluates the two elements (x, y, 2 zq) and
-// (x, y, 2 zq + 1) of the cell, one after the other, from a copy of the damped displacement
-// w = u1 + beta (u1 - u2) that is formed ONCE PER NODE (729 nodes) right after the tile has landed,
-// in a padded structure-of-arrays layout [component][z][y][x] with row stride 12 and plane stride
-// 108: lanes = (x & 3, y), so the 16 lanes of a half-warp (4 x values, 4 consecutive rows) always hit
-// 16 different 8-byte banks (12 y mod 16 = 0, 12, 8, 4) -- gathers and accumulator updates are
-// conflict-free, and an element costs 24 gathers instead of 48.
-// Accumulator updates are ordered by dx: within a warp by __syncwarp (the y neighbours are lanes of the
-// same warp), between warps by two barriers per round = four per tile where the slot-table path needs
-// sixteen (warps = (x >> 2, zq): in one round the warps touch disjoint level pairs, so only the x = 4
-// column is shared between warps, and only between the dx = 0 and dx = 1 passes).
-// (A variant that summed the two elements' shares of their common level in registers before the last
-// butterfly stages -- 36 gathers and 36 updates per pair -- was correct but spilled: r02 call 2.)
+// STRUCTURED tiles (hgpu_internal.h): one aligned 8x8x8 cell of equal elements of one material, walked by
+// tile_loop<..., KIND = 1> with 512 threads and one CTA per SM.  No slot table is needed:
+//   pre-pass       the damped displacement w = u1 + beta (u1 - u2) is formed ONCE PER NODE (729 nodes) right
+//                  after the tile has landed, into three padded planes [component][z][y][x] with row stride 12
+//                  and plane stride 108: lanes = (x & 3, y), so the 16 lanes of a half-warp (4 x values, 4
+//                  consecutive rows) always hit 16 different 8-byte banks (12 y mod 16 = 0, 12, 8, 4)
+//   element phase  thread = element (x, y, z): 24 conflict-free gathers, the factored operator with the tile's
+//                  coefficients, 24 plain stores F[(3 j + c) * 512 + thread]  (j = corner, c = component)
+//   node phase     thread = node (x, y, z) (and far-face node tid < 217): the forces of its (up to) eight
+//                  elements are summed in registers in a fixed order -- no read-modify-write, no accumulator --
+//                  far-face nodes are published as partial forces, owned ones go to a slot-order pass that adds
+//                  the inertia term, scales by 1/mass and stores u(t+dt) as coalesced 24-byte rows
+// Variants that ran before this one (z pairs with register carry, four ordered accumulator passes, a side
+// array for the x = 4 column, shuffle-combined updates, tiles from shared counters, dependency-level order)
+// are recorded with their measurements in profiles/README.md; none of them, nor this one, beats the
+// slot-table path on the bench, so the path is opt-in.
 // ------------------------------------------------------------------------------------------
 constexpr int SP_ROW = 12, SP_Z = 108, SP_C = 972, SP_TOTAL = 3 * SP_C;     // doubles
 constexpr int SF_TOTAL = 24 * 512;                                          // element forces of one structured tile
@@ -659,21 +661,6 @@ HGPU_HD void gather_face(const double *plane, int o, double &w0, double &w1, dou
     w0 = plane[o]; w1 = plane[o + 1]; w2 = plane[o + SP_ROW]; w3 = plane[o + SP_ROW + 1];
 }
 
-// accumulator update of one (dx, dy) node of one level: f = per component value
-HGPU_HD void acc_add3(double *acc, int o, double fx, double fy, double fz)
-{
-    acc[o] += fx; acc[o + SP_C] += fy; acc[o + 2 * SP_C] += fz;
-}
-// the same with the component stride given (the x = 4 side array, see SX4_*)
-HGPU_HD void acc_add3s(double *a, int o, int sc, double fx, double fy, double fz)
-{
-    a[o] += fx; a[o + sc] += fy; a[o + 2 * sc] += fz;
-}
-// What the x < 4 warps add to the nodes of the x = 4 column (their dx = 1 corners at x = 3) goes to a side
-// array [component][z][y] of 3 x 81 doubles instead of the accumulator, where the x >= 4 warps add their
-// dx = 0 corners to the same nodes: with that, no two warps touch one address inside a round, and the
-// dx = 0 and dx = 1 passes need no barrier between them.  The side array is added when the tile is drained.
-constexpr int SX4_C = 81, SX4_TOTAL = 243;
 
 // WPASS (MODE 1, fused update; opt-in, HGPU_FLAG_WPASS): on a tile whose entries share one beta, the
 // damped displacement w = u1 + beta (u1 - u2) is formed ONCE PER STAGED NODE right after the tile has

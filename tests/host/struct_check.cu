@@ -1,7 +1,7 @@
 // struct_check.cu -- HOST emulation of the structured-tile path of step_kernel (hgpu_kernels.cuh),
 // compiled by nvcc for the CPU and run by tests/test_struct_host.py (no GPU needed).
 //
-// It uses the kernel's own helpers (sp_of_slot, gather_face, acc_add3, wht_forward, scale_modes,
+// It uses the kernel's own helpers (sp_of_slot, gather_face, wht_forward, scale_modes,
 // wht_inverse) and mirrors the kernel's thread mapping and pass order (two rounds of a dx = 0 and a dx = 1
 // pass, a __syncwarp between the dy = 0 and dy = 1 halves of a pass) to check, for one aligned 8x8x8 cell:
 //   1. the padded layout: 729 slots map to 729 different offsets inside a plane of SP_C doubles;

@@ -432,8 +432,8 @@ def test_basin_workload_matches_oracle(hb, oracle):
 
 @pytest.mark.parametrize("damping", ["rayleigh", "none"])
 def test_structured_tiles_match_oracle(hb, oracle, damping):
-    """The structured-tile path of the step kernel (aligned 8x8x8 cells of one material evaluated as z
-    pairs from a per-node damped displacement, hgpu_kernels.cuh): a 32 x 32 x 24 two-layer mesh whose
+    """The structured-tile path of the step kernel (opt-in; aligned 8x8x8 cells of one material evaluated
+    without a slot table from a per-node damped displacement): a 32 x 32 x 24 two-layer mesh whose
     interface is cell-aligned -- 18 of its 48 cells take the path, the far-face cells and (second case)
     the cells that straddle an unaligned interface take the generic one -- stepped with a source against
     the oracle (compute_addforce_effective + damping_addforce + solver_compute_displacement,
