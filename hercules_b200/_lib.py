@@ -84,6 +84,9 @@ SYMBOLS = {
     "hgpu_stations_record": (C.c_int, [_H, i32]),
     "hgpu_stations_pending": (C.c_int, [_H]),
     "hgpu_stations_drain": (C.c_int, [_H, C.c_void_p, C.c_void_p, i32, C.POINTER(i32)]),
+    "hgpu_planes_attach": (C.c_int, [_H, i64, C.c_void_p, C.c_void_p]),
+    "hgpu_planes_record": (C.c_int, [_H, C.c_void_p]),
+    "hgpu_planes_wait": (C.c_int, [_H]),
     "hgpu_host_alloc": (C.c_void_p, [C.c_size_t]),
     "hgpu_host_free": (None, [C.c_void_p]),
     "hgpu_sync": (C.c_int, [_H]),

@@ -211,6 +211,12 @@ struct hgpu_solver {
     int32_t st_n = 0, st_vel = 0, st_acc = 0, st_rate = 0, st_cap = 0, st_count = 0;
     int32_t *d_st_nodes = nullptr; double *d_st_local = nullptr, *d_st_rows = nullptr;
     std::vector<int32_t> st_steps;           // step of each recorded row
+    // planes interpolated on the device (hgpu_planes_*): two row buffers [npoints][3], read out on the copy stream
+    struct PlaneSlot { double *rows = nullptr; cudaEvent_t ready = nullptr, done = nullptr; bool busy = false; };
+    int64_t pl_n = 0;
+    int32_t *d_pl_nodes = nullptr; double *d_pl_local = nullptr;
+    PlaneSlot pl[2];
+    int pl_next = 0;
 };
 
 template <typename T>
@@ -815,8 +821,14 @@ extern "C" int hgpu_finalize(hgpu_solver_t *s)
         if (f.ready) cudaEventDestroy(f.ready);
         if (f.done) cudaEventDestroy(f.done);
     }
-    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->copy_stream) { cudaStreamSynchronize(s->copy_stream); cudaStreamDestroy(s->copy_stream); }
     dfree(s->d_st_nodes); dfree(s->d_st_local); dfree(s->d_st_rows);
+    dfree(s->d_pl_nodes); dfree(s->d_pl_local);
+    for (auto &q : s->pl) {
+        dfree(q.rows);
+        if (q.ready) cudaEventDestroy(q.ready);
+        if (q.done) cudaEventDestroy(q.done);
+    }
     free_msglist(s->dn_c); free_msglist(s->dn_s); free_msglist(s->an_c); free_msglist(s->an_s);
     for (int i = 0; i < hgpu_solver::SRC_RING; i++) if (s->src_done[i]) cudaEventDestroy(s->src_done[i]);
     for (EvPair &e : s->evpool) { if (e.a) cudaEventDestroy(e.a); if (e.b) cudaEventDestroy(e.b); }
@@ -1556,6 +1568,64 @@ extern "C" int hgpu_stations_drain(hgpu_solver_t *s, double *rows, int32_t *step
     if (steps) memcpy(steps, s->st_steps.data(), (size_t)s->st_count * sizeof(int32_t));
     *nrows = s->st_count;
     s->st_count = 0; s->st_steps.clear();
+    return check_device_error(s);
+}
+
+// ---- planes on the device -----------------------------------------------------------
+
+extern "C" int hgpu_planes_attach(hgpu_solver_t *s, int64_t npoints, const int32_t *nodes, const double *localcoords)
+{
+    if (!s || npoints < 0 || (npoints > 0 && (!nodes || !localcoords)))
+        return fail(HGPU_EINVAL, "hgpu_planes_attach: bad argument");
+    for (int64_t i = 0; i < 8 * npoints; i++)
+        if (nodes[i] < 0 || nodes[i] >= s->N) return fail(HGPU_EINVAL, "hgpu_planes_attach: node id out of range");
+    CK(cudaSetDevice(s->dev));
+    CK(cudaStreamSynchronize(s->stream));
+    if (s->copy_stream) CK(cudaStreamSynchronize(s->copy_stream));
+    dfree(s->d_pl_nodes); dfree(s->d_pl_local);
+    s->d_pl_nodes = nullptr; s->d_pl_local = nullptr;
+    for (auto &q : s->pl) { dfree(q.rows); q.rows = nullptr; q.busy = false; }
+    s->pl_n = npoints; s->pl_next = 0;
+    if (npoints == 0) return HGPU_OK;
+    int rc;
+    if ((rc = upload(s, &s->d_pl_nodes, nodes, 8 * (size_t)npoints))) return rc;
+    if ((rc = upload(s, &s->d_pl_local, localcoords, 3 * (size_t)npoints))) return rc;
+    for (auto &q : s->pl) {
+        if ((rc = dalloc(s, &q.rows, 3 * (size_t)npoints))) return rc;
+        if (!q.ready) { CK(cudaEventCreateWithFlags(&q.ready, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&q.done, cudaEventDisableTiming)); }
+    }
+    if (!s->copy_stream) CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    return HGPU_OK;
+}
+
+// One plane step: interpolate in stream order (the rows are those of tm1 as of this point of the step
+// sequence), read them out on the copy stream.  Two steps can be in flight; a third waits for the older.
+extern "C" int hgpu_planes_record(hgpu_solver_t *s, double *out)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    if (s->pl_n == 0) return HGPU_OK;
+    if (!out) return fail(HGPU_EINVAL, "hgpu_planes_record: null output buffer");
+    CK(cudaSetDevice(s->dev));
+    hgpu_solver::PlaneSlot &q = s->pl[s->pl_next];
+    s->pl_next ^= 1;
+    if (q.busy) { CK(cudaEventSynchronize(q.done)); q.busy = false; }
+    plane_kernel<<<grid_for(s->pl_n, 128), 128, 0, s->stream>>>((long long)s->pl_n, s->d_pl_nodes, s->d_pl_local,
+                                                                   s->u[s->i1], q.rows);
+    CK(cudaGetLastError());
+    s->tm.launches++;
+    CK(cudaEventRecord(q.ready, s->stream));
+    CK(cudaStreamWaitEvent(s->copy_stream, q.ready, 0));
+    CK(cudaMemcpyAsync(out, q.rows, 3 * (size_t)s->pl_n * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+    CK(cudaEventRecord(q.done, s->copy_stream));
+    q.busy = true;
+    return HGPU_OK;
+}
+
+extern "C" int hgpu_planes_wait(hgpu_solver_t *s)
+{
+    if (!s) return fail(HGPU_EINVAL, "null solver");
+    for (auto &q : s->pl)
+        if (q.busy) { CK(cudaEventSynchronize(q.done)); q.busy = false; }
     return check_device_error(s);
 }
 

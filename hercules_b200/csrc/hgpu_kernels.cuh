@@ -1550,4 +1550,29 @@ __global__ void station_kernel(int nst, const int32_t *__restrict__ nodes, const
     }
 }
 
+// Old_planes_print's interpolation (io_planes.c:168-191) for every plane point of this rank, one thread
+// per point: phi_i = (1 + xi_i lx)(1 + eta_i ly)(1 + zeta_i lz) / 8 evaluated left to right, the three
+// sums over the element's 8 nodes of tm1 in the reference's order, explicitly rounded multiplies and adds
+// (no FMA contraction): a row equals the reference's doubles bit for bit when the field does.
+// row = [npoints][3], the layout of the reference's strip buffers.
+__global__ void plane_kernel(long long npoints, const int32_t *__restrict__ nodes, const double *__restrict__ local,
+                             const double *__restrict__ tm1, double *__restrict__ row)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npoints) return;
+    const double lx = local[3 * p], ly = local[3 * p + 1], lz = local[3 * p + 2];
+    double d[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const double sx = (i & 1) ? 1.0 : -1.0, sy = (i & 2) ? 1.0 : -1.0, sz = (i & 4) ? 1.0 : -1.0;
+        const double phi = __dmul_rn(__dmul_rn(__dadd_rn(1.0, __dmul_rn(sx, lx)), __dadd_rn(1.0, __dmul_rn(sy, ly))),
+                                     __dadd_rn(1.0, __dmul_rn(sz, lz))) * 0.125;      // / 8 is exact
+        const size_t nd = 3 * (size_t)nodes[8 * p + i];
+#pragma unroll
+        for (int c = 0; c < 3; c++) d[c] = __dadd_rn(d[c], __dmul_rn(phi, tm1[nd + c]));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++) row[3 * p + c] = d[c];
+}
+
 }  // namespace hgpu

@@ -298,6 +298,27 @@ class Solver:
         _chk(self._L.hgpu_stations_drain(self._h, out.ctypes.data, steps.ctypes.data, cap, C.byref(n)))
         return steps[:n.value].copy(), out[:n.value]
 
+    # -- planes on the device (Old_planes_print's interpolation, io_planes.c:168-191) ----------------
+    def planes_attach(self, nodes, localcoords) -> None:
+        nodes = np.ascontiguousarray(nodes, np.int32).reshape(-1, 8)
+        loc = np.ascontiguousarray(localcoords, np.float64).reshape(-1, 3)
+        if nodes.shape[0] != loc.shape[0]:
+            raise ValueError("nodes [n][8] and localcoords [n][3] disagree on the point count")
+        self._npl = nodes.shape[0]
+        _chk(self._L.hgpu_planes_attach(self._h, self._npl, nodes.ctypes.data, loc.ctypes.data))
+
+    def planes_record(self, out: np.ndarray | None = None) -> np.ndarray:
+        """Starts the interpolation of every plane point from tm1 and its copy to `out` ([npoints][3]);
+        `out` is valid after planes_wait()."""
+        if out is None:
+            out = np.empty((self._npl, 3), np.float64)
+        assert out.dtype == np.float64 and out.flags.c_contiguous and out.size == 3 * self._npl
+        _chk(self._L.hgpu_planes_record(self._h, out.ctypes.data))
+        return out
+
+    def planes_wait(self) -> None:
+        _chk(self._L.hgpu_planes_wait(self._h))
+
     def sync(self) -> None:
         _chk(self._L.hgpu_sync(self._h))
 

@@ -235,6 +235,24 @@ int hgpu_stations_record(hgpu_solver_t *s, int32_t step);
 int hgpu_stations_pending(hgpu_solver_t *s);
 int hgpu_stations_drain(hgpu_solver_t *s, double *rows, int32_t *steps, int32_t max_rows, int32_t *nrows);
 
+/* ---- planes on the device ----------------------------------------------------
+ * The interpolation of Old_planes_print (io_planes.c:168-191) evaluated by a kernel: a plane step moves 3
+ * doubles per plane point to the host instead of the 8 nodes it is interpolated from, and does not stop the
+ * time loop.  The strip transport to the printing rank and the file format stay the reference's
+ * (io_planes.c:193-250); integration/io_planes_gpu.c shows them on these rows.
+ *
+ * attach: the plane points of this rank in plane / strip / point order: nodes = plane_strip_element_t.
+ *   nodestointerpolate [npoints][8], localcoords = .localcoords [npoints][3] (io_planes.c:83-88).
+ * record: at the point of the step where solver_output_planes runs (psolve.c:4283, after the swap):
+ *   out[point][3] = sum_i phi_i(localcoords) tm1[node_i], the reference's operation order, unfused --
+ *   bit-equal to the reference's doubles for equal fields.  Asynchronous (kernel in stream order, copy on
+ *   the copy stream; `out` page-locked from hgpu_host_alloc for a truly asynchronous copy); two records may
+ *   be in flight, each into its own `out`.
+ * wait: blocks until every recorded step has landed; only waits on events (writer-thread safe). */
+int hgpu_planes_attach(hgpu_solver_t *s, int64_t npoints, const int32_t *nodes, const double *localcoords);
+int hgpu_planes_record(hgpu_solver_t *s, double *out);
+int hgpu_planes_wait(hgpu_solver_t *s);
+
 /* Page-locked host memory for the buffers handed to hgpu_fetch_all / hgpu_store_all / hgpu_fetch_nodes /
  * hgpu_force_source (the calloc'ed tm1/tm2 of solver_init, psolve.c:3317-3325, on the host side):
  * copies to and from it run at full PCIe/C2C speed and without a bounce buffer.  Any host pointer

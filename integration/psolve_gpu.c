@@ -43,6 +43,8 @@ void Timer_Stop(char *name);
 #include "hercules_gpu.h"
 
 int64_t hgpu_planes_node_list(int theNumberOfPlanes, int32_t *out);      /* io_planes_gpu.c */
+int64_t hgpu_planes_point_tables(int theNumberOfPlanes, int32_t *nodes, double *local);
+int hgpu_planes_print_rows(int32_t myID, int theNumberOfPlanes, const double *rows);
 
 #include <pthread.h>
 
@@ -351,7 +353,23 @@ static void gpu_solver_run(void)
      * (PSOLVE_GPU_PLANES_FULL=1 keeps the whole-field copy). */
     int32_t npl = 0, *pl_ids = NULL;
     double *pl_tmp = NULL;
-    if (Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 &&
+    /* PSOLVE_GPU_DEVICE_PLANES=1: the interpolation itself runs on the device (hgpu_planes_*): a plane step moves
+     * 3 doubles per plane point, and the strips travel and are printed as the reference does it
+     * (hgpu_planes_print_rows, io_planes_gpu.c).  Byte-identical files (tests/test_zz_planes_gpu.py). */
+    const int dev_planes = Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 &&
+                           getenv("PSOLVE_GPU_DEVICE_PLANES") && atoi(getenv("PSOLVE_GPU_DEVICE_PLANES"));
+    double *pl_rows = NULL;
+    if (dev_planes) {
+        const int64_t npts = hgpu_planes_point_tables(Param.theNumberOfPlanes, NULL, NULL);
+        int32_t *nd = malloc(sizeof(int32_t) * 8 * (size_t)(npts + 1));
+        double *lc = malloc(sizeof(double) * 3 * (size_t)(npts + 1));
+        hgpu_planes_point_tables(Param.theNumberOfPlanes, nd, lc);
+        GPU(hgpu_planes_attach(theGpu, npts, nd, lc));
+        free(nd); free(lc);
+        pl_rows = hgpu_host_alloc(sizeof(double) * 3 * (size_t)(npts + 1));
+        if (!pl_rows) solver_abort("gpu_solver_run", NULL, "hgpu_host_alloc: %s\n", hgpu_last_error());
+    }
+    if (Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 && !dev_planes &&
         !(getenv("PSOLVE_GPU_PLANES_FULL") && atoi(getenv("PSOLVE_GPU_PLANES_FULL")))) {
         const int64_t nraw = hgpu_planes_node_list(Param.theNumberOfPlanes, NULL);
         int32_t *raw = malloc(sizeof(int32_t) * (size_t)(nraw + 1));
@@ -416,9 +434,11 @@ static void gpu_solver_run(void)
         const int plane = (Param.theNumberOfPlanes != 0) && (step % Param.thePlanePrintRate == 0);
         const int stat = (Param.theNumberOfStations != 0) && (step % Param.theStationsPrintRate == 0);
         const int plane_sparse = plane && pl_ids != NULL;
+        const int plane_dev = plane && dev_planes;
         const int ckpt_sync = ckpt && !async_ckpt;
         if (ckpt && async_ckpt) ckpt_write_async(step, nharboredmax);
-        if (ckpt_sync || wave || (plane && !plane_sparse)) {
+        if (plane_dev) GPU(hgpu_planes_record(theGpu, pl_rows));           /* kernel + copy, no whole field */
+        if (ckpt_sync || wave || (plane && !plane_sparse && !plane_dev)) {
             GPU(hgpu_fetch_all(theGpu, HGPU_TM1, (double *)sv->tm1));
             if (ckpt_sync || wave) GPU(hgpu_fetch_all(theGpu, HGPU_TM2, (double *)sv->tm2));
         } else if (plane_sparse) {
@@ -445,7 +465,14 @@ static void gpu_solver_run(void)
         Param.theCheckPointingRate = saved_ckpt_rate;
         solver_update_status(step, startingStep);
         solver_output_wavefield(step);
-        solver_output_planes(Global.mySolver, Global.myID, step);
+        if (plane_dev) {                                        /* solver_output_planes, psolve.c:3871-3880 */
+            Timer_Start("Print Planes");
+            GPU(hgpu_planes_wait(theGpu));
+            hgpu_planes_print_rows(Global.myID, Param.theNumberOfPlanes, pl_rows);
+            Timer_Stop("Print Planes");
+        } else {
+            solver_output_planes(Global.mySolver, Global.myID, step);
+        }
         if (dev_stations) Param.theNumberOfStations = 0;       /* rows are written by write_station_rows */
         solver_output_stations(step);
         Param.theNumberOfStations = saved_nstations;
@@ -540,7 +567,7 @@ static void gpu_solver_run(void)
     free(st_ids); free(st_tmp); free(st_steps);
     hgpu_host_free(st_rows);
     hgpu_host_free(src_rows);
-    free(pl_ids); hgpu_host_free(pl_tmp);
+    free(pl_ids); hgpu_host_free(pl_tmp); hgpu_host_free(pl_rows);
     hgpu_host_free(theCkpt.tm1); hgpu_host_free(theCkpt.tm2);
     theCkpt.tm1 = theCkpt.tm2 = NULL;
 }
