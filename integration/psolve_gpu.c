@@ -353,12 +353,16 @@ static void gpu_solver_run(void)
      * (PSOLVE_GPU_PLANES_FULL=1 keeps the whole-field copy). */
     int32_t npl = 0, *pl_ids = NULL;
     double *pl_tmp = NULL;
-    /* PSOLVE_GPU_DEVICE_PLANES=1: the interpolation itself runs on the device (hgpu_planes_*): a plane step moves
-     * 3 doubles per plane point, and the strips travel and are printed as the reference does it
-     * (hgpu_planes_print_rows, io_planes_gpu.c).  Byte-identical files (tests/test_zz_planes_gpu.py). */
-    const int dev_planes = Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 &&
-                           getenv("PSOLVE_GPU_DEVICE_PLANES") && atoi(getenv("PSOLVE_GPU_DEVICE_PLANES"));
+    /* Planes on the device (default on one rank; PSOLVE_GPU_DEVICE_PLANES=1/0 forces it on or off): the
+     * interpolation itself runs as a kernel (hgpu_planes_*), a plane step moves 3 doubles per plane point, and
+     * the strips travel and are printed as the reference does it (hgpu_planes_print_rows, io_planes_gpu.c).
+     * Byte-identical files (tests/test_zz_planes_gpu.py; the multi-rank transport: tests/test_planes_host.py). */
+    const int want_dev_planes = getenv("PSOLVE_GPU_DEVICE_PLANES") ? atoi(getenv("PSOLVE_GPU_DEVICE_PLANES"))
+                                                                   : Global.theGroupSize == 1;
+    const int dev_planes = Param.theNumberOfPlanes != 0 && Param.IO_pool_pe_count == 0 && want_dev_planes;
     double *pl_rows = NULL;
+    if (Param.theNumberOfPlanes != 0 && Global.myID == 0)
+        monitor_print("gpu_solver_run() planes: %s\n", dev_planes ? "interpolated on the device" : "reference planes_print on fetched rows");
     if (dev_planes) {
         const int64_t npts = hgpu_planes_point_tables(Param.theNumberOfPlanes, NULL, NULL);
         int32_t *nd = malloc(sizeof(int32_t) * 8 * (size_t)(npts + 1));

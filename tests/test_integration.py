@@ -177,8 +177,8 @@ def test_planes_sparse_fetch_writes_the_same_files():
         pytest.skip("reference binaries / integration/_bin/psolve_gpu not built")
     c = refcase.Case(**TWO_LAYER, **SRC, damping="rayleigh", stiffness="effective", end_t=0.06, planes=PLANES, plane_rate=5)
     keep = [f"out/planes/planedisplacements.{i}" for i in range(len(PLANES))]
-    sparse, _ = _run_gpu(c, keep=keep)
-    full, _ = _run_gpu(c, {"PSOLVE_GPU_PLANES_FULL": "1"}, keep=keep)
+    sparse, _ = _run_gpu(c, {"PSOLVE_GPU_DEVICE_PLANES": "0"}, keep=keep)
+    full, _ = _run_gpu(c, {"PSOLVE_GPU_DEVICE_PLANES": "0", "PSOLVE_GPU_PLANES_FULL": "1"}, keep=keep)
     assert sparse == full
     with tempfile.TemporaryDirectory() as td:
         d = refcase.write_case(c, td)

@@ -3,11 +3,11 @@
 * through the C ABI: every recorded row equals the reference's interpolation arithmetic
   (Old_planes_print, io_planes.c:168-191) on the same field BIT FOR BIT, for arbitrary points;
 * through the reference's own main (integration/_bin/psolve_gpu): planedisplacements.N written from device
-  rows (PSOLVE_GPU_DEVICE_PLANES=1) are byte-identical to the files the reference's planes_print writes from
-  fetched displacements, on one rank and on two.
+  rows (the default on one rank, PSOLVE_GPU_DEVICE_PLANES=1 otherwise) are byte-identical to the files the
+  reference's planes_print writes from fetched displacements, on one rank and on two.
 
-The file sorts last on purpose: this path was written after the round's GPU time was spent (the host side --
-point tables, strip transport, arithmetic order -- is pinned on CPU in tests/test_planes_host.py).
+The host side -- point tables, strip transport on 1/2/4 ranks, arithmetic order -- is pinned on CPU in
+tests/test_planes_host.py.  Hardware run of this file: profiles/r02j_pytest_planes_device_1gpu.log.
 """
 import os
 import subprocess
@@ -96,7 +96,7 @@ def _run_gpu(case, env_extra, nranks, keep):
         p = subprocess.run([str(GPU_BIN), "parameters.in"], cwd=d, env=dict(os.environ, HMPI_NP=str(nranks), **env_extra),
                            stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
         assert p.returncode == 0, p.stdout[-4000:]
-        return [(d / k).read_bytes() for k in keep]
+        return [(d / k).read_bytes() for k in keep], (d / "out" / "monitor.txt").read_text()
 
 
 @pytest.mark.parametrize("nranks", [1, 2])
@@ -108,7 +108,10 @@ def test_device_planes_write_the_same_files(hb, nranks):
     model = TWO_LAYER if nranks == 1 else THREE_LAYER
     c = refcase.Case(**model, **SRC, damping="rayleigh", stiffness="effective", end_t=0.06, planes=PLANES, plane_rate=5)
     keep = [f"out/planes/planedisplacements.{i}" for i in range(len(PLANES))]
-    dev = _run_gpu(c, {"PSOLVE_GPU_DEVICE_PLANES": "1"}, nranks, keep)
-    host = _run_gpu(c, {"PSOLVE_GPU_DEVICE_PLANES": "0"}, nranks, keep)
+    # one rank: device planes are the default; several ranks: opt-in
+    dev, mon = _run_gpu(c, {} if nranks == 1 else {"PSOLVE_GPU_DEVICE_PLANES": "1"}, nranks, keep)
+    assert "planes: interpolated on the device" in mon
+    host, mon = _run_gpu(c, {"PSOLVE_GPU_DEVICE_PLANES": "0"}, nranks, keep)
+    assert "planes: reference planes_print" in mon
     assert dev == host
     assert all(np.abs(np.frombuffer(f, np.float64)).max() > 0 for f in dev)
