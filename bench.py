@@ -269,13 +269,16 @@ def column_grid(world: int) -> tuple[int, int]:
 BASIN_MATS = ((1500.0, 500.0, 2000.0), (3000.0, 1000.0, 2200.0), (5000.0, 2000.0, 2500.0), (6928.0, 4000.0, 2800.0))
 
 
-def basin_workload(n: int, damping: int, part=None):
+def basin_workload(n: int, damping: int, part=None, local: bool = False, allgather=None, threads: int = 1):
     """configs[4] at single-GPU scale: the terashake box (300 x 600 x 84.375 km, tick ratio 32:64:9,
     examples/terashake/physics.in) with a synthetic CVM-like model -- Vs 500 / 1000 / 2000 / 4000 m/s:
     sediment basins (Gaussian blobs, fixed seed 20240901) over a depth-layered crust, piecewise constant
     on cells of 4 h like a material etree -- meshed by hercules_b200.octree exactly as octor would
     (vs rule, 2:1 balance, hanging nodes in every orientation): four octree levels.
-    n = h-cells along the 300 km edge.  Returns (mesh, info, dt, fmax, h)."""
+    n = h-cells along the 300 km edge.  part = (rank, world): that rank's Morton block of the ONE mesh;
+    local: built from the rank's own neighbourhood by hercules_b200.octree_local (native primitives, leaf counts
+    per coarse cell all-gathered through `allgather`) instead of meshing the whole domain on every rank and
+    cutting it -- the two give identical tables (tests/test_octree_local.py).  Returns (mesh, info, dt, fmax, h)."""
     from hercules_b200 import octree
     dims = (n, 2 * n, 9 * n // 32)
     if 9 * n % 32 or dims[2] % 4:
@@ -299,6 +302,11 @@ def basin_workload(n: int, damping: int, part=None):
                         np.where(z < 0.45 * dims[2], 2, 3))).astype(np.int64)
     if part is None or part[1] == 1:
         mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
+    elif local:
+        from hercules_b200 import octree_local
+        mesh, info = octree_local.octree_halfspace_local(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, part[0], part[1],
+                                                         damping=damping, allgather=allgather, threads=threads, model_cell=4)
+        info.pop("model", None)
     else:
         # every rank builds the whole mesh and takes its Morton block (octree.partition); fine up to a few 10 M elements
         mesh, info = octree.octree_halfspace_part(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, part[0], part[1],
@@ -317,8 +325,9 @@ def basin_config(n, info, damping, dt, fmax, h) -> dict:
             "elements_per_gpu": info["E"], "global_elements": info.get("etotal", info["E"]), "hanging_nodes": info["D"],
             "elements_by_size": {int(a): int(b) for a, b in zip(sizes, counts)}, "global_grid": list(info["dims"]), "dt": dt,
             "partition": ("single rank" if info.get("nranks", 1) == 1 else
-                          f"{info['nranks']} blocks of the Morton-ordered leaf list (octree.partition, as octor_partitiontree cuts "
-                          "it); ONE mesh over all GPUs: strong scaling"),
+                          f"{info['nranks']} blocks of the Morton-ordered leaf list (as octor_partitiontree cuts it), every rank "
+                          f"meshing only its block and a one-cell ring (octree_local: {info.get('local_region_elements', 0)} "
+                          "leaves built on this rank); ONE mesh over all GPUs: strong scaling"),
             "l2": "inputs larger than L2 for --edge >= 768; no explicit flush"}
 
 
@@ -596,7 +605,12 @@ def main() -> None:
     basin = args.workload == "basin"
     dt_run, freq_run, h_run = DT, FREQ, H_M
     if basin:
-        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp, (rank, world))
+        def gather_counts(mine):                                  # one int per coarse cell of this rank's share
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            return parts
+        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp, (rank, world), local=True, allgather=gather_counts,
+                                                             threads=max(1, (os.cpu_count() or 1) // world))
     elif adaptive:
         if n % 64:
             raise SystemExit("--workload adaptive needs --edge to be a multiple of 64")

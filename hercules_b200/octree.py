@@ -47,6 +47,11 @@ def refine(dims, smax: int, vs_of, factor_h: float, smin: int = 1):
     nx, ny, nz = dims
     gx, gy, gz = np.meshgrid(np.arange(0, nx, smax), np.arange(0, ny, smax), np.arange(0, nz, smax), indexing="ij")
     cur = (gx.ravel().astype(np.int64), gy.ravel().astype(np.int64), gz.ravel().astype(np.int64))
+    return refine_cells(cur, smax, vs_of, factor_h, smin)
+
+
+def refine_cells(cur, smax: int, vs_of, factor_h: float, smin: int = 1):
+    """refine() from a given set of octants of edge smax: cur = (x, y, z) of their lowest corners."""
     leaves, s = {}, smax
     while cur[0].size:
         x, y, z = cur
@@ -61,8 +66,10 @@ def refine(dims, smax: int, vs_of, factor_h: float, smin: int = 1):
     return {k: v for k, v in leaves.items() if v[0].size}
 
 
-def balance(leaves: dict, dims):
-    """2:1 balance across faces and edges, finest level first (prioritised ripple propagation)."""
+def balance(leaves: dict, dims, as_codes: bool = False):
+    """2:1 balance across faces and edges, finest level first (prioritised ripple propagation).
+    The leaf set may cover only part of the domain: octants that are not there constrain nothing.
+    as_codes: return {size: sorted Morton codes} instead of coordinates."""
     nx, ny, nz = dims
     sets = {s: np.unique(_code(*v)) for s, v in leaves.items()}
     sizes = sorted(sets)
@@ -107,6 +114,8 @@ def balance(leaves: dict, dims):
                             u = hu
                 t *= 2
         s *= 2
+    if as_codes:
+        return {s: c for s, c in sets.items() if c.size}
     return {s: _decode(c) for s, c in sets.items() if c.size}
 
 

@@ -157,14 +157,16 @@ def test_partition_reproduces_octor(name):
         assert np.allclose(mesh.nTable[ismine], v["nTable"][ismine], rtol=2e-15, atol=0)
 
 
+@pytest.mark.parametrize("local", [False, True], ids=["whole-mesh-cut", "per-rank"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_bench_basin_partitions_are_consistent(world):
+def test_bench_basin_partitions_are_consistent(world, local):
     """bench.py --workload basin --gpus N at --edge 128: every node owned once, every element on one rank,
-    the halo schedules of every pair of ranks name the same nodes in the same order."""
+    the halo schedules of every pair of ranks name the same nodes in the same order.  local: the per-rank
+    mesher bench.py uses (hercules_b200.octree_local), otherwise the whole-mesh cut."""
     import bench
     import hercules_b200 as hb
     from test_meshgen import _pairwise_schedules_match
-    parts = [bench.basin_workload(128, hb.BKT, (r, world))[:2] for r in range(world)]
+    parts = [bench.basin_workload(128, hb.BKT, (r, world), local=local)[:2] for r in range(world)]
     whole, winfo = bench.basin_workload(128, hb.BKT)[:2]
     assert _pairwise_schedules_match([p[0] for p in parts], [p[1] for p in parts]) > 0
     assert sum(p[1]["E"] for p in parts) == winfo["E"] == parts[0][1]["etotal"]

@@ -1,0 +1,90 @@
+"""CPU tests: hercules_b200.octree_local -- a rank's mesh from LOCAL work (its Morton block plus a one-cell
+ring; leaf counts per coarse cell instead of the global leaf list) against (a) multi-rank runs of the
+unmodified reference (the same goldens and the same assertions as tests/test_octree.py::
+test_partition_reproduces_octor) and (b) the whole-mesh-then-cut build on the bench's basin model."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, params_of, rank_view
+from test_octree import CASES, PART_CASES, _mat_of
+
+
+@pytest.mark.parametrize("native", [False, True], ids=["numpy", "native"])
+@pytest.mark.parametrize("name", sorted(PART_CASES))
+def test_local_build_reproduces_octor(name, native):
+    """native: refinement, balancing and extraction by csrc/hmesh.cpp on the rasterised model (cells of the
+    CVM leaf edge); otherwise the numpy restatement on the model function."""
+    from hercules_b200 import octree_local as ol
+    base, world = PART_CASES[name]
+    dims, h, smax, cl, mats, box, tops, vs_min, ppw, fmax = CASES[base]
+    g = load_golden(name)
+    counts = None
+    for r in range(world):
+        v = rank_view(g, r); P = params_of(v)
+        mesh, info = ol.octree_halfspace_local(dims, smax, h, P["dt"], mats, _mat_of(CASES[base]), ppw, fmax, r, world,
+                                               freq=P["freq"], damping=P["damping"], vs_min=vs_min, exact=True,
+                                               counts=counts, chunk=5, threads=2, model_cell=cl if native else None)
+        counts = info["counts"]
+        assert np.array_equal(info["elem_geid"], v["elem_geid"])
+        assert mesh.elem_lnid.shape == v["elem_lnid"].shape and np.array_equal(mesh.elem_lnid, v["elem_lnid"])
+        xyz = np.stack(info["node_xyz"], 1)
+        tick = int(v["node_ticks"][v["node_ticks"] > 0].min()) // int(xyz[xyz > 0].min())
+        assert np.array_equal(xyz * tick, v["node_ticks"])
+        ismine = v["node_flags"][:, 0].astype(bool)
+        assert np.array_equal(info["owner"] == r, ismine)
+        assert np.array_equal(info["owner"][~ismine], v["node_owner"][~ismine])
+        assert np.array_equal(info["anchored"], v["node_flags"][:, 1].astype(bool))
+        assert info["share"].shape == v["node_share"].shape and np.array_equal(info["share"], v["node_share"])
+        assert mesh.dnode.shape == v["dnode"].shape and np.array_equal(mesh.dnode, v["dnode"])
+        for side in ("dn_c", "dn_s", "an_c", "an_s"):
+            ml = getattr(mesh, side)
+            hdr = np.stack([ml.peer, ml.nodes], 1).reshape(-1, 2)
+            assert np.array_equal(hdr, v[side + "_hdr"].reshape(-1, 2)), (r, side)
+            assert np.array_equal(ml.mapping, v[side + "_map"]), (r, side)
+        assert np.array_equal(mesh.eTable, v["eTable"])
+        assert np.allclose(mesh.nTable[ismine], v["nTable"][ismine], rtol=2e-15, atol=0)
+
+
+def _same_tables(a, ai, b, bi):
+    assert np.array_equal(ai["elem_geid"], bi["elem_geid"]) and ai["etotal"] == bi["etotal"]
+    for k in ("elem_lnid", "eTable", "dnode", "edata"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(np.stack(ai["node_xyz"]), np.stack(bi["node_xyz"]))
+    assert np.array_equal(ai["owner"], bi["owner"]) and np.array_equal(ai["share"], bi["share"])
+    assert np.array_equal(ai["anchored"], bi["anchored"])
+    mine = ai["owner"] == ai["rank"]
+    assert np.array_equal(a.nTable[mine], b.nTable[mine])       # complete sums, same summation order: bit-equal
+    for side in ("dn_c", "dn_s", "an_c", "an_s"):
+        x, y = getattr(a, side), getattr(b, side)
+        assert np.array_equal(x.peer, y.peer) and np.array_equal(x.nodes, y.nodes) and np.array_equal(x.mapping, y.mapping)
+
+
+@pytest.mark.parametrize("native", [False, True], ids=["numpy", "native"])
+@pytest.mark.parametrize("world", [2, 5])
+def test_local_build_equals_whole_mesh_cut_on_the_basin_model(world, native):
+    """bench.py's configs[4] model at --edge 128 (57 k elements, 4 octree levels, BKT): every rank's tables
+    from the local build equal the cut of the whole mesh; the counts come from the ranks' own shares of the
+    coarse cells, gathered (here: in process)."""
+    import bench
+    import hercules_b200 as hb
+    from hercules_b200 import octree, octree_local as ol
+    n = 128
+    whole = [bench.basin_workload(n, hb.BKT, (r, world))[:2] for r in range(world)]
+    mat_of = whole[0][1]["mat_of"]
+    dims = whole[0][1]["dims"]
+    h, ppw = 300000.0 / n, 8.0
+    fmax, dt = 499.0 / (ppw * h), 0.2 * h / 1500.0
+    g = int(np.gcd.reduce(dims)); smax = min(g & -g, 8)
+    # pass 1 as the ranks would do it: each counts its share of the coarse cells
+    S = min(smax, octree.bootstrap_size(dims, 1 << (max(dims) - 1).bit_length(), world))
+    grid = ol.CoarseGrid(dims, S)
+    vs_tab = np.array([m[1] for m in bench.BASIN_MATS])
+    model = ol.GridModel(dims, 4, mat_of, vs_tab) if native else None
+    shares = [ol.leaf_counts(grid, np.arange(r * grid.n // world, (r + 1) * grid.n // world),
+                             lambda x, y, z: vs_tab[mat_of(x, y, z)], h * ppw * fmax, chunk=300, threads=2, model=model)
+              for r in range(world)]
+    for r in range(world):
+        mesh, info = ol.octree_halfspace_local(dims, smax, h, dt, list(bench.BASIN_MATS), mat_of, ppw, fmax, r, world,
+                                               damping=hb.BKT, allgather=lambda mine: shares, chunk=300, threads=2, model=model)
+        assert info["local_region_elements"] < info["etotal"]
+        _same_tables(mesh, info, *whole[r])
