@@ -538,6 +538,9 @@ def main() -> None:
     ap.add_argument("--tile-nodes", type=int, default=0)
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
+    ap.add_argument("--stiffness", default="effective", choices=["effective", "conventional"],
+                    help="conventional: compute_addforce_conventional (stiffness.c:121-176), the dense 24 x 24 element "
+                         "matrices K1 / K2 -- the DENSE variant of the step kernel (Rayleigh damping only)")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "adaptive", "graded", "basin"],
                     help="uniform = configs[1] (the headline); adaptive = configs[2]: 3-level octree mesh with hanging "
                          "nodes, ~100 M elements at --edge 512 (meshgen.graded_halfspace, single GPU); graded = configs[2] "
@@ -669,7 +672,10 @@ def main() -> None:
     t_mesh = time.time() - t0
 
     t0 = time.time()
-    s = hb.Solver(mesh, dt=dt_run, damping=damp, stiffness=hb.EFFECTIVE, freq=freq_run,
+    if args.stiffness == "conventional" and args.damping != "rayleigh":
+        raise SystemExit("--stiffness conventional is measured with Rayleigh damping only")
+    s = hb.Solver(mesh, dt=dt_run, damping=damp, stiffness=hb.CONVENTIONAL if args.stiffness == "conventional" else hb.EFFECTIVE,
+                  freq=freq_run,
                   loaded_lnid=loaded, rank=rank, nranks=world, device=local,
                   tile_nodes=args.tile_nodes, flags=hb.FLAG_TIMERS | run_flags)
     if world > 1:
@@ -806,7 +812,9 @@ def main() -> None:
                                        args.damping, info if adaptive else None)),
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity_check": parity,
             "roofline": {"bound": "hbm",
-                         "kernel": (("step_kernel<1,false,256,true> (WPASS variant; " if args.wpass else "step_kernel<1,false,256> (") +
+                         "kernel": "step_kernel<1,true,256> (dense 24 x 24 K1 / K2 stiffness + Rayleigh damping + update, fused)"
+                                   if args.stiffness == "conventional" else
+                                   (("step_kernel<1,false,256,true> (WPASS variant; " if args.wpass else "step_kernel<1,false,256> (") +
                                     "stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"
                                     else "step_kernel<3,false,256> (BKT memory variables + constant-Q force + update, fused)"),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -828,10 +836,14 @@ def main() -> None:
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             try:
-                key = f"{args.workload}:{args.damping}:{'wpass' if args.wpass else 'default'}:{E}"
+                variant = "conventional" if args.stiffness == "conventional" else "wpass" if args.wpass else "default"
+                key = f"{args.workload}:{args.damping}:{variant}:{E}"
                 line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("by_workload", {}).get(key)
             except Exception:
                 pass
+        if args.stiffness == "conventional":
+            line["config"]["workload"] = line["config"]["workload"].replace("effective stiffness", "CONVENTIONAL stiffness "
+                                                                            "(compute_addforce_conventional, dense K1 / K2)")
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
