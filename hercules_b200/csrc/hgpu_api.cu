@@ -1339,6 +1339,15 @@ extern "C" int hgpu_run(hgpu_solver_t *s, int32_t step0, int32_t nsteps, const d
         return fail(HGPU_EINVAL, "hgpu_run: steps [%d, %d) are not covered by the preloaded source history",
                     step0, step0 + nsteps);
     const size_t row0 = n > 0 ? (size_t)(step0 - s->Fall_step0) : 0;
+    if (s->st_n > 0 && s->st_rate > 0) {
+        // the station ring must take every row of this run: fail BEFORE the first swap, not in the middle of a step
+        int64_t rows = 0;
+        for (int32_t k = 0; k < nsteps; k++) rows += (step0 + k) % s->st_rate == 0;
+        if (s->st_count + rows > s->st_cap)
+            return fail(HGPU_ESTATE, "hgpu_run: %lld station rows would be recorded but the device ring has room for %d "
+                        "(capacity %d, %d pending): drain it or run fewer steps", (long long)rows, s->st_cap - s->st_count,
+                        s->st_cap, s->st_count);
+    }
     for (int32_t k = 0; k < nsteps; k++) {
         int rc;
         if ((rc = hgpu_step_begin(s, step0 + k))) return rc;

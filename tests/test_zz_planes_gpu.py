@@ -115,3 +115,20 @@ def test_device_planes_write_the_same_files(hb, nranks):
     assert "planes: reference planes_print" in mon
     assert dev == host
     assert all(np.abs(np.frombuffer(f, np.float64)).max() > 0 for f in dev)
+
+
+def test_run_checks_the_station_ring_before_the_first_step(hb):
+    """hgpu_run with stations recorded at a cadence: a run whose rows do not fit the device ring is refused up
+    front (it used to fail in the middle of a step, after the swap), and leaves the solver untouched."""
+    g = load_golden("graded2_rayleigh_eff")
+    P = params_of(g)
+    s = hb.Solver(hb.HostMesh.from_dump(g), dt=P["dt"], dt2=P["dt2"], damping=P["damping"], stiffness=P["stiffness"],
+                  freq=P["freq"], loaded_lnid=g["loaded_lnid"])
+    s.stations_attach(g["station_nodes"][:, 1:].astype(np.int32), g["station_local"], rate=2, capacity=3)
+    with pytest.raises(hb.HerculesGpuError, match="station rows"):
+        s.run(0, 10, g["forces"][:10])                           # rows at steps 0, 2, 4, 6, 8: five > three
+    assert s.stations_pending() == 0 and not s.fetch_all(hb.TM1).any()
+    s.run(0, 6, g["forces"][:6])                                 # rows at 0, 2, 4: fits
+    steps, rows = s.stations_drain()
+    assert list(steps) == [0, 2, 4] and rows.shape[0] == 3
+    s.close()
