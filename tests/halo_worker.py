@@ -12,6 +12,8 @@ whole mesh -- the host-side half of the multi-GPU path (the device half is tests
 usage: halo_worker.py <nx> <ny> <bands as n:s,n:s,...> <steps>     env: RANK WORLD_SIZE MASTER_ADDR MASTER_PORT
        halo_worker.py <nx> <ny> basin <steps>      the laterally varying model of tests/golden/basin_rayleigh_eff*.npz
                                                    through hercules_b200.octree (general mesher and partition)
+       halo_worker.py <nx> <ny> basin-local <steps>  the same through hercules_b200.octree_local: per-rank meshing,
+                                                   leaf counts all-gathered over gloo
 """
 import os
 import sys
@@ -58,7 +60,7 @@ def main():
     import hercules_oracle as ho
     from hercules_b200 import meshgen, octree
     nx, ny = int(sys.argv[1]), int(sys.argv[2])
-    basin = sys.argv[3] == "basin"
+    basin = sys.argv[3] in ("basin", "basin-local")
     bands = None if basin else tuple(tuple(int(t) for t in b.split(":")) for b in sys.argv[3].split(","))
     steps = int(sys.argv[4])
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -66,7 +68,19 @@ def main():
     ho.build() if rank == 0 else None
     dist.barrier()
     L = ho.lib()
-    if basin:
+    if sys.argv[3] == "basin-local":
+        # every rank meshes only its Morton block and one ring of coarse cells (hercules_b200.octree_local, native
+        # primitives); the leaf counts of the ranks' shares of the coarse cells travel over gloo
+        from hercules_b200 import octree_local
+
+        def allgather(mine):
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+            return parts
+        mesh, info = octree_local.octree_halfspace_local((nx, ny, 16), 8, H, DT, BASIN_MATS, basin_mat, 8.0, FREQ, rank, world,
+                                                         vs_min=800.0, allgather=allgather, model_cell=2, chunk=7, threads=2)
+        assert info["local_region_elements"] <= info["etotal"]
+    elif basin:
         mesh, info = octree.octree_halfspace_part((nx, ny, 16), 8, H, DT, BASIN_MATS, basin_mat, 8.0, FREQ, rank, world, vs_min=800.0)
         info["dims"] = (nx, ny, 16)
     else:

@@ -20,7 +20,8 @@ def _free_port():
 
 
 @pytest.mark.parametrize("world,bands", [(2, "2:1,3:2,2:4"), (4, "2:1,7:2"), (4, "4:1,2:2,2:4"),
-                                         (3, "basin"), (4, "basin")])     # basin: general mesher + general partition
+                                         (3, "basin"), (4, "basin"),      # basin: general mesher + general partition
+                                         (2, "basin-local"), (4, "basin-local")])   # per-rank meshing, counts over gloo
 def test_partitioned_time_loop_equals_whole_mesh(world, bands):
     port = _free_port()
     procs = []
