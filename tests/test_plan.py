@@ -75,3 +75,24 @@ def test_tile_plan_on_partitioned_adaptive_workload(world, rank):
     r = solver.plan_build(mesh.elem_lnid, info["N"], 0, mesh=mesh)
     assert r["tile_elems_total"] >= info["E"] and r["early_tiles"] >= 1
     assert r["smem_bytes"] <= 115712
+
+
+@pytest.mark.parametrize("world,rank", [(2, 1), (4, 0), (8, 5)])
+def test_tile_plan_on_per_rank_basin_workload(world, rank):
+    """bench.py --workload basin --gpus N (configs[4]; hercules_b200.octree_local: every rank meshes only its block
+    and one ring) at --edge 256: the tile plan builds and self-checks on the rank's mesh -- 4 octree levels, BKT,
+    hanging nodes and anchors on other ranks -- and the mesh handed to hgpu_init is self-consistent."""
+    import bench
+    import hercules_b200 as hb
+    from hercules_b200 import solver
+    mesh, info = bench.basin_workload(256, hb.BKT, (rank, world), local=True, threads=2)[:2]
+    E, N = info["E"], info["N"]
+    assert mesh.elem_lnid.shape == (E, 8) and mesh.elem_lnid.min() == 0 and mesh.elem_lnid.max() == N - 1
+    assert mesh.nTable.shape == (N, 7) and (mesh.nTable[info["owner"] == rank, 0] > 0).all()       # owned masses complete
+    assert mesh.dnode.shape[0] == info["D"] > 0 and mesh.dnode[:, 0].max() < N
+    for ml in (mesh.dn_c, mesh.dn_s, mesh.an_c, mesh.an_s):
+        assert ml.mapping.size == ml.nodes.sum() and (ml.mapping.size == 0 or ml.mapping.max() < N)
+        assert rank not in ml.peer.tolist()
+    r = solver.plan_build(mesh.elem_lnid, N, 0, mesh=mesh)
+    assert r["tile_elems_total"] >= E and r["early_tiles"] >= 1
+    assert r["smem_bytes"] <= 115712
