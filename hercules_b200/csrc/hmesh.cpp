@@ -18,6 +18,8 @@
 //
 // Plain C ABI, no CUDA: built into libhercules_mesh.so by csrc/Makefile.  Coordinates are integers in units
 // of the finest admissible edge h, below 2^16; Morton codes interleave x (least significant), y, z.
+#include "hercules_mesh.h"
+
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>

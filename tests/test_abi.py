@@ -32,6 +32,19 @@ def test_header_symbols_exported(hb):
     assert hb.lib().hgpu_abi_version() == 1
 
 
+def test_mesh_header_symbols_exported(hb):
+    """libhercules_mesh.so (host-side octree primitives of the per-rank mesher) exports what
+    include/hercules_mesh.h declares, and the Python side binds each of them."""
+    import ctypes
+    from hercules_b200 import octree_local
+    hdr = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "hercules_mesh.h").read_text(), flags=re.S)
+    declared = set(re.findall(r"\b(hmesh_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == {"hmesh_abi_version", "hmesh_free", "hmesh_chunk_leaves", "hmesh_chunk_nodes", "hmesh_lnid"}
+    L = ctypes.CDLL(str(ROOT / "hercules_b200" / "libhercules_mesh.so"))
+    assert not [n for n in declared if not hasattr(L, n)]
+    assert octree_local.mesh_lib().hmesh_abi_version() == 1
+
+
 def test_no_cpu_fallback(hb):
     import torch
     if torch.cuda.is_available():
