@@ -300,13 +300,13 @@ def basin_workload(n: int, damping: int, part=None, local: bool = False, allgath
             depth = np.maximum(depth, dz * np.exp(-((x - bx_) ** 2 + (y - by_) ** 2) / r ** 2))
         return np.where(z < depth, 0, np.where(z < 2 * depth + 0.06 * dims[2], 1,
                         np.where(z < 0.45 * dims[2], 2, 3))).astype(np.int64)
-    if part is None or part[1] == 1:
-        mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
-    elif local:
+    if local and part is not None:
         from hercules_b200 import octree_local
         mesh, info = octree_local.octree_halfspace_local(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, part[0], part[1],
                                                          damping=damping, allgather=allgather, threads=threads, model_cell=4)
         info.pop("model", None)
+    elif part is None or part[1] == 1:
+        mesh, info = octree.octree_halfspace(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, damping=damping)
     else:
         # every rank builds the whole mesh and takes its Morton block (octree.partition); fine up to a few 10 M elements
         mesh, info = octree.octree_halfspace_part(dims, smax, h, dt, list(BASIN_MATS), mat_of, ppw, fmax, part[0], part[1],
@@ -324,7 +324,7 @@ def basin_config(n, info, damping, dt, fmax, h) -> dict:
                         f"orientation; {damping} damping, effective stiffness, point source, 5 stations",
             "elements_per_gpu": info["E"], "global_elements": info.get("etotal", info["E"]), "hanging_nodes": info["D"],
             "elements_by_size": {int(a): int(b) for a, b in zip(sizes, counts)}, "global_grid": list(info["dims"]), "dt": dt,
-            "partition": ("single rank" if info.get("nranks", 1) == 1 else
+            "partition": ("single rank (meshed by hercules_b200.octree_local, native primitives)" if info.get("nranks", 1) == 1 else
                           f"{info['nranks']} blocks of the Morton-ordered leaf list (as octor_partitiontree cuts it), every rank "
                           f"meshing only its block and a one-cell ring (octree_local: {info.get('local_region_elements', 0)} "
                           "leaves built on this rank); ONE mesh over all GPUs: strong scaling"),
@@ -612,7 +612,8 @@ def main() -> None:
             parts = [None] * world
             dist.all_gather_object(parts, mine)
             return parts
-        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp, (rank, world), local=True, allgather=gather_counts,
+        mesh, info, dt_run, freq_run, h_run = basin_workload(n, damp, (rank, world), local=True,
+                                                             allgather=gather_counts if world > 1 else None,
                                                              threads=max(1, (os.cpu_count() or 1) // world))
     elif adaptive:
         if n % 64:
