@@ -88,3 +88,18 @@ def test_local_build_equals_whole_mesh_cut_on_the_basin_model(world, native):
                                                damping=hb.BKT, allgather=lambda mine: shares, chunk=300, threads=2, model=model)
         assert info["local_region_elements"] < info["etotal"]
         _same_tables(mesh, info, *whole[r])
+
+
+def test_local_build_on_one_rank_equals_the_whole_mesh():
+    """world = 1 (bench.py --workload basin on one GPU): X is the whole domain and the tables are those of the
+    numpy whole-mesh build, nTable included bit for bit."""
+    import bench
+    import hercules_b200 as hb
+    a, ai = bench.basin_workload(256, hb.BKT)[:2]
+    b, bi = bench.basin_workload(256, hb.BKT, (0, 1), local=True, threads=2)[:2]
+    assert bi["local_region_elements"] == bi["E"] == ai["E"] and bi["N"] == ai["N"]
+    for k in ("elem_lnid", "eTable", "nTable", "dnode", "edata"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+    assert np.array_equal(np.stack(ai["node_xyz"]), np.stack(bi["node_xyz"]))
+    assert np.array_equal(np.stack(ai["elem_xyz"]), np.stack(bi["elem_xyz"])) and np.array_equal(ai["elem_size"], bi["elem_size"])
+    assert b.dn_c.peer.size == b.dn_s.peer.size == b.an_c.peer.size == b.an_s.peer.size == 0 and (bi["owner"] == 0).all()
