@@ -277,7 +277,7 @@ def _msglist(nd, peers):
 
 
 def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: int, world: int, dang=None, trash=None,
-                    holder=None):
+                    holder=None, lcode=None):
     """octree.partition on the leaves of X (the rank's cells and one ring) instead of the whole mesh:
     gidx = global Morton index of every leaf of X (ascending), etotal = leaves of the whole mesh.  Same rules,
     same return values; ranks other than `rank` are only described where they meet nodes `rank` owns."""
@@ -285,7 +285,8 @@ def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: i
     ex, ey, ez, es = leaves
     px, py, pz = nodes
     N = px.size
-    lcode = oc._code(ex, ey, ez)
+    if lcode is None:
+        lcode = oc._code(ex, ey, ez)
     if holder is None:
         qx, qy, qz = np.minimum(px, nx - 1), np.minimum(py, ny - 1), np.minimum(pz, nz - 1)
         hl = np.searchsorted(lcode, oc._code(qx, qy, qz), side="right") - 1
@@ -310,7 +311,7 @@ def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: i
     downer = owner[dnode[:, 0]]
     for r in ranks:
         d = np.zeros(N, bool)
-        d[lnid[eown == r].reshape(-1)] = True
+        d[(lnid[a:b] if r == rank else lnid[np.nonzero(eown == r)[0]]).reshape(-1)] = True
         hb = d | (owner == r)
         anc = dnode[downer == r][:, 2:6]
         hb[anc[anc >= 0]] = True
@@ -445,7 +446,7 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     else:
         leaves = {int(s): oc._decode(codes[sizes == s]) for s in np.unique(sizes)}
         (ex, ey, ez, es), (px, py, pz), lnid, dnode = oc.extract(leaves, dims)
-    del codes, sizes, cell
+    del sizes, cell
     # solver_init's tables on X (rows of the nodes this rank owns are complete: every element that touches
     # them, and every dangling node anchored at them with all ITS elements, is in X)
     abase, bbase = mg.compute_setab(damping, fmax if freq is None else freq)
@@ -461,7 +462,7 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     mg._distribute(nT, dnode)
     (a, b), H, l_lnid, l_dnode, owner, share, anch, msg = partition_local(dims, (ex, ey, ez, es), gidx, etotal,
                                                                           (px, py, pz), lnid, dnode, rank, world,
-                                                                          dang, trash, holder)
+                                                                          dang, trash, holder, codes)
     edata = np.zeros((b - a, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"][a:b], pr["Vp"][a:b], pr["Vs"][a:b], pr["rho"][a:b]
     if damping == BKT:
