@@ -103,3 +103,21 @@ def test_local_build_on_one_rank_equals_the_whole_mesh():
     assert np.array_equal(np.stack(ai["node_xyz"]), np.stack(bi["node_xyz"]))
     assert np.array_equal(np.stack(ai["elem_xyz"]), np.stack(bi["elem_xyz"])) and np.array_equal(ai["elem_size"], bi["elem_size"])
     assert b.dn_c.peer.size == b.dn_s.peer.size == b.an_c.peer.size == b.an_s.peer.size == 0 and (bi["owner"] == 0).all()
+
+
+@pytest.mark.parametrize("n", [128, 256])
+def test_bench_basin_elements_do_not_straddle_materials(n):
+    """mesh_correct_properties (psolve.c:7103-7200) gives an element the mean of 27 samples (0.005 / 0.5 / 0.995 of
+    its edge along every axis); the meshers here sample the centre.  The two agree exactly when no element sees
+    two materials -- which is what makes the bench's basin tables the reference's: checked here."""
+    import bench
+    import hercules_b200 as hb
+    mesh, info = bench.basin_workload(n, hb.BKT, (0, 1), local=True, threads=2)[:2]
+    mat_of = info["mat_of"]
+    ex, ey, ez = info["elem_xyz"]
+    es = info["elem_size"]
+    centre = mat_of(ex + 0.5 * es, ey + 0.5 * es, ez + 0.5 * es)
+    for a in (0.005, 0.5, 0.995):
+        for b in (0.005, 0.5, 0.995):
+            for c in (0.005, 0.5, 0.995):
+                assert np.array_equal(mat_of(ex + a * es, ey + b * es, ez + c * es), centre), (a, b, c)
