@@ -462,6 +462,29 @@ int hmesh_lnid(const int32_t *dims, int32_t S, const uint64_t *xkeys, int64_t nX
     return 0;
 }
 
+// solver_init's lumped-mass sums (psolve.c:3445-3473) for the grouped form meshgen._accumulate uses: for every
+// corner column j = 0..7 in turn, col[n] = sum over the elements e (ascending) with lnid[e][j] == n of w[e], then
+// out[n] += col[n] -- the summation order of the numpy restatement (np.bincount per column), so that the two give
+// the same doubles.  nw weight arrays w[k][E] -> out[k][N] (out is accumulated into); scratch-free for the caller.
+int hmesh_corner_sums(int64_t E, const int32_t *lnid, int64_t N, int32_t nw, const double *const *w, double *const *out)
+{
+    if (E < 0 || N < 0 || nw < 1 || !lnid || !w || !out) return -1;
+    std::vector<double> col((size_t)N);
+    for (int k = 0; k < nw; k++)
+        for (int j = 0; j < 8; j++) {
+            std::fill(col.begin(), col.end(), 0.0);
+            const double *wk = w[k];
+            for (int64_t e = 0; e < E; e++) {
+                const int32_t n = lnid[8 * e + j];
+                if (n < 0 || n >= N) return -3;
+                col[(size_t)n] += wk[e];
+            }
+            double *o = out[k];
+            for (int64_t n = 0; n < N; n++) o[n] += col[(size_t)n];
+        }
+    return 0;
+}
+
 void hmesh_free(void *p) { std::free(p); }
 
 int hmesh_abi_version(void) { return 1; }

@@ -234,6 +234,38 @@ def extract_native(grid: CoarseGrid, X, codes, sizes, lstart, chunk: int = 4096,
     return (ex_, ey_, ez_, np.asarray(sizes, np.int64)), (px, py, pz), lnid, dnode, dang, holder, N
 
 
+def _accumulate_native(nT, lnid, pr, dt, threads: int = 1):
+    """meshgen._accumulate (grouped form, exact = False) with the two big per-node sums -- sum(M) and sum(dt a M)
+    over the incident (element, corner) pairs -- done by hmesh_corner_sums in the same summation order; the
+    dashpot terms (boundary elements only) stay in numpy.  Same doubles as the numpy restatement."""
+    L = mesh_lib()
+    L.hmesh_corner_sums.restype = C.c_int
+    L.hmesh_corner_sums.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+    E, N = lnid.shape[0], nT.shape[0]
+    lnid = np.ascontiguousarray(lnid, np.int32)
+    M = np.ascontiguousarray(pr["M"], np.float64)
+    daM = np.ascontiguousarray(dt * pr["a"] * pr["M"], np.float64)
+    sumM, sumaM = np.zeros(N), np.zeros(N)
+
+    def one(args):
+        w, out = args
+        wp, op = (C.c_void_p * 1)(w.ctypes.data), (C.c_void_p * 1)(out.ctypes.data)
+        rc = L.hmesh_corner_sums(E, lnid.ctypes.data, N, 1, wp, op)
+        if rc != 0:
+            raise RuntimeError(f"hmesh_corner_sums failed ({rc})")
+    with ThreadPoolExecutor(2 if threads > 1 else 1) as ex:
+        list(ex.map(one, [(M, sumM), (daM, sumaM)]))
+    nT[:, 0] += sumM
+    base1, base2 = sumM - sumaM, 2 * sumM - sumaM
+    bi, dash = pr["bidx"], pr["dash"]
+    bflat = lnid[bi].reshape(-1)
+    for ax in range(3):
+        d = dt * dash[:, :, ax].reshape(-1)
+        dsum = np.bincount(bflat, d, N) if bflat.size else 0.0
+        nT[:, 4 + ax] += base1 - dsum
+        nT[:, 1 + ax] += base2 - dsum
+
+
 def _chunks(ids, chunk):
     return [ids[i:i + chunk] for i in range(0, ids.size, chunk)]
 
@@ -254,17 +286,18 @@ def leaf_counts(grid: CoarseGrid, ids, vs_of, factor_h, chunk: int = 4096, threa
 
 
 def exact_leaves(grid: CoarseGrid, ids, vs_of, factor_h, chunk: int = 4096, threads: int = 1, model: GridModel | None = None):
-    """(codes ascending, sizes) of the whole-domain mesh inside the cells `ids` (ascending)."""
+    """(codes ascending, sizes, leaves per cell) of the whole-domain mesh inside the cells `ids` (ascending)."""
     parts = _chunks(np.asarray(ids, np.int64), chunk)
     if model is not None:
         def one(sub):
-            return _chunk_leaves_native(grid, sub, model, factor_h)[:2]
+            return _chunk_leaves_native(grid, sub, model, factor_h)
     else:
         def one(sub):
-            return _chunk_leaves(grid, sub, vs_of, factor_h)[:2]
+            return _chunk_leaves(grid, sub, vs_of, factor_h)
     with ThreadPoolExecutor(max(threads, 1)) as ex:
         res = list(ex.map(one, parts))
-    return np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res])
+    return (np.concatenate([r[0] for r in res]), np.concatenate([r[1] for r in res]),
+            np.concatenate([r[2] for r in res]).astype(np.int64))
 
 
 def _msglist(nd, peers):
@@ -433,12 +466,11 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     c0 = int(np.searchsorted(prefix, lo, side="right")) - 1
     c1 = int(np.searchsorted(prefix, hi, side="left"))
     X = grid.ring(np.arange(c0, max(c1, c0 + 1)))
-    codes, sizes = exact_leaves(grid, X, vs_of, factor_h, chunk, threads, model)
-    cell = np.searchsorted(grid.key[X], codes >> grid.shift)                    # position in X of every leaf's cell
-    per_cell = np.bincount(cell, minlength=X.size)
+    codes, sizes, per_cell = exact_leaves(grid, X, vs_of, factor_h, chunk, threads, model)
     assert np.array_equal(per_cell, counts[X]), "leaf counts of the two passes disagree"
     start = np.concatenate([[0], np.cumsum(per_cell)])[:-1]
-    gidx = prefix[X][cell] + (np.arange(codes.size) - start[cell])
+    # global Morton index of every leaf of X: first leaf of its cell in the whole mesh + position inside the cell
+    gidx = np.repeat(prefix[X] - start, per_cell) + np.arange(codes.size)
     dang = trash = holder = None
     if model is not None:
         (ex, ey, ez, es), (px, py, pz), lnid, dnode, dang, holder, trash = extract_native(
@@ -446,7 +478,7 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     else:
         leaves = {int(s): oc._decode(codes[sizes == s]) for s in np.unique(sizes)}
         (ex, ey, ez, es), (px, py, pz), lnid, dnode = oc.extract(leaves, dims)
-    del sizes, cell
+    del sizes
     # solver_init's tables on X (rows of the nodes this rank owns are complete: every element that touches
     # them, and every dangling node anchored at them with all ITS elements, is in X)
     abase, bbase = mg.compute_setab(damping, fmax if freq is None else freq)
@@ -458,7 +490,10 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
         mat = mat_of(ex + 0.5 * es, ey + 0.5 * es, ez + 0.5 * es).astype(np.int64)
     pr = mg._elem_props(ex, ey, ez, dims, h, dt, layers, abase, bbase, thr_damping, thr_vpvs, size=es, mat=mat)
     nT = np.zeros((px.size, 7))
-    mg._accumulate(nT, lnid, pr, dt, exact)
+    if model is not None and not exact:
+        _accumulate_native(nT, lnid, pr, dt, threads)
+    else:
+        mg._accumulate(nT, lnid, pr, dt, exact)
     mg._distribute(nT, dnode)
     (a, b), H, l_lnid, l_dnode, owner, share, anch, msg = partition_local(dims, (ex, ey, ez, es), gidx, etotal,
                                                                           (px, py, pz), lnid, dnode, rank, world,
@@ -466,8 +501,12 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     edata = np.zeros((b - a, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"][a:b], pr["Vp"][a:b], pr["Vs"][a:b], pr["rho"][a:b]
     if damping == BKT:
-        mu, first, inv = np.unique(mat[a:b], return_index=True, return_inverse=True)
-        edata[:, 4:14] = mg.bkt_coefficients(pr["Vp"][a:b][first], pr["Vs"][a:b][first])[inv]
+        mab = mat[a:b]                                           # one table search per material, not per element
+        mu = np.flatnonzero(np.bincount(mab))
+        first = np.array([int(np.argmax(mab == m)) for m in mu], np.int64)
+        lut = np.zeros(int(mu.max()) + 1 if mu.size else 1, np.int64)
+        lut[mu] = np.arange(mu.size)
+        edata[:, 4:14] = mg.bkt_coefficients(pr["Vp"][a:b][first], pr["Vs"][a:b][first])[lut[mab]]
     K1, K2 = mg.compute_K()
     part = HostMesh(l_lnid, pr["eT"][a:b], nT[H], l_dnode, edata, K1, K2, msg["dn_c"], msg["dn_s"], msg["an_c"], msg["an_s"])
     info = dict(E=b - a, N=H.size, D=int(l_dnode.shape[0]), node_xyz=(px[H], py[H], pz[H]),

@@ -61,6 +61,12 @@ int hmesh_chunk_nodes(const int32_t *dims, int32_t S, const uint64_t *xkeys, int
 int hmesh_lnid(const int32_t *dims, int32_t S, const uint64_t *xkeys, int64_t nX, const int64_t *nstart, const uint64_t *ncodes,
                const uint64_t *lcodes, const int32_t *lsizes, int64_t e0, int64_t e1, int32_t missing, int32_t *lnid, int32_t *exyz);
 
+/* The per-node sums of solver_init's lumped terms (psolve.c:3445-3473: mass_simple += M, ... -= dt a M) in grouped
+ * form: out[k][n] += sum over corner columns j = 0..7 (in turn) of the sum over elements e (ascending) with
+ * lnid[e][j] == n of w[k][e].  Fixed summation order = the order of the numpy restatement (one np.bincount per
+ * column), so both give the same doubles.  nw weight arrays of E doubles, nw output arrays of N doubles. */
+int hmesh_corner_sums(int64_t E, const int32_t *lnid, int64_t N, int32_t nw, const double *const *w, double *const *out);
+
 #ifdef __cplusplus
 }
 #endif
