@@ -539,8 +539,11 @@ def main() -> None:
     ap.add_argument("--damping", default="rayleigh", choices=["rayleigh", "bkt"],
                     help="rayleigh = the headline workload (configs[1]); bkt = the same mesh with BKT damping")
     ap.add_argument("--stiffness", default="effective", choices=["effective", "conventional"],
-                    help="conventional: compute_addforce_conventional (stiffness.c:121-176), the dense 24 x 24 element "
-                         "matrices K1 / K2 -- the DENSE variant of the step kernel (Rayleigh damping only)")
+                    help="conventional: a solver created with HGPU_STIFFNESS_CONVENTIONAL (stiffness.c:121-176); it applies "
+                         "the same operator in factored form unless --dense-k is given (Rayleigh damping only)")
+    ap.add_argument("--dense-k", action="store_true",
+                    help="with --stiffness conventional: HGPU_FLAG_DENSE_K, the literal dense 24 x 24 K1 / K2 products "
+                         "(the DENSE variant of the step kernel; profiles/r02k_bench_conventional_160.json)")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "adaptive", "graded", "basin"],
                     help="uniform = configs[1] (the headline); adaptive = configs[2]: 3-level octree mesh with hanging "
                          "nodes, ~100 M elements at --edge 512 (meshgen.graded_halfspace, single GPU); graded = configs[2] "
@@ -592,8 +595,10 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not hb.SO.exists():
         hb.build()
+    if args.dense_k and args.stiffness != "conventional":
+        raise SystemExit("--dense-k goes with --stiffness conventional")
     run_flags = (hb.FLAG_NO_OVERLAP if args.no_overlap else 0) | (hb.FLAG_TAIL_OVERLAP if args.tail_overlap else 0) | \
-                (hb.FLAG_WPASS if args.wpass else 0)
+                (hb.FLAG_WPASS if args.wpass else 0) | (hb.FLAG_DENSE_K if args.dense_k else 0)
     note("process group up")
     parity = parity_check(hb, dist, rank, world, local, args.halo, run_flags) if world > 1 and not args.no_parity_check else None
     note(f"parity check done: {parity and parity['rel_l2']}")
@@ -814,7 +819,7 @@ def main() -> None:
             "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity_check": parity,
             "roofline": {"bound": "hbm",
                          "kernel": "step_kernel<1,true,256> (dense 24 x 24 K1 / K2 stiffness + Rayleigh damping + update, fused)"
-                                   if args.stiffness == "conventional" else
+                                   if args.dense_k else
                                    (("step_kernel<1,false,256,true> (WPASS variant; " if args.wpass else "step_kernel<1,false,256> (") +
                                     "stiffness + Rayleigh damping + update, fused)" if args.damping == "rayleigh"
                                     else "step_kernel<3,false,256> (BKT memory variables + constant-Q force + update, fused)"),
@@ -837,14 +842,16 @@ def main() -> None:
         traffic_file = ROOT / "profiles" / "traffic.json"
         if traffic_file.exists():
             try:
-                variant = "conventional" if args.stiffness == "conventional" else "wpass" if args.wpass else "default"
+                variant = "dense-k" if args.dense_k else "wpass" if args.wpass else "default"
                 key = f"{args.workload}:{args.damping}:{variant}:{E}"
                 line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("by_workload", {}).get(key)
             except Exception:
                 pass
         if args.stiffness == "conventional":
-            line["config"]["workload"] = line["config"]["workload"].replace("effective stiffness", "CONVENTIONAL stiffness "
-                                                                            "(compute_addforce_conventional, dense K1 / K2)")
+            line["config"]["workload"] = line["config"]["workload"].replace(
+                "effective stiffness", "CONVENTIONAL stiffness (compute_addforce_conventional: " +
+                ("literal dense K1 / K2 products, HGPU_FLAG_DENSE_K)" if args.dense_k else
+                 "the same operator, applied in the factored form of the effective method)"))
         sys.stdout.flush()
         os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)

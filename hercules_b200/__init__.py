@@ -10,5 +10,5 @@ from ._lib import build, lib, SO  # noqa: F401
 from .solver import (  # noqa: F401
     Solver, HostMesh, MsgList, HerculesGpuError, PinnedArray,
     RAYLEIGH, MASS, NONE, BKT, CONVENTIONAL, EFFECTIVE, TM1, TM2, TM3, FORCE, CONV_SHEAR_1, CONV_SHEAR_2, CONV_KAPPA_1, CONV_KAPPA_2,
-    FLAG_NO_FUSE, FLAG_TIMERS, FLAG_NO_OVERLAP, FLAG_TAIL_OVERLAP, FLAG_WPASS, FLAG_NO_STRUCT, FLAG_STRUCT,
+    FLAG_NO_FUSE, FLAG_TIMERS, FLAG_NO_OVERLAP, FLAG_TAIL_OVERLAP, FLAG_WPASS, FLAG_NO_STRUCT, FLAG_STRUCT, FLAG_DENSE_K,
 )

@@ -878,7 +878,12 @@ static int launch_range(hgpu_solver *s, Terms tm, bool fuse, int32_t begin, int3
     A.tile_beta = s->t_beta;
     A.tile_coef = s->t_coef;
     A.err = s->d_err;
-    const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt;
+    // compute_addforce_conventional (stiffness.c:121-176) applies theK1 x -c1 and theK2 x -c2 as dense 24 x 24
+    // matrices; compute_addforce_effective (:180-237) applies the SAME operator in factored form (the reference's
+    // two methods differ by rounding only: 5e-16 rel L2 over a whole run, oracle on the conventional golden).
+    // A solver created with HGPU_STIFFNESS_CONVENTIONAL therefore runs the factored kernels too (7x faster:
+    // profiles/r02k_*); HGPU_FLAG_DENSE_K asks for the literal dense evaluation with the K1 / K2 handed over.
+    const bool dense = s->P.stiffness == HGPU_STIFFNESS_CONVENTIONAL && !tm.bkt && (s->P.flags & HGPU_FLAG_DENSE_K);
     const int mode = tm.bkt ? 3 : tm.stiff ? (tm.need_u2 ? 1 : 0) : 2;
     // fused launches have no counterpart among the reference's timers; an unfused launch is
     // booked under "Compute addforces e" when it carries the stiffness term, else under damping

@@ -35,6 +35,7 @@ FLAG_TAIL_OVERLAP = 8
 FLAG_WPASS = 16
 FLAG_NO_STRUCT = 32
 FLAG_STRUCT = 64
+FLAG_DENSE_K = 128
 
 
 class HerculesGpuError(RuntimeError):

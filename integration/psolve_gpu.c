@@ -184,6 +184,9 @@ static void gpu_attach(void)
     p.nloaded = Global.theNodesLoaded; p.loaded_lnid = Global.theNodesLoadedList;
     p.device = -1;
     p.flags = HGPU_FLAG_TIMERS;
+    /* stiffness_calculation_method = conventional: the same operator as effective, applied in its factored form
+     * unless the literal dense K1 / K2 products are asked for (include/hercules_gpu.h, HGPU_FLAG_DENSE_K) */
+    if (getenv("PSOLVE_GPU_DENSE_K") && atoi(getenv("PSOLVE_GPU_DENSE_K"))) p.flags |= HGPU_FLAG_DENSE_K;
     GPU(hgpu_init(&theGpu, &m, &p));
     if (Global.theGroupSize > 1) {
         /* every rank's mailbox descriptor to every rank (fixed-size slots: MPI_Allgather) */

@@ -116,6 +116,27 @@ def test_whole_run_matches_reference(hb, name, flags):
     s.close()
 
 
+@pytest.mark.parametrize("flags", [0, 1])
+def test_dense_conventional_kernel_matches_reference(hb, flags):
+    """HGPU_FLAG_DENSE_K: compute_addforce_conventional as the literal dense 24 x 24 K1 / K2 products (the DENSE
+    variant of the step kernel) -- whole run against the reference's conventional-stiffness snapshots, in the
+    loop of test_whole_run_matches_reference.  Without the flag a conventional solver applies the same operator
+    in factored form (test_whole_run_matches_reference[graded2_rayleigh_conv])."""
+    g = load_golden("graded2_rayleigh_conv")
+    s, P = make_solver(hb, g, flags=flags | hb.FLAG_DENSE_K)
+    assert P["stiffness"] == hb.CONVENTIONAL
+    snaps = snapshots(g)
+    F = g["forces"]
+    for k in range(P["steps"]):
+        s.step_begin(k)
+        if k in snaps and np.abs(snaps[k]).max() > 0:
+            assert rel_l2(s.fetch_all(hb.TM1), snaps[k]) < REL_TOL_RUN, k
+        s.compute_force_source(F[k]); s.compute_force_stiffness(); s.compute_force_damping()
+        s.send_force_and_adjust(); s.compute_displacement(); s.send_displacement_and_adjust()
+    assert np.abs(snaps[max(snaps)]).max() > 0
+    s.close()
+
+
 @pytest.mark.parametrize("edata", ["golden", "random"])
 @pytest.mark.parametrize("flags", [0, 1])
 def test_bkt_memory_variables_match_oracle(hb, oracle, flags, edata):
