@@ -485,6 +485,56 @@ int hmesh_corner_sums(int64_t E, const int32_t *lnid, int64_t N, int32_t nw, con
     return 0;
 }
 
+// com_allocpctl's neighbour discovery (octor.c:2639-2742) for a rank: its leaves in Morton order, per leaf 4 x 4 x 4
+// probe points half an edge apart starting half an edge below the lowest corner (z outermost, x innermost), points
+// outside the domain skipped; the rank of a point = the rank of the leaf that holds it.  cand[ncand] = indices (into
+// lcodes, ascending) of the rank's leaves worth probing, key_base[ncand] = their position in the rank's leaf list;
+// gidx[l] = global Morton index of leaf l, rank of a leaf = ((gidx + 1) * world - 1) / etotal (octor.c:738-742).
+// first[world] (caller's, preset to INT64_MAX) receives, per foreign rank, the smallest key position * 64 + probe
+// number at which it was met.
+int hmesh_discovery(const int32_t *dims, int32_t S, const uint64_t *xkeys, int64_t nX, const int64_t *lstart,
+                    const uint64_t *lcodes, const int32_t *lsizes, const int64_t *gidx, int64_t etotal, int32_t world,
+                    int32_t rank, const int64_t *cand, const int64_t *key_base, int64_t ncand, int64_t *first)
+{
+    if (!dims || S <= 0 || (S & (S - 1)) || !xkeys || !lstart || !lcodes || !lsizes || !gidx || !cand || !key_base || !first ||
+        world < 1 || etotal < 1)
+        return -1;
+    XCells X{xkeys, nX, 0, S, {dims[0], dims[1], dims[2]}};
+    while ((1 << X.K) < S) X.K++;
+    uint64_t last_key = ~0ull;
+    int64_t last_j = -1;
+    for (int64_t ci = 0; ci < ncand; ci++) {
+        const int64_t l = cand[ci];
+        int32_t x, y, z;
+        decode3(lcodes[l], x, y, z);
+        const int32_t s = lsizes[l];
+        for (int k = 0; k < 4; k++)
+            for (int j = 0; j < 4; j++)
+                for (int i = 0; i < 4; i++) {
+                    // doubled coordinates: 2 x - s + s i
+                    const int64_t p2[3] = {2 * (int64_t)x - s + (int64_t)s * i, 2 * (int64_t)y - s + (int64_t)s * j,
+                                           2 * (int64_t)z - s + (int64_t)s * k};
+                    if (p2[0] < 0 || p2[0] >= 2 * (int64_t)dims[0] || p2[1] < 0 || p2[1] >= 2 * (int64_t)dims[1] || p2[2] < 0 ||
+                        p2[2] >= 2 * (int64_t)dims[2])
+                        continue;
+                    const int32_t q[3] = {(int32_t)(p2[0] / 2), (int32_t)(p2[1] / 2), (int32_t)(p2[2] / 2)};
+                    const uint64_t ck = X.key_of_point(q[0], q[1], q[2]);
+                    if (ck != last_key) { last_key = ck; last_j = X.find(ck); }
+                    if (last_j < 0) return -3;                    // a probe of a rank's leaf lies within X by construction
+                    const uint64_t qc = code3(q[0], q[1], q[2]);
+                    const uint64_t *b = lcodes + lstart[last_j], *e = lcodes + lstart[last_j + 1];
+                    const uint64_t *it = std::upper_bound(b, e, qc);
+                    if (it == b) return -3;
+                    const int64_t h = (int64_t)(it - 1 - lcodes);
+                    const int64_t r = ((gidx[h] + 1) * (int64_t)world - 1) / etotal;
+                    if (r == rank || r < 0 || r >= world) continue;
+                    const int64_t key = key_base[ci] * 64 + (k * 16 + j * 4 + i);
+                    if (key < first[r]) first[r] = key;
+                }
+    }
+    return 0;
+}
+
 void hmesh_free(void *p) { std::free(p); }
 
 int hmesh_abi_version(void) { return 1; }

@@ -310,7 +310,7 @@ def _msglist(nd, peers):
 
 
 def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: int, world: int, dang=None, trash=None,
-                    holder=None, lcode=None):
+                    holder=None, lcode=None, native=None):
     """octree.partition on the leaves of X (the rank's cells and one ring) instead of the whole mesh:
     gidx = global Morton index of every leaf of X (ascending), etotal = leaves of the whole mesh.  Same rules,
     same return values; ranks other than `rank` are only described where they meet nodes `rank` owns."""
@@ -369,7 +369,7 @@ def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: i
     an, dn = nm[anch[nm]], nm[~anch[nm]]
     msg["an_c"] = _msglist(an, owner[H[an]].astype(np.int64))
     msg["dn_c"] = _msglist(dn, owner[H[dn]].astype(np.int64))
-    disc = _discovery_order_local(dims, leaves, lcode, gidx, etotal, a, b, rank, world, harbor, lnid)
+    disc = _discovery_order_local(dims, leaves, lcode, gidx, etotal, a, b, rank, world, harbor, lnid, native)
     pos = {p_: i for i, p_ in enumerate(disc)}
     sh_n, sh_p, sh_k = [], [], []
     own_l = ln[mine]
@@ -395,13 +395,36 @@ def partition_local(dims, leaves, gidx, etotal: int, nodes, lnid, dnode, rank: i
     return (a, b), H, l_lnid, l_dnode, owner[H], share, anch, msg
 
 
-def _discovery_order_local(dims, leaves, lcode, gidx, etotal, a, b, rank, world, harbor, lnid):
+def _discovery_order_local(dims, leaves, lcode, gidx, etotal, a, b, rank, world, harbor, lnid, native=None):
     """octree._discovery_order with the rank of a probe point taken from the global index of the X leaf
-    that holds it (every probe lies within half an edge of one of the rank's leaves: inside X)."""
+    that holds it (every probe lies within half an edge of one of the rank's leaves: inside X).
+    native = (S, xkeys, lstart): the probes run in hmesh_discovery."""
     nx, ny, nz = dims
     ex, ey, ez, es = leaves
     shared_node = np.sum([h for h in harbor.values()], axis=0) > 1
     cand = a + np.nonzero(shared_node[lnid[a:b]].any(1))[0]
+    if native is not None:
+        S, xkeys, lstart = native
+        L = mesh_lib()
+        L.hmesh_discovery.restype = C.c_int
+        L.hmesh_discovery.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        d32 = np.array(dims, np.int32)
+        xkeys = np.ascontiguousarray(xkeys, np.uint64)
+        lstart = np.ascontiguousarray(lstart, np.int64)
+        codes = np.ascontiguousarray(lcode, np.uint64)
+        sizes32 = np.ascontiguousarray(es, np.int32)
+        g64 = np.ascontiguousarray(gidx, np.int64)
+        cand64 = np.ascontiguousarray(cand, np.int64)
+        base = np.ascontiguousarray(cand - a, np.int64)
+        first = np.full(world, np.iinfo(np.int64).max, np.int64)
+        rc = L.hmesh_discovery(d32.ctypes.data, S, xkeys.ctypes.data, xkeys.size, lstart.ctypes.data, codes.ctypes.data,
+                               sizes32.ctypes.data, g64.ctypes.data, etotal, world, rank, cand64.ctypes.data, base.ctypes.data,
+                               cand64.size, first.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"hmesh_discovery failed ({rc})")
+        met = np.nonzero(first != np.iinfo(np.int64).max)[0]
+        return [int(p_) for p_ in met[np.argsort(first[met], kind="stable")]]
     x, y, z, s = ex[cand], ey[cand], ez[cand], es[cand]
     first = {}
     for k in range(4):
@@ -471,10 +494,12 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     start = np.concatenate([[0], np.cumsum(per_cell)])[:-1]
     # global Morton index of every leaf of X: first leaf of its cell in the whole mesh + position inside the cell
     gidx = np.repeat(prefix[X] - start, per_cell) + np.arange(codes.size)
-    dang = trash = holder = None
+    dang = trash = holder = native = None
     if model is not None:
+        lstart = np.concatenate([start, [codes.size]])
         (ex, ey, ez, es), (px, py, pz), lnid, dnode, dang, holder, trash = extract_native(
-            grid, X, codes, sizes, np.concatenate([start, [codes.size]]), chunk, threads)
+            grid, X, codes, sizes, lstart, chunk, threads)
+        native = (S, grid.key[X], lstart)
     else:
         leaves = {int(s): oc._decode(codes[sizes == s]) for s in np.unique(sizes)}
         (ex, ey, ez, es), (px, py, pz), lnid, dnode = oc.extract(leaves, dims)
@@ -497,7 +522,7 @@ def octree_halfspace_local(dims, smax: int, h: float, dt: float, materials, mat_
     mg._distribute(nT, dnode)
     (a, b), H, l_lnid, l_dnode, owner, share, anch, msg = partition_local(dims, (ex, ey, ez, es), gidx, etotal,
                                                                           (px, py, pz), lnid, dnode, rank, world,
-                                                                          dang, trash, holder, codes)
+                                                                          dang, trash, holder, codes, native)
     edata = np.zeros((b - a, 14), np.float32)
     edata[:, 0], edata[:, 1], edata[:, 2], edata[:, 3] = pr["edge"][a:b], pr["Vp"][a:b], pr["Vs"][a:b], pr["rho"][a:b]
     if damping == BKT:

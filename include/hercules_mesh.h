@@ -67,6 +67,16 @@ int hmesh_lnid(const int32_t *dims, int32_t S, const uint64_t *xkeys, int64_t nX
  * column), so both give the same doubles.  nw weight arrays of E doubles, nw output arrays of N doubles. */
 int hmesh_corner_sums(int64_t E, const int32_t *lnid, int64_t N, int32_t nw, const double *const *w, double *const *out);
 
+/* com_allocpctl's neighbour discovery order (octor.c:2639-2742), which fixes the order of the sharers in a node's
+ * share list and with it the messenger order of the schedules: for the rank's leaves cand[ncand] (indices into
+ * lcodes, ascending; key_base = their position in the rank's leaf list) 4 x 4 x 4 probe points half an edge apart,
+ * starting half an edge below the lowest corner (z outermost, x innermost); first[world] (preset to INT64_MAX by
+ * the caller) = per foreign rank the smallest key_base * 64 + probe number at which one of its leaves was met.
+ * gidx[l] = global Morton index of leaf l of X; rank of a leaf = ((gidx + 1) world - 1) / etotal (octor.c:738-742). */
+int hmesh_discovery(const int32_t *dims, int32_t S, const uint64_t *xkeys, int64_t nX, const int64_t *lstart,
+                    const uint64_t *lcodes, const int32_t *lsizes, const int64_t *gidx, int64_t etotal, int32_t world,
+                    int32_t rank, const int64_t *cand, const int64_t *key_base, int64_t ncand, int64_t *first);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ def test_mesh_header_symbols_exported(hb):
     hdr = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "hercules_mesh.h").read_text(), flags=re.S)
     declared = set(re.findall(r"\b(hmesh_[a-z_0-9]+)\s*\(", hdr))
     assert declared == {"hmesh_abi_version", "hmesh_free", "hmesh_chunk_leaves", "hmesh_chunk_nodes", "hmesh_lnid",
-                        "hmesh_corner_sums"}
+                        "hmesh_corner_sums", "hmesh_discovery"}
     L = ctypes.CDLL(str(ROOT / "hercules_b200" / "libhercules_mesh.so"))
     assert not [n for n in declared if not hasattr(L, n)]
     assert octree_local.mesh_lib().hmesh_abi_version() == 1
