@@ -121,3 +121,76 @@ def test_bench_basin_elements_do_not_straddle_materials(n):
         for b in (0.005, 0.5, 0.995):
             for c in (0.005, 0.5, 0.995):
                 assert np.array_equal(mat_of(ex + a * es, ey + b * es, ez + c * es), centre), (a, b, c)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_native_primitives_equal_the_numpy_restatement_on_random_models(seed):
+    """Random piecewise-constant models (random cells of edge cl, four materials whose Vs make the vs rule ask for
+    every level, so isolated fine octants sit in coarse surroundings and balancing has to ripple): the native
+    refine + balance on random chunks, and the native extraction on the whole domain, against octree.py's numpy
+    restatement (itself pinned on the reference's meshes) -- leaves, node order, lnid, hanging-node table, all exact."""
+    from hercules_b200 import octree as oc, octree_local as ol
+    rng = np.random.default_rng(100 + seed)
+    S = 8
+    dims = tuple(int(S * rng.integers(2, 5)) for _ in range(3))
+    cl = int(rng.choice([1, 2, 4]))
+    g = tuple(-(-n // cl) for n in dims)
+    # stiff cells (leaves of edge 8) mixed with softer ones down to edge 1: the vs rule looks at octant centres only
+    grid_mat = rng.choice(4, size=g, p=[0.55, 0.2, 0.15, 0.1]).astype(np.int64)
+    vs_tab = np.array([8.5, 4.5, 2.5, 1.2])                      # factor_h = 1: an octant of edge s splits while s > Vs
+
+    def mat_of(x, y, z):
+        return grid_mat[np.floor(np.asarray(x) / cl).astype(int), np.floor(np.asarray(y) / cl).astype(int),
+                        np.floor(np.asarray(z) / cl).astype(int)]
+
+    def vs_of(x, y, z):
+        return vs_tab[mat_of(x, y, z)]
+    grid = ol.CoarseGrid(dims, S)
+    model = ol.GridModel(dims, cl, mat_of, vs_tab)
+    assert np.array_equal(model.grid, grid_mat.astype(np.uint8))
+    # random chunks
+    for _ in range(4):
+        sub = np.sort(rng.choice(grid.n, size=int(rng.integers(1, grid.n + 1)), replace=False))
+        a = ol._chunk_leaves(grid, sub, vs_of, 1.0)
+        b = ol._chunk_leaves_native(grid, sub, model, 1.0)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+        assert np.array_equal(ol._chunk_leaves_native(grid, sub, model, 1.0, want_leaves=False)[2], a[2])
+    # the whole domain: the chunked leaves are the whole-domain balanced refinement
+    whole = oc.balance(oc.refine(dims, S, vs_of, 1.0), dims)
+    X = np.arange(grid.n)
+    codes, sizes, per_cell = ol.exact_leaves(grid, X, None, 1.0, chunk=5, threads=2, model=model)
+    wc = np.concatenate([oc._code(*v) for v in whole.values()])
+    ws = np.concatenate([np.full(v[0].size, s, np.int64) for s, v in whole.items()])
+    o = np.argsort(wc)
+    assert np.array_equal(codes, wc[o]) and np.array_equal(sizes, ws[o])
+    assert len(set(sizes.tolist())) >= 3                         # several levels, or the test says nothing
+    # extraction
+    (ex, ey, ez, es), (px, py, pz), lnid, dnode = oc.extract(whole, dims)
+    lstart = np.concatenate([[0], np.cumsum(per_cell)])
+    (nex, ney, nez, nes), (npx, npy, npz), nlnid, ndnode, dang, holder, trash = ol.extract_native(grid, X, codes, sizes, lstart,
+                                                                                               chunk=3, threads=2)
+    assert np.array_equal(np.stack([ex, ey, ez, es]), np.stack([nex, ney, nez, nes]))
+    assert trash == px.size and np.array_equal(np.stack([px, py, pz]), np.stack([npx, npy, npz])[:, :-1])
+    assert np.array_equal(lnid, nlnid) and nlnid.max() < trash   # X is the whole domain: nothing is outside
+    assert dnode.shape == ndnode.shape and np.array_equal(dnode, ndnode) and dnode.shape[0] > 0
+    assert np.array_equal(np.nonzero(dang)[0], dnode[:, 0])
+    # holders: the leaf whose half-open box holds the node (far faces pulled in)
+    q = [np.minimum(p, n - 1) for p, n in zip((px, py, pz), dims)]
+    h = holder[:-1]
+    assert (h >= 0).all()
+    assert all(((c[h] <= qq) & (qq < c[h] + es[h])).all() for c, qq in zip((ex, ey, ez), q))
+
+
+def test_native_primitives_reject_bad_input():
+    from hercules_b200 import octree_local as ol
+    dims = (16, 16, 8)
+    grid = ol.CoarseGrid(dims, 8)
+    model = ol.GridModel(dims, 4, lambda x, y, z: np.zeros(np.shape(x), np.int64), np.array([100.0]))
+    with pytest.raises(RuntimeError, match="hmesh_chunk_leaves failed"):
+        ol._chunk_leaves_native(grid, np.array([1, 0]), model, 1.0)          # cells not in ascending Morton order
+    with pytest.raises(ValueError, match="power of two"):
+        ol.CoarseGrid(dims, 6)
+    with pytest.raises(ValueError, match="power of two"):
+        ol.CoarseGrid((16, 16, 12), 8)                                       # edge does not divide the domain
+    codes, sizes, per_cell = ol.exact_leaves(grid, np.arange(grid.n), None, 1.0, model=model)
+    assert codes.size == grid.n and (sizes == 8).all() and (per_cell == 1).all()      # stiff everywhere: the coarse cells
