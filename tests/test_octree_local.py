@@ -194,3 +194,30 @@ def test_native_primitives_reject_bad_input():
         ol.CoarseGrid((16, 16, 12), 8)                                       # edge does not divide the domain
     codes, sizes, per_cell = ol.exact_leaves(grid, np.arange(grid.n), None, 1.0, model=model)
     assert codes.size == grid.n and (sizes == 8).all() and (per_cell == 1).all()      # stiff everywhere: the coarse cells
+
+
+@pytest.mark.parametrize("seed,world", [(0, 2), (1, 3), (2, 5), (3, 7)])
+def test_local_build_equals_whole_mesh_cut_on_random_models(seed, world):
+    """The one-ring argument under stress: random models with isolated fine octants anywhere, block boundaries
+    wherever the leaf counts put them.  Every rank's tables from its own neighbourhood (native path) must be the
+    cut of the whole mesh: elements, numbering, hanging nodes with anchors on other ranks, ownership, share
+    lists, all four schedules, owned nTable rows."""
+    from hercules_b200 import octree as oc, octree_local as ol
+    rng = np.random.default_rng(500 + seed)
+    dims, cl = (64, 32, 32), 2
+    g = tuple(n // cl for n in dims)
+    grid_mat = rng.choice(4, size=g, p=[0.6, 0.2, 0.12, 0.08]).astype(np.int64)
+    mats = [(3.0 * v, v, 2000.0) for v in (8.5, 4.5, 2.5, 1.2)]             # (Vp, Vs, rho); h * ppw * fmax = 1
+
+    def mat_of(x, y, z):
+        return grid_mat[np.floor(np.asarray(x) / cl).astype(int), np.floor(np.asarray(y) / cl).astype(int),
+                        np.floor(np.asarray(z) / cl).astype(int)]
+    counts = model = None
+    for r in range(world):
+        whole = oc.octree_halfspace_part(dims, 8, 1.0, 1e-3, mats, mat_of, 1.0, 1.0, r, world)
+        mesh, info = ol.octree_halfspace_local(dims, 8, 1.0, 1e-3, mats, mat_of, 1.0, 1.0, r, world, counts=counts,
+                                               model=model, model_cell=cl, chunk=11, threads=2)
+        counts, model = info["counts"], info["model"]
+        assert len(set(info["elem_size"].tolist())) >= 2 and info["D"] > 0
+        assert world == 2 or info["local_region_elements"] < 0.9 * info["etotal"]      # a real subset of the mesh
+        _same_tables(mesh, info, *whole)
