@@ -115,6 +115,12 @@ def mesh_lib() -> C.CDLL:
         L.hmesh_lnid.restype = C.c_int
         L.hmesh_lnid.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                  C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        L.hmesh_corner_sums.restype = C.c_int
+        L.hmesh_corner_sums.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
+        L.hmesh_discovery.restype = C.c_int
+        L.hmesh_discovery.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+        L.hmesh_abi_version.restype, L.hmesh_abi_version.argtypes = C.c_int, []
         L.hmesh_free.restype, L.hmesh_free.argtypes = None, [C.c_void_p]
         _mesh = L
     return _mesh
@@ -239,8 +245,6 @@ def _accumulate_native(nT, lnid, pr, dt, threads: int = 1):
     over the incident (element, corner) pairs -- done by hmesh_corner_sums in the same summation order; the
     dashpot terms (boundary elements only) stay in numpy.  Same doubles as the numpy restatement."""
     L = mesh_lib()
-    L.hmesh_corner_sums.restype = C.c_int
-    L.hmesh_corner_sums.argtypes = [C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]
     E, N = lnid.shape[0], nT.shape[0]
     lnid = np.ascontiguousarray(lnid, np.int32)
     M = np.ascontiguousarray(pr["M"], np.float64)
@@ -406,9 +410,6 @@ def _discovery_order_local(dims, leaves, lcode, gidx, etotal, a, b, rank, world,
     if native is not None:
         S, xkeys, lstart = native
         L = mesh_lib()
-        L.hmesh_discovery.restype = C.c_int
-        L.hmesh_discovery.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         d32 = np.array(dims, np.int32)
         xkeys = np.ascontiguousarray(xkeys, np.uint64)
         lstart = np.ascontiguousarray(lstart, np.int64)
