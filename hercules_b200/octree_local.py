@@ -23,8 +23,14 @@ local work only:
 4. extraction, solver_init's tables and the partition bookkeeping then run on X exactly as
    octree.extract / octree.partition run on the whole mesh, with the global leaf index taken from (1).
 
-tests/test_octree_local.py pins the result against the reference's multi-rank goldens and against the
-whole-mesh cut, table by table.  Chunks of cells are independent, so both passes run on a thread pool.
+The heavy steps have native counterparts in csrc/hmesh.cpp (libhercules_mesh.so, include/hercules_mesh.h): refine +
+balance per chunk, node extraction per chunk, lnid, the per-node mass sums and the neighbour discovery order.  They
+are used when the material model is given on a grid (`model_cell` / `model`); the numpy restatement of every step
+stays here and in octree.py as the checker.  Chunks of cells are independent, so the passes run on a thread pool
+(ctypes drops the GIL).
+
+tests/test_octree_local.py pins the result against the reference's multi-rank goldens and against the whole-mesh
+cut, table by table, on the reference's models and on random ones.
 """
 from __future__ import annotations
 
