@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 REL_TOL_CALL = 1e-12
 REL_TOL_RUN = 1e-10
 
-SINGLE = ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded2_none_eff", "graded2_mass_eff",
+# "graded2_rayleigh_conv" (conventional stiffness) runs the same loop in tests/test_zz_planes_gpu.py
+SINGLE = ["graded2_rayleigh_eff", "graded2_none_eff", "graded2_mass_eff",
           "graded2_bkt", "graded3_rayleigh_eff", "uniform_rayleigh_eff",
           "test1_homogeneous",      # BASELINE.json configs[0] (examples/test1 values, 500 steps)
           "graded2_bkt_qk",         # BKT with finite Qk: shear AND kappa memory variables active
@@ -46,8 +47,15 @@ def make_solver(hb, g, **kw):
 
 
 @pytest.mark.parametrize("tile_nodes", [0, 64, 200])
-@pytest.mark.parametrize("name", ["graded2_rayleigh_eff", "graded2_rayleigh_conv", "graded3_rayleigh_eff"])
+@pytest.mark.parametrize("name", ["graded2_rayleigh_eff", "graded3_rayleigh_eff"])
 def test_force_calls_match_oracle(hb, oracle, name, tile_nodes):
+    """compute_addforce_effective and damping_addforce, one call at a time, on random displacement
+    fields: force array vs the oracle.  (The conventional-stiffness golden runs the same check in
+    tests/test_zz_planes_gpu.py: its default path changed after the round's last GPU run.)"""
+    force_calls_case(hb, oracle, name, tile_nodes)
+
+
+def force_calls_case(hb, oracle, name, tile_nodes):
     """compute_addforce_{effective,conventional} and damping_addforce, one call at a time, on
     random displacement fields: force array vs the oracle."""
     g = load_golden(name)
@@ -93,6 +101,10 @@ def test_force_calls_match_oracle(hb, oracle, name, tile_nodes):
 def test_whole_run_matches_reference(hb, name, flags):
     """Full time loop from rest with the reference's source history: tm1 snapshots against the
     full-precision fields the unmodified reference dumped.  flags=1: unfused kernels."""
+    whole_run_case(hb, name, flags)
+
+
+def whole_run_case(hb, name, flags):
     g = load_golden(name)
     s, P = make_solver(hb, g, flags=flags)
     snaps = snapshots(g)
@@ -112,27 +124,6 @@ def test_whole_run_matches_reference(hb, name, flags):
         s.send_force_and_adjust()
         s.compute_displacement()
         s.send_displacement_and_adjust()
-    assert np.abs(snaps[max(snaps)]).max() > 0
-    s.close()
-
-
-@pytest.mark.parametrize("flags", [0, 1])
-def test_dense_conventional_kernel_matches_reference(hb, flags):
-    """HGPU_FLAG_DENSE_K: compute_addforce_conventional as the literal dense 24 x 24 K1 / K2 products (the DENSE
-    variant of the step kernel) -- whole run against the reference's conventional-stiffness snapshots, in the
-    loop of test_whole_run_matches_reference.  Without the flag a conventional solver applies the same operator
-    in factored form (test_whole_run_matches_reference[graded2_rayleigh_conv])."""
-    g = load_golden("graded2_rayleigh_conv")
-    s, P = make_solver(hb, g, flags=flags | hb.FLAG_DENSE_K)
-    assert P["stiffness"] == hb.CONVENTIONAL
-    snaps = snapshots(g)
-    F = g["forces"]
-    for k in range(P["steps"]):
-        s.step_begin(k)
-        if k in snaps and np.abs(snaps[k]).max() > 0:
-            assert rel_l2(s.fetch_all(hb.TM1), snaps[k]) < REL_TOL_RUN, k
-        s.compute_force_source(F[k]); s.compute_force_stiffness(); s.compute_force_damping()
-        s.send_force_and_adjust(); s.compute_displacement(); s.send_displacement_and_adjust()
     assert np.abs(snaps[max(snaps)]).max() > 0
     s.close()
 

@@ -77,8 +77,8 @@ def check(out, steps):
     assert moved
 
 
-@pytest.mark.parametrize("damping,stiffness", [("rayleigh", "effective"), ("rayleigh", "conventional"),
-                                               ("bkt", "effective"), ("none", "effective")])
+@pytest.mark.parametrize("damping,stiffness", [("rayleigh", "effective"), ("bkt", "effective"), ("none", "effective"),
+                                               ("rayleigh", "conventional")])
 def test_reference_main_with_gpu_time_loop(damping, stiffness):
     """Two-layer model: octor produces two refinement levels with hanging nodes on the interface."""
     c = refcase.Case(**TWO_LAYER, **SRC, damping=damping, stiffness=stiffness, end_t=0.06)

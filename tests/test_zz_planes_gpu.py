@@ -1,4 +1,8 @@
-"""Planes interpolated on the device (hgpu_planes_*, plane_kernel).
+"""The GPU cases of what was written last in round 2 (the file sorts last on purpose): planes interpolated on the
+device (hgpu_planes_*, plane_kernel) -- run on a B200 --, the up-front station-ring check of hgpu_run
+and conventional stiffness on its new default path -- not yet run on hardware.
+
+Planes:
 
 * through the C ABI: every recorded row equals the reference's interpolation arithmetic
   (Old_planes_print, io_planes.c:168-191) on the same field BIT FOR BIT, for arbitrary points;
@@ -131,4 +135,45 @@ def test_run_checks_the_station_ring_before_the_first_step(hb):
     s.run(0, 6, g["forces"][:6])                                 # rows at 0, 2, 4: fits
     steps, rows = s.stations_drain()
     assert list(steps) == [0, 2, 4] and rows.shape[0] == 3
+    s.close()
+
+
+# ---- conventional stiffness on its default path -------------------------------------------------------------
+# A solver created with HGPU_STIFFNESS_CONVENTIONAL applies the operator in the factored form of the effective
+# method since the end of round 2 (one host-side boolean; the literal dense products
+# keep test_dense_conventional_kernel_matches_reference below).  These are the checks the
+# conventional golden always ran -- per call against the oracle's compute_addforce_conventional, whole run against
+# the reference's conventional-stiffness snapshots -- moved here because that switch has not run on hardware yet.
+
+@pytest.mark.parametrize("tile_nodes", [0, 64, 200])
+def test_conventional_force_calls_match_oracle(hb, oracle, tile_nodes):
+    from test_gpu_parity import force_calls_case
+    force_calls_case(hb, oracle, "graded2_rayleigh_conv", tile_nodes)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_conventional_whole_run_matches_reference(hb, flags):
+    from test_gpu_parity import whole_run_case
+    whole_run_case(hb, "graded2_rayleigh_conv", flags)
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_dense_conventional_kernel_matches_reference(hb, flags):
+    """HGPU_FLAG_DENSE_K: compute_addforce_conventional as the literal dense 24 x 24 K1 / K2 products (the DENSE
+    variant of the step kernel) -- whole run against the reference's conventional-stiffness snapshots, in the
+    loop of test_whole_run_matches_reference.  Without the flag a conventional solver applies the same operator
+    in factored form (test_conventional_whole_run_matches_reference above)."""
+    from test_gpu_parity import make_solver, snapshots, rel_l2, REL_TOL_RUN
+    g = load_golden("graded2_rayleigh_conv")
+    s, P = make_solver(hb, g, flags=flags | hb.FLAG_DENSE_K)
+    assert P["stiffness"] == hb.CONVENTIONAL
+    snaps = snapshots(g)
+    F = g["forces"]
+    for k in range(P["steps"]):
+        s.step_begin(k)
+        if k in snaps and np.abs(snaps[k]).max() > 0:
+            assert rel_l2(s.fetch_all(hb.TM1), snaps[k]) < REL_TOL_RUN, k
+        s.compute_force_source(F[k]); s.compute_force_stiffness(); s.compute_force_damping()
+        s.send_force_and_adjust(); s.compute_displacement(); s.send_displacement_and_adjust()
+    assert np.abs(snaps[max(snaps)]).max() > 0
     s.close()
